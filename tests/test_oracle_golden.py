@@ -1,0 +1,132 @@
+"""The oracle (oracle/) against the golden vectors produced by the reference's own numba kernels
+(tests/golden/make_golden.py).  CPU only.  Bar: bit-exact (the oracle restates the same FP64 operations
+in the same order and calls the same libm)."""
+import numpy as np
+import pytest
+
+import oracle
+from oracle import lut as olut
+from oracle import numba_port
+
+
+def same(a, b):
+    """Equal where both finite/inf, NaN positions equal (payload/sign of NaN not compared: SURVEY A.5)."""
+    a, b = np.asarray(a), np.asarray(b)
+    na, nb = np.isnan(a), np.isnan(b)
+    return a.shape == b.shape and np.array_equal(na, nb) and np.array_equal(a[~na], b[~nb])
+
+
+@pytest.mark.parametrize("name", list(oracle.MODEL_IDS))
+def test_gmf_points_bit_exact(golden, name):
+    g = golden("gmf_points")
+    got = oracle.gmf_eval(name, g[name + "/inc"], g[name + "/wspd"], g[name + "/phi"])
+    assert np.array_equal(got, g[name + "/sigma0"])
+    phi = g.get(name + "/lut_phi")
+    lut = oracle.lut_build(name, g[name + "/lut_inc"], g[name + "/lut_wspd"], phi)
+    assert np.array_equal(lut, g[name + "/lut"])
+
+
+def test_known_answers():
+    # value of the reference's own code, and the docstring example of gmfs.py:60-63
+    assert oracle.gmf_scalar("gmf_cmod5n", 35.0, 10.0, 45.0) == 0.05376709128885202
+
+
+def _run(d, co=True, cr=True, **over):
+    kw = {}
+    if co:
+        kw.update(co_lut=d["co_lut_db"], inc_grid=d["inc_grid"], wspd_grid=d["wspd_grid"], phi_grid=d["phi_grid"])
+    if cr:
+        kw.update(cr_lut=d["cr_lut_db"], inc_cr_grid=d["inc_grid"], wspd_cr_grid=d["wspd_cr_grid"])
+    kw.update(over)
+    return kw
+
+
+@pytest.mark.parametrize("case", ["inv_small", "inv_slabs"])
+def test_inversion_dual_bit_exact(golden, case):
+    d = golden(case)
+    co, dual, ic, ix = oracle.invert(d["inc"], d["s0_co_db"], d["s0_cr_db"], d["dsig_cr"], d["anc"], **_run(d))
+    assert same(co, d["out_co"])
+    assert same(dual, d["out_cr"])
+    # indices agree with the returned grid values
+    ok = ic >= 0
+    n_phi = d["phi_grid"].size
+    assert np.array_equal(np.abs(d["out_co"][ok]).round(9), d["wspd_grid"][ic[ok] // n_phi].round(9))
+    okx = ix >= 0
+    assert np.allclose(np.abs(d["out_cr"][okx]), d["wspd_cr_grid"][ix[okx]], rtol=1e-14, atol=0)
+
+
+def test_inversion_mono_variants(golden):
+    d = golden("inv_small")
+    nanr = np.full(d["inc"].shape, np.nan)
+    co, dual, _, _ = oracle.invert(d["inc"], d["s0_co_db"], nanr, 0.1, d["anc"], **_run(d, cr=False))
+    assert same(co, d["co_only"]) and same(dual, d["co_only_cr"])
+    co, dual, _, _ = oracle.invert(d["inc"], nanr, d["s0_cr_db"], d["dsig_cr"], nanr + 0j, **_run(d, co=False))
+    assert same(co, d["cr_only_co"]) and same(dual, d["cr_only"])
+
+
+def test_inversion_nan_lut_and_unmirrored_phi(golden):
+    d = golden("inv_ifr2")
+    nanr = np.full(d["inc"].shape, np.nan)
+    assert np.isnan(d["co_lut_db"]).any()
+    co, dual, ic, _ = oracle.invert(d["inc"], d["s0_co_db"], nanr, 0.1, d["anc"], co_lut=d["co_lut_db"],
+                                    inc_grid=d["inc_grid"], wspd_grid=d["wspd_grid"], phi_grid=d["phi_grid"])
+    assert same(co, d["out_co"]) and same(dual, d["out_cr"])
+    assert not oracle.phi_is_180(d["phi_grid2"])
+    co2, _, _, _ = oracle.invert(d["inc"], d["s0_co_db"], nanr, 0.1, d["anc"], co_lut=d["co2_lut_db"],
+                                 inc_grid=d["inc_grid"], wspd_grid=d["wspd_grid"], phi_grid=d["phi_grid2"],
+                                 dsig_co=float(d["dsig_co2"]))
+    assert same(co2, d["out2_co"])
+
+
+def test_numba_port_equals_c_oracle(golden):
+    d = golden("inv_small")
+    n = 500
+    sl = slice(0, n)
+    f = numba_port.make_inverter(d["co_lut_db"], d["inc_grid"], d["wspd_grid"], d["phi_grid"], d["cr_lut_db"],
+                                 d["inc_grid"], d["wspd_cr_grid"], parallel=False)
+    with np.errstate(all="ignore"):
+        co, dual = f(d["inc"][sl], d["s0_co_db"][sl], d["s0_cr_db"][sl], d["dsig_cr"][sl], d["anc"][sl])
+    assert same(co, d["out_co"][sl]) and same(dual, d["out_cr"][sl])
+
+
+def test_interp_matches_scipy_interp1d():
+    from scipy.interpolate import interp1d
+
+    lut, (gi, gw, gp), res, steps = olut.raw_lut("gmf_cmod5n", inc_step_lr=5.0, wspd_step_lr=2.0, phi_step_lr=15.0)
+    ti, tw, tp = olut.grid([16.0, 66.0], 0.5), olut.grid([0.2, 50.0], 0.3), olut.grid([0.0, 180.0], 4.0)
+    want = lut
+    for ax, (xs, xd) in enumerate([(gi, ti), (gw, tw), (gp, tp)]):
+        want = interp1d(xs, want, kind="linear", axis=ax, bounds_error=True)(xd)
+    got = lut
+    for ax, (xs, xd) in enumerate([(gi, ti), (gw, tw), (gp, tp)]):
+        got = oracle.interp_axis(got, ax, xs, xd)
+    assert np.array_equal(got, want)
+    with pytest.raises(ValueError):
+        oracle.interp_axis(lut, 0, gi, np.array([15.0, 20.0]))
+
+
+def test_to_lut_decision_table():
+    # SURVEY appendix A.1
+    lut, (gi, gw, gp) = olut.to_lut("gmf_cmod5n", units="dB", inc_step_lr=5.0, wspd_step_lr=1.0, phi_step_lr=10.0,
+                                    inc_step=1.0, wspd_step=0.5, phi_step=5.0)
+    assert lut.shape == (51, 101, 37)           # low-res evaluated then interpolated to the "high" steps
+    hi, (hi_i, hi_w, hi_p) = olut.to_lut("gmf_cmod5n", units="dB", resolution="high", inc_step=1.0, wspd_step=0.5,
+                                         phi_step=5.0)
+    assert hi.shape == lut.shape and not np.array_equal(hi, lut)   # direct evaluation differs from interpolation
+    assert np.abs(hi - lut).max() < 3.0
+    lo, grids = olut.to_lut("gmf_cmod5n", resolution="low")
+    assert lo.shape == (51, 250, 73)
+    x, gx = olut.to_lut("gmf_s1_v2", units="dB", resolution=None)
+    assert x.shape == (501, 771) and gx[2] is None
+    np.testing.assert_array_equal(gx[1], np.linspace(3.0, 80.0, 771))
+
+
+def test_detrend_oracle():
+    rng = np.random.default_rng(0)
+    s0 = rng.uniform(0.01, 0.2, (7, 33))
+    inc = np.linspace(30, 45, 33)
+    prof = oracle.gmf_eval("gmf_cmod5n", inc, 10.0, 45.0)
+    prof[3] = np.nan
+    want = s0 / (prof / np.nanmean(prof))
+    got = oracle.detrend(s0, prof)
+    np.testing.assert_allclose(got, want, rtol=1e-14, equal_nan=True)
