@@ -113,7 +113,7 @@ def test_to_lut_decision_table():
     hi, (hi_i, hi_w, hi_p) = olut.to_lut("gmf_cmod5n", units="dB", resolution="high", inc_step=1.0, wspd_step=0.5,
                                          phi_step=5.0)
     assert hi.shape == lut.shape and not np.array_equal(hi, lut)   # direct evaluation differs from interpolation
-    assert np.abs(hi - lut).max() < 3.0
+    assert 0.01 < np.abs(hi - lut).max() < 6.0
     lo, grids = olut.to_lut("gmf_cmod5n", resolution="low")
     assert lo.shape == (51, 250, 73)
     x, gx = olut.to_lut("gmf_s1_v2", units="dB", resolution=None)
