@@ -1,0 +1,223 @@
+"""Device-side operators of the hot path: thin Python over the C ABI (xsarsea_b200/_native.py).
+
+Everything here takes/returns torch CUDA tensors (float64 unless stated); the host only computes the small
+grid vectors (np.linspace, np.cos/np.sin of the phi grid) so that they carry numpy's rounding, exactly as
+the reference does.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from . import _native as nat
+
+
+def _t():
+    return nat.torch_cuda()
+
+
+def to_device(a, dtype=None):
+    torch = _t()
+    if isinstance(a, torch.Tensor):
+        t = a.cuda()
+        return t.to(dtype).contiguous() if dtype is not None else t.contiguous()
+    a = np.ascontiguousarray(a)
+    t = torch.from_numpy(a).cuda()
+    return t.to(dtype) if dtype is not None else t
+
+
+def gmf_eval(model_id: int, inc, wspd, phi=None):
+    """Element-wise GMF over already-broadcast device tensors (reference K3, gmfs.py:210-214).
+    inc/wspd float64 or float32 (both the same); phi float64 or None (cross-pol)."""
+    torch = _t()
+    L = nat.load()
+    assert inc.shape == wspd.shape and inc.dtype == wspd.dtype
+    dt = nat.XS_F64 if inc.dtype == torch.float64 else nat.XS_F32
+    inc, wspd = inc.contiguous(), wspd.contiguous()
+    if phi is not None:
+        phi = phi.to(torch.float64).contiguous()
+        assert phi.shape == inc.shape
+    out = torch.empty_like(inc)
+    nat.check(L.xs_gmf_eval(model_id, dt, nat.dptr(inc), nat.dptr(wspd), nat.dptr(phi), nat.dptr(out), inc.numel(),
+                            nat.stream_ptr()), "xs_gmf_eval")
+    return out
+
+
+def lut_build(model_id: int, inc_grid, wspd_grid, phi_grid=None):
+    """Outer-product LUT [n_inc, n_wspd(, n_phi)] float64 on device (reference K2, gmfs.py:218-230)."""
+    torch = _t()
+    L = nat.load()
+    gi, gw = nat.host_f64(inc_grid), nat.host_f64(wspd_grid)
+    gp = None if phi_grid is None else nat.host_f64(phi_grid)
+    shape = (gi.size, gw.size) + (() if gp is None else (gp.size,))
+    out = torch.empty(shape, dtype=torch.float64, device="cuda")
+    nat.check(L.xs_lut_build(model_id, nat.hptr(gi), gi.size, nat.hptr(gw), gw.size, nat.hptr(gp),
+                             0 if gp is None else gp.size, nat.dptr(out), nat.stream_ptr()), "xs_lut_build")
+    return out
+
+
+def lut_interp_axis(lut, axis: int, x_src, x_dst):
+    """scipy interp1d(kind='linear', bounds_error=True) along `axis` on device (reference K5, models.py:167)."""
+    torch = _t()
+    L = nat.load()
+    lut = lut.contiguous()
+    xs, xd = nat.host_f64(x_src), nat.host_f64(x_dst)
+    assert lut.shape[axis] == xs.size
+    outer = int(np.prod(lut.shape[:axis], dtype=np.int64))
+    inner = int(np.prod(lut.shape[axis + 1:], dtype=np.int64))
+    out = torch.empty(tuple(lut.shape[:axis]) + (xd.size,) + tuple(lut.shape[axis + 1:]), dtype=torch.float64,
+                      device="cuda")
+    nat.check(L.xs_lut_interp_axis(nat.dptr(lut), outer, xs.size, inner, nat.hptr(xs), nat.hptr(xd), xd.size,
+                                   nat.dptr(out), nat.stream_ptr()), "xs_lut_interp_axis")
+    return out
+
+
+def lut_to_db(lut):
+    torch = _t()
+    out = torch.empty_like(lut)
+    nat.check(nat.load().xs_lut_to_db(nat.dptr(lut.contiguous()), nat.dptr(out), lut.numel(), nat.stream_ptr()),
+              "xs_lut_to_db")
+    return out
+
+
+def lut_to_linear(lut):
+    torch = _t()
+    out = torch.empty_like(lut)
+    nat.check(nat.load().xs_lut_to_linear(nat.dptr(lut.contiguous()), nat.dptr(out), lut.numel(), nat.stream_ptr()),
+              "xs_lut_to_linear")
+    return out
+
+
+def detrend(sigma0, gmf_line):
+    """out[l, s] = sigma0[l, s] / (gmf_line[s] / nanmean(gmf_line)) (reference detrend.py:63-64)."""
+    torch = _t()
+    sigma0 = sigma0.contiguous()
+    assert sigma0.dim() == 2 and gmf_line.numel() == sigma0.shape[1]
+    dt = nat.XS_F64 if sigma0.dtype == torch.float64 else nat.XS_F32
+    gmf_line = gmf_line.to(torch.float64).contiguous()
+    out = torch.empty_like(sigma0)
+    nat.check(nat.load().xs_detrend(nat.dptr(sigma0), nat.dptr(gmf_line), sigma0.shape[0], sigma0.shape[1], dt,
+                                    nat.dptr(out), nat.stream_ptr()), "xs_detrend")
+    return out
+
+
+class InversionPlan:
+    """Owns an xs_plan: the device LUTs of one (co-pol, cross-pol) model pair plus the scan image.
+
+    co = (lut_db [n_inc, n_wspd, n_phi] device f64, inc_grid, wspd_grid, phi_grid) or None
+    cr = (lut_db [n_inc, n_wspd] device f64, inc_grid, wspd_grid) or None
+    Mirrors the per-call setup of windspeed.py:139-181 (done once here and cached by the caller).
+    """
+
+    def __init__(self, co=None, cr=None, dsig_co=0.1):
+        torch = _t()
+        L = nat.load()
+        self._handle = None
+        d = nat.PlanDesc()
+        keep = []
+        self.co_grids = self.cr_grids = None
+        if co is not None:
+            lut, gi, gw, gp = co
+            lut = lut.to(torch.float64).contiguous()
+            gi, gw, gp = nat.host_f64(gi), nat.host_f64(gw), nat.host_f64(gp)
+            assert tuple(lut.shape) == (gi.size, gw.size, gp.size), (tuple(lut.shape), gi.size, gw.size, gp.size)
+            cphi, sphi = np.cos(np.radians(gp)), np.sin(np.radians(gp))  # windspeed.py:167-168
+            keep += [lut, gi, gw, gp, cphi, sphi]
+            d.co_lut_db_dev = lut.data_ptr()
+            d.inc_grid_host, d.wspd_grid_host, d.phi_grid_host = gi.ctypes.data, gw.ctypes.data, gp.ctypes.data
+            d.cos_phi_host, d.sin_phi_host = cphi.ctypes.data, sphi.ctypes.data
+            d.n_inc, d.n_wspd, d.n_phi = gi.size, gw.size, gp.size
+            self.co_lut = lut
+            self.co_grids = (gi, gw, gp)
+        if cr is not None:
+            lut, gi, gw = cr
+            lut = lut.to(torch.float64).contiguous()
+            gi, gw = nat.host_f64(gi), nat.host_f64(gw)
+            assert tuple(lut.shape) == (gi.size, gw.size)
+            keep += [lut, gi, gw]
+            d.cr_lut_db_dev = lut.data_ptr()
+            d.inc_cr_grid_host, d.wspd_cr_grid_host = gi.ctypes.data, gw.ctypes.data
+            d.n_inc_cr, d.n_wspd_cr = gi.size, gw.size
+            self.cr_lut = lut
+            self.cr_grids = (gi, gw)
+        d.dsig_co = float(dsig_co)
+        self._keep = keep
+        h = ctypes.c_void_p()
+        nat.check(L.xs_plan_create(ctypes.byref(d), nat.stream_ptr(), ctypes.byref(h)), "xs_plan_create")
+        self._handle = h
+        self._workspace = None
+
+    def close(self):
+        if self._handle is not None:
+            nat.load().xs_plan_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def workspace_bytes(self, n_px: int) -> int:
+        return int(nat.load().xs_invert_workspace_bytes(self._handle, int(n_px)))
+
+    def invert(self, inc, sigma0_co=None, sigma0_cr=None, dsig_cr=0.1, ancillary=None, *, sigma0_db=False,
+               merge_dual=False, cr_abs=False, mode=nat.MODE_FAST, want_idx=False, out_co=None, out_cr=None):
+        """Run K1 on device tensors (all the same shape; float64/complex128 or float32/complex64).
+
+        Returns (wind_co complex128 | None, wind_cr complex128 (float64 if cr_abs) | None, idx_co, idx_cr).
+        """
+        torch = _t()
+        L = nat.load()
+        inc = inc.contiguous()
+        shape, n = inc.shape, inc.numel()
+        f32 = inc.dtype == torch.float32
+        rdt, cdt = (torch.float32, torch.complex64) if f32 else (torch.float64, torch.complex128)
+
+        def prep(x, dt):
+            if x is None:
+                return None
+            x = x.contiguous()
+            if x.dtype != dt or x.shape != shape:
+                raise TypeError(f"raster of dtype {x.dtype}/shape {tuple(x.shape)}; expected {dt}/{tuple(shape)}")
+            return x
+
+        s_co, s_cr, anc = prep(sigma0_co, rdt), prep(sigma0_cr, rdt), prep(ancillary, cdt)
+        a = nat.InvertArgs()
+        a.inc, a.sigma0_co, a.sigma0_cr = inc.data_ptr(), nat.dptr(s_co), nat.dptr(s_cr)
+        a.ancillary = nat.dptr(anc)
+        dsig_t = None
+        if hasattr(dsig_cr, "shape") and getattr(dsig_cr, "ndim", 0) > 0:
+            dsig_t = prep(dsig_cr, rdt)
+            a.dsig_cr = dsig_t.data_ptr()
+        else:
+            a.dsig_cr_scalar = float(dsig_cr)
+        a.dtype = nat.XS_F32 if f32 else nat.XS_F64
+        a.flags = (nat.FLAG_SIGMA0_DB if sigma0_db else 0) | (nat.FLAG_MERGE_DUAL if merge_dual else 0) | (
+            nat.FLAG_CR_ABS if cr_abs else 0)
+        a.mode = mode
+        a.n_px = n
+        has_co = self.co_grids is not None and s_co is not None
+        has_cr = self.cr_grids is not None and s_cr is not None
+        if out_co is None and (has_co or has_cr):
+            out_co = torch.empty(shape, dtype=torch.complex128, device="cuda")
+        if out_cr is None:
+            out_cr = torch.empty(shape, dtype=torch.float64 if cr_abs else torch.complex128, device="cuda")
+        a.out_co, a.out_cr = nat.dptr(out_co), nat.dptr(out_cr)
+        idx_co = idx_cr = None
+        if want_idx:
+            idx_co = torch.empty(shape, dtype=torch.int32, device="cuda")
+            idx_cr = torch.empty(shape, dtype=torch.int32, device="cuda")
+            a.idx_co, a.idx_cr = idx_co.data_ptr(), idx_cr.data_ptr()
+        need = self.workspace_bytes(n)
+        if self._workspace is None or self._workspace.numel() < need:
+            self._workspace = torch.empty(need, dtype=torch.uint8, device="cuda")
+        a.workspace, a.workspace_bytes = self._workspace.data_ptr(), self._workspace.numel()
+        nat.check(L.xs_invert(self._handle, ctypes.byref(a), nat.stream_ptr()), "xs_invert")
+        return out_co, out_cr, idx_co, idx_cr
+
+    def last_stats(self):
+        s = (ctypes.c_int64 * 4)()
+        nat.check(nat.load().xs_plan_last_stats(self._handle, s), "xs_plan_last_stats")
+        return dict(scan_pixels=s[0], fp64_chunks=s[1], exhaustive_pixels=s[2], tiles=s[3])

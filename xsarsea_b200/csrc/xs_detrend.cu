@@ -1,0 +1,111 @@
+// K7: sigma0 detrending (reference detrend.py:55-64): out[l][s] = sigma0[l][s] / (gmf[s] / nanmean(gmf)).
+// HBM-bound: one streaming read and one streaming write of the raster; the [W] ratio vector stays in L2.
+#include <math_constants.h>
+
+#include "xs_common.cuh"
+
+namespace xs {
+
+// ratio[s] = gmf[s] / nanmean(gmf); single CTA, FP64 tree reduction
+__global__ void __launch_bounds__(1024) k_detrend_ratio(const double *__restrict__ gmf, int64_t w, double *__restrict__ ratio) {
+    __shared__ double sh_sum[32];
+    __shared__ long long sh_cnt[32];
+    __shared__ double mean_s;
+    double sum = 0.0;
+    long long cnt = 0;
+    for (int64_t i = threadIdx.x; i < w; i += blockDim.x) {
+        const double v = gmf[i];
+        if (!isnan(v)) {
+            sum += v;
+            ++cnt;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        sh_sum[threadIdx.x >> 5] = sum;
+        sh_cnt[threadIdx.x >> 5] = cnt;
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        sum = threadIdx.x < (blockDim.x >> 5) ? sh_sum[threadIdx.x] : 0.0;
+        cnt = threadIdx.x < (blockDim.x >> 5) ? sh_cnt[threadIdx.x] : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        }
+        if (threadIdx.x == 0) mean_s = cnt ? sum / (double)cnt : CUDART_NAN;
+    }
+    __syncthreads();
+    const double mean = mean_s;
+    for (int64_t i = threadIdx.x; i < w; i += blockDim.x) ratio[i] = gmf[i] / mean;
+}
+
+// VEC elements per thread per step (16-byte accesses); W % VEC == 0 on this path
+template <typename T, typename V, int VEC>
+__global__ void __launch_bounds__(256) k_detrend_vec(const V *__restrict__ s0, const double *__restrict__ ratio, int64_t h,
+                                                     int64_t wv, V *__restrict__ out) {
+    const int64_t n = h * wv;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int64_t col = (i % wv) * VEC;
+        V v = __ldcs(&s0[i]);  // streaming: read once
+        T *e = reinterpret_cast<T *>(&v);
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) e[k] = (T)((double)e[k] / ratio[col + k]);
+        __stcs(&out[i], v);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_detrend_scalar(const T *__restrict__ s0, const double *__restrict__ ratio, int64_t h,
+                                                        int64_t w, T *__restrict__ out) {
+    const int64_t n = h * w;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        out[i] = (T)((double)s0[i] / ratio[i % w]);
+}
+
+}  // namespace xs
+
+extern "C" int xs_detrend(const void *sigma0, const double *gmf_line, int64_t n_lines, int64_t n_samples, int dtype,
+                          void *out, void *stream) {
+    using namespace xs;
+    if (!sigma0 || !gmf_line || !out || n_lines < 0 || n_samples <= 0 || (dtype != XS_F64 && dtype != XS_F32)) {
+        set_error("xs_detrend: invalid argument");
+        return XS_E_INVALID;
+    }
+    if (n_lines == 0) return XS_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    double *ratio = nullptr;
+    XS_CUDA(cudaMallocAsync(&ratio, sizeof(double) * (size_t)n_samples, st));
+    XS_LAUNCH(k_detrend_ratio, 1, 1024, 0, stream, gmf_line, n_samples, ratio);
+    const int64_t n = n_lines * n_samples;
+    const bool aligned = (((uintptr_t)sigma0 | (uintptr_t)out) & 15) == 0;
+    auto grid_for = [](int64_t items) {
+        int64_t g = ceil_div(items, 256);
+        const int64_t cap = (int64_t)kNumSMs * 32;
+        return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+    };
+    if (dtype == XS_F64) {
+        if (aligned && n_samples % 2 == 0)
+            XS_LAUNCH((k_detrend_vec<double, double2, 2>), grid_for(n / 2), 256, 0, stream, (const double2 *)sigma0, ratio,
+                      n_lines, n_samples / 2, (double2 *)out);
+        else
+            XS_LAUNCH(k_detrend_scalar<double>, grid_for(n), 256, 0, stream, (const double *)sigma0, ratio, n_lines, n_samples,
+                      (double *)out);
+    } else {
+        if (aligned && n_samples % 4 == 0)
+            XS_LAUNCH((k_detrend_vec<float, float4, 4>), grid_for(n / 4), 256, 0, stream, (const float4 *)sigma0, ratio,
+                      n_lines, n_samples / 4, (float4 *)out);
+        else
+            XS_LAUNCH(k_detrend_scalar<float>, grid_for(n), 256, 0, stream, (const float *)sigma0, ratio, n_lines, n_samples,
+                      (float *)out);
+    }
+    XS_CUDA(cudaFreeAsync(ratio, st));
+    return XS_OK;
+}

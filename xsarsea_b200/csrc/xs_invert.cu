@@ -1,0 +1,888 @@
+// K1: wind inversion (reference windspeed/windspeed.py:132-331) for B200 / sm_100a.
+//
+// Per pixel the reference evaluates a cost J over the whole wspd x phi grid of the LUT slab of the pixel's
+// incidence bin and takes np.argmin (windspeed.py:212-232).  J is a squared distance in 3-D:
+//     J(w,phi) = ((w cos phi - a)/2)^2 + ((w sin phi - b)/2)^2 + ((L[inc][w][phi] - s)/dsig_co)^2
+// Dropping the per-pixel constant (a^2+b^2)/4 leaves
+//     J'(w,phi) = d^2 + t,   d = L/dsig_co - s/dsig_co,   t = w^2/4 - (w/2) g(phi),   g = a cos phi + b sin phi
+// which costs three FP32 FMA-pipe operations per candidate (FADD, FFMA, FFMA) and, with the packed
+// f32x2 forms of sm_100 (FADD2/FFMA2) plus the 3-input FMNMX3, two issue slots per candidate.
+//
+// Pipeline of one xs_invert call (all on the caller's stream, no host synchronisation):
+//   k_bin_count / k_bin_offsets / k_bin_scatter   counting sort of the co-pol pixels by incidence bin
+//   k_scan_co      persistent CTAs; a tile = 64 pixels of one bin; the bin's slab (scan image, FP32) is
+//                  streamed through a 4-stage shared-memory ring by bulk-async (TMA) copies, 8 rows at a
+//                  time; lane l owns the phi pairs {2(l+32j), 2(l+32j)+1}; each warp scans 8 pixels at once
+//                  keeping per lane and pixel the best 8-row chunk and the runner-up chunk minimum;
+//                  then per pixel: warp-shuffle min, FP64 re-evaluation (reference operation order) of every
+//                  chunk whose FP32 minimum lies within the rigorous FP32 error band of the warp minimum,
+//                  warp-shuffle lexicographic (J, index) argmin.  Pixels where one lane holds two chunks inside
+//                  the band go to the exhaustive FP64 kernel.
+//   k_exact_list   exhaustive FP64 scan (warp per pixel) of the few pixels the fast path could not settle
+//   k_cross        cross-pol / dual-pol pass (windspeed.py:252-279), merge (:426-428), NaN classes
+#include <string.h>
+
+#include <cmath>
+
+#include "xs_invert.cuh"
+
+namespace xs {
+
+typedef unsigned long long u64;
+
+// ---- packed FP32 helpers (sm_100 FADD2 / FFMA2 / FMNMX3) -------------------------------------------------
+__device__ __forceinline__ u64 pack2(float x, float y) {
+    u64 d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(x), "f"(y));
+    return d;
+}
+__device__ __forceinline__ void unpack2(u64 v, float &x, float &y) { asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(v)); }
+__device__ __forceinline__ u64 ffma2(u64 a, u64 b, u64 c) {
+    u64 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ u64 fadd2(u64 a, u64 b) {
+    u64 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ float fmin3(float a, float b, float c) {
+    float d;
+    asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+
+// ---- mbarrier / bulk-async copy (TMA) ----------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// ---- workspace layout ----------------------------------------------------------------------------------------
+// counters (u64): [0] n_tiles, [1] fallback count, [2] pixels scanned by k_scan_co, [3] chunks re-evaluated in
+// FP64, [4] tiles skipped through the NaN-slab shortcut
+struct Workspace {
+    u64 *counters;         // [8]
+    unsigned *hist;        // [n_inc]
+    unsigned *bin_start;   // [n_inc + 1]
+    unsigned *cursor;      // [n_inc]
+    unsigned *tile_start;  // [n_inc + 1]
+    unsigned *list;        // [n_px] pixel indices grouped by bin
+    unsigned *fallback;    // [n_px] pixels for k_exact_list
+};
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+static size_t ws_layout(int n_inc, int64_t n_px, char *base, Workspace *w) {
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        char *p = base ? base + off : nullptr;
+        off += align_up(bytes, 256);
+        return p;
+    };
+    char *c = take(8 * sizeof(u64));
+    char *h = take(sizeof(unsigned) * (size_t)(n_inc + 1));
+    char *bs = take(sizeof(unsigned) * (size_t)(n_inc + 1));
+    char *cu = take(sizeof(unsigned) * (size_t)(n_inc + 1));
+    char *ts = take(sizeof(unsigned) * (size_t)(n_inc + 1));
+    char *li = take(sizeof(unsigned) * (size_t)n_px);
+    char *fb = take(sizeof(unsigned) * (size_t)n_px);
+    if (w) {
+        w->counters = (u64 *)c;
+        w->hist = (unsigned *)h;
+        w->bin_start = (unsigned *)bs;
+        w->cursor = (unsigned *)cu;
+        w->tile_start = (unsigned *)ts;
+        w->list = (unsigned *)li;
+        w->fallback = (unsigned *)fb;
+    }
+    return off;
+}
+
+// ---- plan construction kernels -----------------------------------------------------------------------------
+// scan[bin][row][slot] = (float)(L/dsig_co), +inf in the padding; per-slab first NaN and max finite magnitude
+__global__ void k_build_scan(xs_plan pl) {
+    const int64_t per_slab = (int64_t)pl.n_wspd_pad * pl.nph_pad;
+    const int64_t n = per_slab * pl.n_inc;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int bin = (int)(i / per_slab);
+        const int64_t r = i % per_slab;
+        const int row = (int)(r / pl.nph_pad), slot = (int)(r % pl.nph_pad);
+        float v = CUDART_INF_F;
+        if (row < pl.n_wspd && slot < pl.n_phi) {
+            const double L = pl.co_lut[((int64_t)bin * pl.n_wspd + row) * pl.n_phi + slot];
+            v = (float)(L / pl.dsig_co);
+            if (isnan(L))
+                atomicMin(&pl.first_nan[bin], row * pl.n_phi + slot);
+            else if (!isinf(v))
+                atomicMax(reinterpret_cast<unsigned *>(&pl.slab_absmax[bin]), __float_as_uint(fabsf(v)));
+        }
+        pl.scan[i] = v;
+    }
+}
+__global__ void k_build_rowtab(xs_plan pl) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= pl.n_wspd_pad) return;
+    float2 v = make_float2(0.f, 0.f);
+    if (i < pl.n_wspd) {
+        const double w = pl.wspd_grid[i];
+        v = make_float2((float)(-0.5 * w), (float)(0.25 * w * w));
+    }
+    pl.rowtab[i] = v;
+}
+// plans without a scan image still need the first-NaN table
+__global__ void k_find_first_nan(xs_plan pl) {
+    const int64_t per_slab = (int64_t)pl.n_wspd * pl.n_phi;
+    const int64_t n = per_slab * pl.n_inc;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        if (isnan(pl.co_lut[i])) atomicMin(&pl.first_nan[i / per_slab], (int)(i % per_slab));
+}
+__global__ void k_fix_first_nan(xs_plan pl) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < pl.n_inc && pl.first_nan[i] == 0x7f7f7f7f) pl.first_nan[i] = -1;
+}
+
+// ---- counting sort of the co-pol pixels by incidence bin -----------------------------------------------------
+constexpr int kBinThreads = 256;
+constexpr int kBinPxPerCta = 256 * 32;
+
+__global__ void __launch_bounds__(kBinThreads) k_bin_count(xs_plan pl, RasterArgs a, int64_t n_px, Workspace ws) {
+    extern __shared__ unsigned sh_hist[];
+    for (int b = threadIdx.x; b < pl.n_inc; b += blockDim.x) sh_hist[b] = 0;
+    __syncthreads();
+    const int64_t lo = (int64_t)blockIdx.x * kBinPxPerCta;
+    const int64_t hi = min(lo + (int64_t)kBinPxPerCta, n_px);
+    for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+        int bin;
+        if (pixel_co_bin(pl, a, i, &bin)) atomicAdd(&sh_hist[bin], 1u);
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < pl.n_inc; b += blockDim.x)
+        if (sh_hist[b]) atomicAdd(&ws.hist[b], sh_hist[b]);
+}
+
+// single CTA: exclusive scans of the bin counts (pixels and tiles)
+__global__ void k_bin_offsets(int n_inc, int tile_px, Workspace ws) {
+    __shared__ unsigned carry_px, carry_tiles;
+    __shared__ unsigned sh_px[1024], sh_tl[1024];
+    if (threadIdx.x == 0) carry_px = carry_tiles = 0;
+    __syncthreads();
+    for (int base = 0; base < n_inc; base += blockDim.x) {
+        const int b = base + threadIdx.x;
+        const unsigned cnt = b < n_inc ? ws.hist[b] : 0u;
+        const unsigned tiles = (cnt + tile_px - 1) / tile_px;
+        sh_px[threadIdx.x] = cnt;
+        sh_tl[threadIdx.x] = tiles;
+        __syncthreads();
+        for (int o = 1; o < blockDim.x; o <<= 1) {  // Hillis-Steele inclusive scan
+            unsigned vp = 0, vt = 0;
+            if ((int)threadIdx.x >= o) {
+                vp = sh_px[threadIdx.x - o];
+                vt = sh_tl[threadIdx.x - o];
+            }
+            __syncthreads();
+            sh_px[threadIdx.x] += vp;
+            sh_tl[threadIdx.x] += vt;
+            __syncthreads();
+        }
+        if (b < n_inc) {
+            const unsigned ep = carry_px + sh_px[threadIdx.x] - cnt, et = carry_tiles + sh_tl[threadIdx.x] - tiles;
+            ws.bin_start[b] = ep;
+            ws.cursor[b] = ep;
+            ws.tile_start[b] = et;
+        }
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) {
+            carry_px += sh_px[threadIdx.x];
+            carry_tiles += sh_tl[threadIdx.x];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        ws.bin_start[n_inc] = carry_px;
+        ws.tile_start[n_inc] = carry_tiles;
+        ws.counters[0] = carry_tiles;
+    }
+}
+
+__global__ void __launch_bounds__(kBinThreads) k_bin_scatter(xs_plan pl, RasterArgs a, int64_t n_px, Workspace ws) {
+    extern __shared__ unsigned sh[];  // [n_inc] counts -> bases, [n_inc] local cursors
+    unsigned *sh_base = sh, *sh_cur = sh + pl.n_inc;
+    for (int b = threadIdx.x; b < pl.n_inc; b += blockDim.x) {
+        sh_base[b] = 0;
+        sh_cur[b] = 0;
+    }
+    __syncthreads();
+    const int64_t lo = (int64_t)blockIdx.x * kBinPxPerCta;
+    const int64_t hi = min(lo + (int64_t)kBinPxPerCta, n_px);
+    for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+        int bin;
+        if (pixel_co_bin(pl, a, i, &bin)) atomicAdd(&sh_base[bin], 1u);
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < pl.n_inc; b += blockDim.x)
+        if (sh_base[b]) sh_base[b] = atomicAdd(&ws.cursor[b], sh_base[b]);
+    __syncthreads();
+    for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+        int bin;
+        if (pixel_co_bin(pl, a, i, &bin)) ws.list[sh_base[bin] + atomicAdd(&sh_cur[bin], 1u)] = (unsigned)i;
+    }
+}
+
+// ---- co-pol result of one pixel ----------------------------------------------------------------------------
+// windspeed.py:231-247.  The reference picks +phi or -phi by comparing |angle(anc/sol)| and |angle(anc/sol2)|
+// (ties keep +phi); for phi in [0,180] that is Im(anc) >= 0 ("direction sign").
+__device__ __forceinline__ void write_co(const xs_plan &pl, int idx, double2 anc, int64_t px, double2 *out_co,
+                                         int *idx_co) {
+    const int iw = idx / pl.n_phi, ip = idx - iw * pl.n_phi;
+    const double w = pl.wspd_grid[iw];
+    double re = w * pl.cos_phi[ip], im = w * pl.sin_phi[ip];
+    if (pl.phi_180 && anc.y < 0.0) im = -im;
+    out_co[px] = make_double2(re, im);
+    if (idx_co) idx_co[px] = idx;
+}
+
+// Exhaustive FP64 argmin of one pixel by one warp (reference semantics incl. NaN).  lane <-> phi index.
+__device__ int exact_scan_co(const xs_plan &pl, int bin, double qa, double qb, double s, int lane) {
+    const bool finite_q = isfinite(qa) && isfinite(qb) && isfinite(s);
+    if (finite_q && pl.first_nan[bin] >= 0) return pl.first_nan[bin];  // J is NaN exactly where L is NaN
+    ArgMin am;
+    am.init();
+    const double *slab = pl.co_lut + (int64_t)bin * pl.n_wspd * pl.n_phi;
+    for (int ip = lane; ip < pl.n_phi; ip += 32) {
+        const double c = pl.cos_phi[ip], sn = pl.sin_phi[ip];
+        for (int iw = 0; iw < pl.n_wspd; ++iw) {
+            const double J = exact_cost_co(pl.wspd_grid[iw], c, sn, slab[(int64_t)iw * pl.n_phi + ip], qa, qb, s, pl.dsig_co);
+            am.feed(J, iw * pl.n_phi + ip);
+        }
+    }
+    am.warp_reduce();
+    return am.result();
+}
+
+// MODE_FP64 (list == nullptr: every pixel) and the fallback list of the fast path.
+__global__ void __launch_bounds__(256) k_exact(xs_plan pl, RasterArgs a, int64_t n_px, const unsigned *list,
+                                               const u64 *list_count, double2 *out_co, int *idx_co) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t n = list ? (int64_t)*list_count : n_px;
+    for (int64_t e = warp; e < n; e += n_warps) {
+        const int64_t px = list ? (int64_t)list[e] : e;
+        const Pixel p = load_pixel(pl, a, px);
+        if (!p.co) continue;
+        const int bin = nearest_bin(pl.inc_grid, pl.n_inc, p.inc, pl.inc_sorted);
+        const double qb = pl.phi_180 ? fabs(p.anc.y) : p.anc.y;
+        const int idx = exact_scan_co(pl, bin, p.anc.x, qb, p.s_co, lane);
+        if (lane == 0) write_co(pl, idx, p.anc, px, out_co, idx_co);
+    }
+}
+
+// ---- the FP32 scan --------------------------------------------------------------------------------------------
+struct PixelSlot {  // per-pixel state kept in shared memory during a tile
+    double qa, qb, s;  // m_antenna, m_azi (|.| if phi_180), sigma0 dB
+    double anc_im;
+    unsigned px;
+    int state;  // 0: empty slot, 1: scan, 2: result known (NaN-slab shortcut), 3: exhaustive FP64 needed
+    int idx;
+    int pad;
+};
+
+template <int KP, int P>
+struct ScanSmem {
+    static constexpr int kRowFloats = 64 * KP;
+    static constexpr int kChunkBytes = kChunkRows * kRowFloats * 4;
+    alignas(128) float ring[kStages][kChunkRows * kRowFloats];
+    alignas(16) uint64_t full[kStages];
+    alignas(16) uint64_t empty[kStages];
+    PixelSlot px[kScanWarps * P];
+};
+
+template <int KP, int P>
+__global__ void __launch_bounds__(kScanWarps * 32, (KP <= 3 ? 2 : 1))
+k_scan_co(xs_plan pl, RasterArgs a, Workspace ws, double2 *out_co, int *idx_co) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    using Smem = ScanSmem<KP, P>;
+    Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
+    float2 *rowtab_s = reinterpret_cast<float2 *>(smem_raw + sizeof(Smem));  // [n_wspd_pad]
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int TP = kScanWarps * P;  // pixels per tile
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&sm.full[s], 1);
+            mbar_init(&sm.empty[s], kScanWarps);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = threadIdx.x; i < pl.n_wspd_pad; i += blockDim.x) rowtab_s[i] = pl.rowtab[i];
+    __syncthreads();
+
+    const unsigned n_tiles = (unsigned)ws.counters[0];
+    const int n_chunks = pl.n_wspd_pad / kChunkRows;
+    unsigned it = 0;  // chunks consumed so far by this CTA (ring position, continues across tiles)
+    u64 n_scanned = 0, n_refined = 0;
+
+    for (unsigned tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        // tile -> (bin, pixel range): last bin with tile_start[bin] <= tile
+        int lo = 0, hi = pl.n_inc;
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (ws.tile_start[mid] <= tile)
+                lo = mid;
+            else
+                hi = mid;
+        }
+        const int bin = lo;
+        const unsigned first = ws.bin_start[bin] + (tile - ws.tile_start[bin]) * TP;
+        const unsigned last = min(first + TP, ws.bin_start[bin + 1]);
+        const int nan_idx = pl.first_nan[bin];
+
+        // ---- load the tile's pixels (one thread per pixel) ----
+        __syncthreads();  // previous tile's slots are no longer read
+        if (threadIdx.x < TP) {
+            PixelSlot sl;
+            sl.state = 0;
+            sl.px = 0;
+            sl.idx = -1;
+            sl.qa = sl.qb = sl.s = sl.anc_im = 0.0;
+            sl.pad = 0;
+            const unsigned e = first + threadIdx.x;
+            if (e < last) {
+                const unsigned px = ws.list[e];
+                const Pixel p = load_pixel(pl, a, px);
+                sl.px = px;
+                sl.qa = p.anc.x;
+                sl.anc_im = p.anc.y;
+                sl.qb = pl.phi_180 ? fabs(p.anc.y) : p.anc.y;
+                sl.s = p.s_co;
+                const bool finite_q = isfinite(sl.qa) && isfinite(sl.qb) && isfinite(sl.s);
+                if (!finite_q)
+                    sl.state = 3;
+                else if (nan_idx >= 0) {
+                    sl.state = 2;
+                    sl.idx = nan_idx;
+                } else
+                    sl.state = 1;
+            }
+            sm.px[threadIdx.x] = sl;
+        }
+        __syncthreads();
+
+        if (nan_idx < 0) {
+            // ---- per-lane per-pixel query constants ----
+            u64 g[P][KP];   // {g(phi_even), g(phi_odd)} as packed FP32
+            float nqs[P];   // -s/dsig_co
+#pragma unroll
+            for (int j = 0; j < KP; ++j) {
+                const int ip0 = 2 * (lane + 32 * j);
+                double c0 = 0, s0 = 0, c1 = 0, s1 = 0;
+                if (ip0 < pl.n_phi) {
+                    c0 = pl.cos_phi[ip0];
+                    s0 = pl.sin_phi[ip0];
+                }
+                if (ip0 + 1 < pl.n_phi) {
+                    c1 = pl.cos_phi[ip0 + 1];
+                    s1 = pl.sin_phi[ip0 + 1];
+                }
+#pragma unroll
+                for (int p = 0; p < P; ++p) {
+                    const PixelSlot &sl = sm.px[warp * P + p];
+                    const bool on = sl.state == 1;
+                    const float g0 = on ? (float)(sl.qa * c0 + sl.qb * s0) : 0.f;
+                    const float g1 = on ? (float)(sl.qa * c1 + sl.qb * s1) : 0.f;
+                    g[p][j] = pack2(g0, g1);
+                }
+            }
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+                const PixelSlot &sl = sm.px[warp * P + p];
+                nqs[p] = sl.state == 1 ? (float)(-(sl.s / pl.dsig_co)) : 0.f;
+            }
+
+            float best[P], second[P], m[P];
+            int bchunk[P];
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+                best[p] = CUDART_INF_F;
+                second[p] = CUDART_INF_F;
+                m[p] = CUDART_INF_F;
+                bchunk[p] = 0;
+            }
+
+            const float *slab = pl.scan + (int64_t)bin * pl.n_wspd_pad * pl.nph_pad;
+            // ---- producer prologue: fill the ring ----
+            if (threadIdx.x == 0) {
+                const int pre = min(kStages - 1, n_chunks);
+                for (int c = 0; c < pre; ++c) {
+                    const unsigned g_it = it + c;
+                    const int s = g_it % kStages;
+                    if (g_it >= kStages) mbar_wait(&sm.empty[s], ((g_it / kStages) - 1) & 1);
+                    mbar_expect_tx(&sm.full[s], Smem::kChunkBytes);
+                    bulk_g2s(sm.ring[s], slab + (int64_t)c * kChunkRows * Smem::kRowFloats, Smem::kChunkBytes, &sm.full[s]);
+                }
+            }
+            // ---- main loop over 8-row chunks ----
+            for (int c = 0; c < n_chunks; ++c) {
+                const unsigned g_it = it + c;
+                const int s = g_it % kStages;
+                if (threadIdx.x == 0 && c + kStages - 1 < n_chunks) {  // refill the slot consumed last iteration
+                    const unsigned n_it = g_it + kStages - 1;
+                    const int ns = n_it % kStages;
+                    if (n_it >= kStages) mbar_wait(&sm.empty[ns], ((n_it / kStages) - 1) & 1);
+                    mbar_expect_tx(&sm.full[ns], Smem::kChunkBytes);
+                    bulk_g2s(sm.ring[ns], slab + (int64_t)(c + kStages - 1) * kChunkRows * Smem::kRowFloats,
+                             Smem::kChunkBytes, &sm.full[ns]);
+                }
+                __syncwarp();
+                mbar_wait(&sm.full[s], (g_it / kStages) & 1);
+                const u64 *rows = reinterpret_cast<const u64 *>(sm.ring[s]);
+#pragma unroll 2
+                for (int r = 0; r < kChunkRows; ++r) {
+                    const float2 rt = rowtab_s[c * kChunkRows + r];
+                    const u64 nwh = pack2(rt.x, rt.x), w2q = pack2(rt.y, rt.y);
+                    u64 L[KP];
+#pragma unroll
+                    for (int j = 0; j < KP; ++j) L[j] = rows[r * (32 * KP) + lane + 32 * j];
+#pragma unroll
+                    for (int p = 0; p < P; ++p) {
+                        const u64 q2 = pack2(nqs[p], nqs[p]);
+#pragma unroll
+                        for (int j = 0; j < KP; ++j) {
+                            const u64 d = fadd2(L[j], q2);
+                            const u64 t = ffma2(nwh, g[p][j], w2q);
+                            const u64 J = ffma2(d, d, t);
+                            float j0, j1;
+                            unpack2(J, j0, j1);
+                            m[p] = fmin3(m[p], j0, j1);
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sm.empty[s]);
+#pragma unroll
+                for (int p = 0; p < P; ++p) {
+                    const bool lt = m[p] < best[p];
+                    second[p] = fminf(second[p], fmaxf(best[p], m[p]));
+                    best[p] = fminf(best[p], m[p]);
+                    bchunk[p] = lt ? c : bchunk[p];
+                    m[p] = CUDART_INF_F;
+                }
+            }
+            it += n_chunks;
+
+            // ---- settle each pixel: warp-shuffle min, FP64 re-evaluation inside the error band ----
+            const double *slab64 = pl.co_lut + (int64_t)bin * pl.n_wspd * pl.n_phi;
+            const float lmax = pl.slab_absmax[bin];
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+                PixelSlot &sl = sm.px[warp * P + p];
+                if (sl.state != 1) continue;  // warp-uniform
+                float m32 = best[p];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) m32 = fminf(m32, __shfl_xor_sync(0xffffffffu, m32, o));
+                // rigorous bound E on |J'_fp32 - J'_exact| for every candidate that can still win
+                const float A = (float)hypot(sl.qa, sl.qb) * 1.0000002f;
+                const float W = (float)pl.w_absmax * 1.0000002f;
+                const float T = W * A + 0.25f * W * W;
+                const float D = sqrtf(fmaxf(m32, 0.f) + 0.25f * A * A + 1.0f);
+                const float Q = fabsf(nqs[p]);
+                const float E = 5.9604645e-8f * 1.5f * (3.f * T + 2.f * D * (lmax + Q + D) + (fabsf(m32) + 0.25f * A * A + T));
+                const float thr = m32 + 2.f * E;
+                const bool sane = (E < 0.25f) && (m32 < CUDART_INF_F);
+                const bool ambiguous = __any_sync(0xffffffffu, second[p] <= thr);
+                if (!sane || ambiguous) {
+                    if (lane == 0) sl.state = 3;
+                    continue;
+                }
+                unsigned cont = __ballot_sync(0xffffffffu, best[p] <= thr);
+                ArgMin am;
+                am.init();
+                while (cont) {
+                    const int L = __ffs(cont) - 1;
+                    cont &= cont - 1;
+                    const int ch = __shfl_sync(0xffffffffu, bchunk[p], L);
+                    for (int k = lane; k < kChunkRows * 2 * KP; k += 32) {
+                        const int iw = ch * kChunkRows + k / (2 * KP);
+                        const int slot = k % (2 * KP);
+                        const int ip = 2 * (L + 32 * (slot >> 1)) + (slot & 1);
+                        if (iw < pl.n_wspd && ip < pl.n_phi) {
+                            const double J = exact_cost_co(pl.wspd_grid[iw], pl.cos_phi[ip], pl.sin_phi[ip],
+                                                           slab64[(int64_t)iw * pl.n_phi + ip], sl.qa, sl.qb, sl.s, pl.dsig_co);
+                            am.feed(J, iw * pl.n_phi + ip);
+                        }
+                    }
+                    ++n_refined;
+                }
+                am.warp_reduce();
+                if (lane == 0) {
+                    sl.idx = am.result();
+                    sl.state = 2;
+                }
+                ++n_scanned;
+            }
+        }
+        __syncthreads();
+        // ---- write results / queue leftovers ----
+        if (threadIdx.x < TP) {
+            const PixelSlot &sl = sm.px[threadIdx.x];
+            if (sl.state == 2)
+                write_co(pl, sl.idx, make_double2(sl.qa, sl.anc_im), sl.px, out_co, idx_co);
+            else if (sl.state == 3)
+                ws.fallback[atomicAdd(&ws.counters[1], 1ull)] = sl.px;
+        }
+    }
+    if (lane == 0) {
+        if (n_scanned) atomicAdd(&ws.counters[2], n_scanned);
+        if (n_refined) atomicAdd(&ws.counters[3], n_refined);
+    }
+}
+
+// ---- cross-pol / dual-pol pass + NaN classes + merge --------------------------------------------------------
+// windspeed.py:198-207 (NaN classes), :250 (no co-pol), :252-279 (cross-pol argmin), :422-428 (abs / merge).
+// One warp per pixel.
+__global__ void __launch_bounds__(256) k_cross(xs_plan pl, RasterArgs a, int64_t n_px, double2 *out_co, void *out_cr,
+                                               int *idx_co, int *idx_cr) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const double nan = CUDART_NAN;
+    for (int64_t px = warp; px < n_px; px += n_warps) {
+        const Pixel p = load_pixel(pl, a, px);
+        double2 co, dual;
+        int ix = -1;
+        if (p.cls == 0) {
+            co = make_double2(nan, 0.0);
+            dual = make_double2(nan, 0.0);
+        } else {
+            co = p.co ? out_co[px] : make_double2(nan, nan);
+            if (!isnan(p.s_cr) && !isnan(p.dsig_cr) && pl.n_inc_cr > 0) {
+                const int bin = nearest_bin(pl.inc_cr_grid, pl.n_inc_cr, p.inc, pl.inc_cr_sorted);
+                const double *col = pl.cr_lut + (int64_t)bin * pl.n_wspd_cr;
+                const double mag = hypot(co.x, co.y);
+                const bool has_co = !isnan(mag);
+                ArgMin am;
+                am.init();
+                for (int w = lane; w < pl.n_wspd_cr; w += 32) {
+                    const double ts = __ddiv_rn(__dsub_rn(col[w], p.s_cr), p.dsig_cr);
+                    double J = __dmul_rn(ts, ts);
+                    if (has_co) {
+                        const double tw = __dmul_rn(__dsub_rn(pl.wspd_cr_grid[w], mag), 0.5);
+                        J = __dadd_rn(J, __dmul_rn(tw, tw));
+                    }
+                    am.feed(J, w);
+                }
+                am.warp_reduce();
+                ix = am.result();
+                const double wd = pl.wspd_cr_grid[ix];
+                if (has_co && mag > 0.0 && !isinf(mag))
+                    dual = make_double2(wd * (co.x / mag), wd * (co.y / mag));
+                else if (has_co && isinf(mag)) {
+                    const double ang = atan2(co.y, co.x);
+                    dual = make_double2(wd * cos(ang), wd * sin(ang));
+                } else
+                    dual = make_double2(wd, 0.0);  // angle(0) = 0, and phi_dual = 0 without co-pol
+            } else
+                dual = make_double2(nan, nan);
+        }
+        if (lane == 0) {
+            if (!p.co && out_co) {
+                out_co[px] = co;
+                if (idx_co) idx_co[px] = -1;
+            }
+            if (idx_cr) idx_cr[px] = ix;
+            if (out_cr) {
+                double2 o = dual;
+                if (a.flags & XS_FLAG_MERGE_DUAL) {
+                    const double aco = hypot(co.x, co.y), adu = hypot(dual.x, dual.y);
+                    if (aco < 5.0 || adu < 5.0) o = co;
+                }
+                if (a.flags & XS_FLAG_CR_ABS)
+                    reinterpret_cast<double *>(out_cr)[px] = hypot(o.x, o.y);
+                else
+                    reinterpret_cast<double2 *>(out_cr)[px] = o;
+            }
+        }
+    }
+}
+
+template <int KP, int P>
+static int launch_scan(const xs_plan *pl, const RasterArgs &ra, const Workspace &ws, double2 *out_co, int *idx_co,
+                       void *stream) {
+    const size_t smem = sizeof(ScanSmem<KP, P>) + sizeof(float2) * (size_t)pl->n_wspd_pad;
+    static bool configured = false;  // per instantiation
+    if (!configured) {
+        XS_CUDA(cudaFuncSetAttribute(k_scan_co<KP, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        configured = true;
+    }
+    if (smem > 200 * 1024) {
+        set_error("xs_invert: wspd grid too long for the shared-memory row table");
+        return XS_E_UNSUPPORTED;
+    }
+    int per_sm = 1;
+    XS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_scan_co<KP, P>, kScanWarps * 32, smem));
+    if (per_sm < 1) per_sm = 1;
+    int sms = kNumSMs;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, pl->device);
+    XS_LAUNCH((k_scan_co<KP, P>), sms * per_sm, kScanWarps * 32, smem, stream, *pl, ra, ws, out_co, idx_co);
+    return XS_OK;
+}
+
+}  // namespace xs
+
+using namespace xs;
+
+// ---- plan ----------------------------------------------------------------------------------------------------
+static int upload(double **dst, const double *src, int n, cudaStream_t st) {
+    *dst = nullptr;
+    if (n <= 0) return XS_OK;
+    XS_CUDA(cudaMalloc(dst, sizeof(double) * (size_t)n));
+    XS_CUDA(cudaMemcpyAsync(*dst, src, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, st));
+    return XS_OK;
+}
+static bool strictly_ascending(const double *g, int n) {
+    for (int i = 0; i < n; ++i)
+        if (!(g[i] == g[i]) || (i > 0 && !(g[i] > g[i - 1]))) return false;
+    return true;
+}
+
+extern "C" void xs_plan_destroy(xs_plan *pl) {
+    if (!pl) return;
+    cudaFree(pl->inc_grid);
+    cudaFree(pl->wspd_grid);
+    cudaFree(pl->phi_grid);
+    cudaFree(pl->cos_phi);
+    cudaFree(pl->sin_phi);
+    cudaFree(pl->scan);
+    cudaFree(pl->rowtab);
+    cudaFree(pl->first_nan);
+    cudaFree(pl->slab_absmax);
+    cudaFree(pl->inc_cr_grid);
+    cudaFree(pl->wspd_cr_grid);
+    cudaFree(pl->stats);
+    delete pl;
+}
+
+extern "C" int xs_plan_create(const xs_plan_desc *d, void *stream, xs_plan **out) {
+    if (!d || !out) {
+        set_error("xs_plan_create: null argument");
+        return XS_E_INVALID;
+    }
+    *out = nullptr;
+    const bool has_co = d->co_lut_db_dev != nullptr, has_cr = d->cr_lut_db_dev != nullptr;
+    if (!has_co && !has_cr) {
+        set_error("xs_plan_create: neither a co-pol nor a cross-pol model given");
+        return XS_E_INVALID;
+    }
+    if (has_co && (!d->inc_grid_host || !d->wspd_grid_host || !d->phi_grid_host || !d->cos_phi_host || !d->sin_phi_host ||
+                   d->n_inc <= 0 || d->n_wspd <= 0 || d->n_phi <= 0)) {
+        set_error("xs_plan_create: incomplete co-pol model description");
+        return XS_E_INVALID;
+    }
+    if (has_cr && (!d->inc_cr_grid_host || !d->wspd_cr_grid_host || d->n_inc_cr <= 0 || d->n_wspd_cr <= 0)) {
+        set_error("xs_plan_create: incomplete cross-pol model description");
+        return XS_E_INVALID;
+    }
+    if (has_co && (int64_t)d->n_wspd * d->n_phi >= 0x7fffffffLL) {
+        set_error("xs_plan_create: wspd x phi grid too large");
+        return XS_E_UNSUPPORTED;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    xs_plan *pl = new xs_plan();
+    memset(pl, 0, sizeof(*pl));
+    cudaGetDevice(&pl->device);
+    int rc = XS_OK;
+    auto fail = [&](int code) {
+        xs_plan_destroy(pl);
+        return code;
+    };
+    if ((rc = xs::check(cudaMalloc(&pl->stats, 8 * sizeof(unsigned long long)), "cudaMalloc stats")) != XS_OK) return fail(rc);
+    cudaMemsetAsync(pl->stats, 0, 8 * sizeof(unsigned long long), st);
+    if (has_co) {
+        pl->n_inc = d->n_inc;
+        pl->n_wspd = d->n_wspd;
+        pl->n_phi = d->n_phi;
+        pl->dsig_co = d->dsig_co;
+        pl->co_lut = d->co_lut_db_dev;
+        pl->phi_180 = (180.0 - (d->phi_grid_host[d->n_phi - 1] - d->phi_grid_host[0])) < 2.0;  // windspeed.py:152
+        pl->inc_sorted = strictly_ascending(d->inc_grid_host, d->n_inc);
+        double wmax = 0;
+        for (int i = 0; i < d->n_wspd; ++i) wmax = fmax(wmax, fabs(d->wspd_grid_host[i]));
+        pl->w_absmax = wmax;
+        if ((rc = upload(&pl->inc_grid, d->inc_grid_host, d->n_inc, st)) != XS_OK) return fail(rc);
+        if ((rc = upload(&pl->wspd_grid, d->wspd_grid_host, d->n_wspd, st)) != XS_OK) return fail(rc);
+        if ((rc = upload(&pl->phi_grid, d->phi_grid_host, d->n_phi, st)) != XS_OK) return fail(rc);
+        if ((rc = upload(&pl->cos_phi, d->cos_phi_host, d->n_phi, st)) != XS_OK) return fail(rc);
+        if ((rc = upload(&pl->sin_phi, d->sin_phi_host, d->n_phi, st)) != XS_OK) return fail(rc);
+        if ((rc = xs::check(cudaMalloc(&pl->first_nan, sizeof(int) * (size_t)d->n_inc), "cudaMalloc")) != XS_OK) return fail(rc);
+        // FP32 scan image: only for grids the scan kernel is instantiated for and a sane dsig_co
+        const int kp = (d->n_phi + 63) / 64;
+        const bool kp_ok = kp == 1 || kp == 2 || kp == 3 || kp == 4 || kp == 6;
+        pl->kp = kp;
+        pl->nph_pad = 64 * kp;
+        pl->n_wspd_pad = (d->n_wspd + kChunkRows - 1) / kChunkRows * kChunkRows;
+        pl->fast_ok = kp_ok && std::isfinite(d->dsig_co) && d->dsig_co != 0.0 && std::isfinite(wmax) &&
+                      d->n_inc <= kMaxIncBins && pl->n_wspd_pad <= 16384;
+        if (pl->fast_ok) {
+            const size_t n_scan = (size_t)d->n_inc * pl->n_wspd_pad * pl->nph_pad;
+            if ((rc = xs::check(cudaMalloc(&pl->scan, sizeof(float) * n_scan), "cudaMalloc scan image")) != XS_OK) return fail(rc);
+            if ((rc = xs::check(cudaMalloc(&pl->rowtab, sizeof(float2) * (size_t)pl->n_wspd_pad), "cudaMalloc")) != XS_OK) return fail(rc);
+            if ((rc = xs::check(cudaMalloc(&pl->slab_absmax, sizeof(float) * (size_t)d->n_inc), "cudaMalloc")) != XS_OK) return fail(rc);
+        }
+    }
+    if (has_cr) {
+        pl->n_inc_cr = d->n_inc_cr;
+        pl->n_wspd_cr = d->n_wspd_cr;
+        pl->cr_lut = d->cr_lut_db_dev;
+        pl->inc_cr_sorted = strictly_ascending(d->inc_cr_grid_host, d->n_inc_cr);
+        if ((rc = upload(&pl->inc_cr_grid, d->inc_cr_grid_host, d->n_inc_cr, st)) != XS_OK) return fail(rc);
+        if ((rc = upload(&pl->wspd_cr_grid, d->wspd_cr_grid_host, d->n_wspd_cr, st)) != XS_OK) return fail(rc);
+    }
+    auto build = [&]() -> int {
+        if (!has_co) return XS_OK;
+        XS_CUDA(cudaMemsetAsync(pl->first_nan, 0x7f, sizeof(int) * (size_t)pl->n_inc, st));  // 0x7f7f7f7f > any index
+        if (pl->fast_ok) {
+            XS_CUDA(cudaMemsetAsync(pl->slab_absmax, 0, sizeof(float) * (size_t)pl->n_inc, st));
+            XS_LAUNCH(k_build_scan, kNumSMs * 8, 256, 0, st, *pl);
+            XS_LAUNCH(k_build_rowtab, (int)ceil_div(pl->n_wspd_pad, 256), 256, 0, st, *pl);
+        } else {
+            XS_LAUNCH(k_find_first_nan, kNumSMs * 8, 256, 0, st, *pl);
+        }
+        XS_LAUNCH(k_fix_first_nan, (int)ceil_div(pl->n_inc, 256), 256, 0, st, *pl);
+        return XS_OK;
+    };
+    if ((rc = build()) != XS_OK) return fail(rc);
+    if ((rc = xs::check(cudaStreamSynchronize(st), "xs_plan_create sync")) != XS_OK) return fail(rc);
+    *out = pl;
+    return XS_OK;
+}
+
+extern "C" size_t xs_invert_workspace_bytes(const xs_plan *pl, int64_t n_px) {
+    if (!pl || n_px < 0) return 0;
+    return ws_layout(pl->n_inc, n_px, nullptr, nullptr);
+}
+
+extern "C" int xs_invert(const xs_plan *pl, const xs_invert_args *ar, void *stream) {
+    if (!pl || !ar) {
+        set_error("xs_invert: null argument");
+        return XS_E_INVALID;
+    }
+    const int64_t n = ar->n_px;
+    if (n < 0 || n > 0x7fffffffLL) {
+        set_error("xs_invert: n_px out of range (0 .. 2^31-1)");
+        return XS_E_INVALID;
+    }
+    if (n == 0) return XS_OK;
+    if (!ar->inc || (ar->dtype != XS_F64 && ar->dtype != XS_F32) || (ar->mode != XS_MODE_FAST && ar->mode != XS_MODE_FP64)) {
+        set_error("xs_invert: invalid argument (inc/dtype/mode)");
+        return XS_E_INVALID;
+    }
+    const bool co_run = pl->n_inc > 0 && ar->sigma0_co && ar->ancillary;
+    if (pl->n_inc > 0 && ar->sigma0_co && !ar->out_co) {
+        set_error("xs_invert: out_co is required when a co-pol raster is inverted");
+        return XS_E_INVALID;
+    }
+    if ((ar->flags & XS_FLAG_CR_ABS) && (ar->flags & XS_FLAG_MERGE_DUAL)) {
+        set_error("xs_invert: XS_FLAG_CR_ABS and XS_FLAG_MERGE_DUAL are exclusive");
+        return XS_E_INVALID;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    RasterArgs ra;
+    ra.inc = ar->inc;
+    ra.s_co = pl->n_inc > 0 ? ar->sigma0_co : nullptr;
+    ra.s_cr = pl->n_inc_cr > 0 ? ar->sigma0_cr : nullptr;
+    ra.dsig_cr = ar->dsig_cr;
+    ra.anc = ar->ancillary;
+    ra.dsig_cr_scalar = ar->dsig_cr_scalar;
+    ra.dtype = ar->dtype;
+    ra.flags = ar->flags;
+    double2 *out_co = (double2 *)ar->out_co;
+    int sms = kNumSMs;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, pl->device);
+
+    XS_CUDA(cudaMemsetAsync(pl->stats, 0, 8 * sizeof(unsigned long long), st));
+    if (co_run) {
+        const bool fast = ar->mode == XS_MODE_FAST && pl->fast_ok;
+        if (fast) {
+            const size_t need = ws_layout(pl->n_inc, n, nullptr, nullptr);
+            if (!ar->workspace || ar->workspace_bytes < need) {
+                set_error("xs_invert: workspace too small (%zu < %zu)", ar->workspace_bytes, need);
+                return XS_E_WORKSPACE;
+            }
+            if (((uintptr_t)ar->workspace & 255) != 0) {
+                set_error("xs_invert: workspace must be 256-byte aligned");
+                return XS_E_INVALID;
+            }
+            Workspace ws;
+            ws_layout(pl->n_inc, n, (char *)ar->workspace, &ws);
+            // counters + hist are contiguous at the start of the workspace
+            XS_CUDA(cudaMemsetAsync(ws.counters, 0, (char *)ws.bin_start - (char *)ws.counters, st));
+            const int tile_px = kScanWarps * (pl->kp <= 3 ? 8 : 4);
+            const int bin_grid = (int)ceil_div(n, kBinPxPerCta);
+            XS_LAUNCH(k_bin_count, bin_grid, kBinThreads, sizeof(unsigned) * pl->n_inc, st, *pl, ra, n, ws);
+            XS_LAUNCH(k_bin_offsets, 1, 1024, 0, st, pl->n_inc, tile_px, ws);
+            XS_LAUNCH(k_bin_scatter, bin_grid, kBinThreads, 2 * sizeof(unsigned) * pl->n_inc, st, *pl, ra, n, ws);
+            int rc;
+            switch (pl->kp) {
+                case 1: rc = launch_scan<1, 8>(pl, ra, ws, out_co, ar->idx_co, stream); break;
+                case 2: rc = launch_scan<2, 8>(pl, ra, ws, out_co, ar->idx_co, stream); break;
+                case 3: rc = launch_scan<3, 8>(pl, ra, ws, out_co, ar->idx_co, stream); break;
+                case 4: rc = launch_scan<4, 4>(pl, ra, ws, out_co, ar->idx_co, stream); break;
+                default: rc = launch_scan<6, 4>(pl, ra, ws, out_co, ar->idx_co, stream); break;
+            }
+            if (rc != XS_OK) return rc;
+            XS_LAUNCH(k_exact, sms * 8, 256, 0, st, *pl, ra, n, ws.fallback, ws.counters + 1, out_co, ar->idx_co);
+            XS_CUDA(cudaMemcpyAsync(pl->stats, ws.counters, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
+        } else {
+            XS_LAUNCH(k_exact, sms * 8, 256, 0, st, *pl, ra, n, (const unsigned *)nullptr, (const u64 *)nullptr, out_co,
+                      ar->idx_co);
+        }
+    }
+    {
+        const int64_t warps_needed = n;
+        int64_t grid = ceil_div(warps_needed * 32, 256);
+        const int64_t cap = (int64_t)sms * 16;
+        if (grid > cap) grid = cap;
+        XS_LAUNCH(k_cross, (int)grid, 256, 0, st, *pl, ra, n, out_co, ar->out_cr, ar->idx_co, ar->idx_cr);
+    }
+    return XS_OK;
+}
+
+extern "C" int xs_plan_last_stats(const xs_plan *pl, int64_t stats[4]) {
+    if (!pl || !stats) {
+        set_error("xs_plan_last_stats: null argument");
+        return XS_E_INVALID;
+    }
+    unsigned long long h[8];
+    XS_CUDA(cudaMemcpy(h, pl->stats, sizeof(h), cudaMemcpyDeviceToHost));
+    stats[0] = (int64_t)h[2];  // pixels settled by the FP32 scan
+    stats[1] = (int64_t)h[3];  // chunks re-evaluated in FP64
+    stats[2] = (int64_t)h[1];  // pixels sent to the exhaustive FP64 scan
+    stats[3] = (int64_t)h[0];  // tiles
+    return XS_OK;
+}
