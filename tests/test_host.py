@@ -1,0 +1,221 @@
+"""CPU-only checks: the C-ABI library loads and exports every symbol of include/xsarsea_b200.h, the host-side mirror
+of the reference interface (registry, aliases, labelled-array shim, utils), the loud failure without a GPU, and the
+row sharding + gather on a world_size-2 gloo group."""
+import os
+import re
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from xsarsea_b200 import _native
+
+    _native.build()
+    lib = _native.load()
+    header = open(os.path.join(ROOT, "include", "xsarsea_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(xs_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_native.EXPORTS), declared ^ set(_native.EXPORTS)
+    for sym in declared:
+        assert hasattr(lib, sym), sym
+    assert lib.xs_abi_version() == 1
+    assert lib.xs_launch_count() == 0    # loading the library launches nothing
+
+
+def test_no_cpu_fallback():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from xsarsea_b200 import _native, windspeed
+
+    n = 16
+    with pytest.raises(_native.NativeError, match="CUDA device"):
+        windspeed.invert_from_model(np.full(n, 35.0), np.full(n, 0.05), ancillary_wind=np.full(n, 5 + 5j),
+                                    model="gmf_cmod5n")
+    with pytest.raises(_native.NativeError):
+        windspeed.get_model("gmf_cmod5n").to_lut()
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "xsarsea_b200")
+    for base, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(base, f)).read()
+                assert not re.search(r"^\s*(import|from)\s+oracle\b", src, flags=re.M), f
+                assert "oracle/" not in src and "xs_oracle" not in src, f
+
+
+def test_registry_and_aliases():
+    from xsarsea_b200 import windspeed as ws
+    from xsarsea_b200.windspeed.models import LutModel, Model
+
+    df = ws.available_models()
+    assert list(df.columns) == ["alias", "pol", "model"]
+    for name in ("gmf_cmod5", "gmf_cmod5n", "gmf_cmod5n_pr_zhangA", "gmf_cmod5n_pr_mouche1", "gmf_cmodifr2", "gmf_rs2_v2",
+                 "gmf_s1_v2", "gmf_rcm_noaa", "gmf_s1_v3_ew_rec", "gmf_rs2_v3", "gmf_rcm_v3", "gmf_rcm_v4", "gmf_rs2_v4"):
+        assert name in df.index
+    assert ws.get_model("cmod5n") is ws.get_model("gmf_cmod5n")
+    m = ws.get_model("gmf_cmod5n")
+    assert ws.get_model(m) is m and m.iscopol and m.pol == "VV" and m.phi_range == [0.0, 180.0]
+    assert m.wspd_range == [0.2, 50.0] and m.inc_range == [16.0, 66.0] and m.units == "linear"
+    x = ws.get_model("gmf_rcm_v4")
+    assert x.iscrosspol and x.phi_range is None and x.wspd_range == [3.0, 80.0]
+    assert set(ws.available_models(pol="HH").index) == {"gmf_cmod5n_pr_zhangA", "gmf_cmod5n_pr_mouche1"}
+    with pytest.raises(KeyError, match="not found"):
+        ws.get_model("nope")
+
+    # alias ownership by priority (models.py:477-482): a priority-1 model with the same short name takes the alias
+    # from the GmfModel (priority 3), exactly how Cmod7Model (1) would win over a gmf_cmod7 GmfModel
+    class Fake(LutModel):
+        _name_prefix = "fake_"
+        _priority = 1
+
+    try:
+        f = Fake("fake_cmod5n", pol="VV")
+        df = ws.available_models()
+        assert df.loc["fake_cmod5n", "alias"] == "cmod5n" and df.loc["gmf_cmod5n", "alias"] is None
+        assert ws.get_model("cmod5n") is f and ws.get_model("gmf_cmod5n") is m
+    finally:
+        Model._available_models.pop("fake_cmod5n", None)
+    assert ws.get_model("cmod5n") is m
+
+
+def test_gmf_register_decorator_host_side():
+    from xsarsea_b200 import windspeed as ws
+    from xsarsea_b200.windspeed.models import Model
+
+    with pytest.raises(ValueError, match="must start with"):
+        ws.GmfModel.register(pol="VV")(lambda i, w, p: 1.0)
+
+    try:
+        @ws.GmfModel.register(name="gmf_host360", pol="VV", units="linear", defer=False)
+        def _f(inc, wspd, phi):
+            return 1e-3 * wspd * (2 + np.cos(np.deg2rad(phi)) + 0.3 * np.sin(np.deg2rad(phi)))
+
+        @ws.GmfModel.register(name="gmf_host180", pol="HH", units="linear", defer=False)
+        def _g(inc, wspd, phi):
+            return 1e-3 * wspd * (2 + np.cos(np.deg2rad(phi)))
+
+        @ws.GmfModel.register(name="gmf_hostx", pol="VH", units="linear", defer=True)
+        def _h(inc, wspd, phi=None):
+            return 1e-4 * wspd
+
+        # gmfs.py:146-158 probes phi in [0, 90, 180, 270] and takes the *min* of |f(phi) - f(-phi)|: phi = 0 always gives
+        # 0, so the reference classifies every gmf that uses phi as [0, 180] -- reproduced as is
+        assert ws.get_model("gmf_host360").phi_range == [0.0, 180.0]
+        assert ws.get_model("gmf_host180").phi_range == [0.0, 180.0]
+        assert "gmf_hostx" not in Model._available_models               # deferred
+        ws.GmfModel.activate_gmfs_impl(gmfs_names=["gmf_hostx"])
+        assert ws.get_model("gmf_hostx").phi_range is None and ws.get_model("gmf_hostx").wspd_range == [3.0, 80.0]
+    finally:
+        for n in ("gmf_host360", "gmf_host180", "gmf_hostx"):
+            Model._available_models.pop(n, None)
+        ws.GmfModel._deferred_registrations[:] = [d for d in ws.GmfModel._deferred_registrations if d[1] != "gmf_hostx"]
+
+
+def test_dataarray_lite():
+    from xsarsea_b200._xr import DataArrayLite, is_labelled, like
+
+    a = DataArrayLite(np.arange(24.0).reshape(2, 3, 4), ("incidence", "wspd", "phi"),
+                      dict(incidence=[1, 2], wspd=[1, 2, 3], phi=[0, 1, 2, 3]), dict(units="dB"), "lut")
+    assert is_labelled(a) and a.shape == (2, 3, 4) and np.asarray(a).sum() == 276
+    assert np.array_equal(np.asarray(a.wspd), [1, 2, 3])
+    t = a.transpose("wspd", "phi", "incidence")
+    assert t.dims == ("wspd", "phi", "incidence") and t.shape == (3, 4, 2) and t.values[1, 2, 1] == a.values[1, 1, 2]
+    s = a.isel(incidence=0)
+    assert s.dims == ("wspd", "phi") and "incidence" not in s.coords
+    assert a.isel(phi=[0]).squeeze("phi").dims == ("incidence", "wspd")
+    b = like(a, np.zeros(a.shape), name="z")
+    assert b.dims == a.dims and b.attrs == {} and b.name == "z"
+    assert not is_labelled(np.zeros(3))
+
+
+def test_windspeed_utils():
+    from xsarsea_b200 import windspeed as ws
+
+    rng = np.random.default_rng(0)
+    s, nesz, inc = rng.uniform(1e-4, 1e-2, 50), np.full(50, 10 ** -3.2), rng.uniform(20, 45, 50)
+    np.testing.assert_allclose(ws.get_dsig("nc_lut_cmodms1ahw", inc, s, nesz), (1.25 / (s / nesz)) ** 4.0)
+    np.testing.assert_allclose(ws.get_dsig("gmf_rs2_v2", inc, s, nesz), 1 / np.sqrt((s / nesz) ** 8))
+    c = 1.46852088 + 1.4058646 / (1 + np.exp(-1.57952257 * (inc - 25.61843791)))
+    np.testing.assert_allclose(ws.get_dsig("gmf_s1_v2", inc, s, nesz), 1 / np.sqrt((s / nesz) ** c))
+    with pytest.raises(ValueError):
+        ws.get_dsig("other", inc, s, nesz)
+    a = ws.get_dsig_wspd("dsig_wspd_rs2_v3", np.array([5.0, 20.0, 40.0]), np.array([1.0, 1.0, 1.0]))
+    assert a.shape == (3,) and (a >= 0).all() and (a <= 1).all() and a[2] < 1e-6
+    # nesz_flattening: an exactly log-linear noise profile is reproduced shifted by -1 dB
+    incg = np.broadcast_to(np.linspace(20, 45, 64), (5, 64)).copy()
+    noise = 10 ** ((-30 + 0.2 * incg) / 10)
+    noise[1, 5] = np.nan
+    flat = ws.nesz_flattening(noise, incg)
+    np.testing.assert_allclose(10 * np.log10(flat), -31 + 0.2 * incg, atol=1e-9)
+    with pytest.raises(IndexError):
+        ws.nesz_flattening(noise[0], incg[0])
+
+
+def test_row_shard_partition():
+    from xsarsea_b200.parallel import row_shard
+
+    for n, w in ((16700, 8), (10, 3), (5, 8), (0, 2)):
+        blocks = [row_shard(n, w, r) for r in range(w)]
+        assert blocks[0][0] == 0 and blocks[-1][1] == n
+        assert all(b[1] == c[0] for b, c in zip(blocks, blocks[1:]))
+        sizes = [b[1] - b[0] for b in blocks]
+        assert max(sizes) - min(sizes) <= 1
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+
+    sys.path.insert(0, ROOT)
+    from xsarsea_b200.parallel import invert_sharded, row_shard
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(0)
+        inc = rng.uniform(20, 40, (11, 7))
+        s0, s1 = rng.uniform(0.01, 0.1, (11, 7)), rng.uniform(0.001, 0.01, (11, 7))
+        anc = rng.normal(size=(11, 7)) + 1j * rng.normal(size=(11, 7))
+        seen = {}
+
+        def stub(i, a, b=None, ancillary_wind=None, dsig_cr=0.1, model=None):
+            seen["rows"] = i.shape[0]
+            co = (i + a) * ancillary_wind
+            return (co, co * dsig_cr + b) if b is not None else co
+
+        full = invert_sharded(inc, s0, s1, ancillary_wind=anc, dsig_cr=0.5, model="m", _invert=stub)
+        lo, hi = row_shard(11, world, rank)
+        ok = seen["rows"] == hi - lo
+        want_co = (inc + s0) * anc
+        ok &= np.array_equal(full[0], want_co) and np.array_equal(full[1], want_co * 0.5 + s1)
+        only0 = invert_sharded(inc, s0, ancillary_wind=anc, model="m", gather=0, _invert=stub)
+        ok &= (only0 is None) if rank != 0 else np.array_equal(only0, want_co)
+        mine = invert_sharded(inc, s0, ancillary_wind=anc, model="m", gather=None, _invert=stub)
+        ok &= np.array_equal(mine, want_co[lo:hi])
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_row_sharded_gather_gloo_world2():
+    import torch.multiprocessing as mp
+
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in procs)
+    for p in procs:
+        p.join(60)
+    assert res == [(0, True), (1, True)]

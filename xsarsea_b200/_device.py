@@ -200,7 +200,7 @@ class InversionPlan:
         a.n_px = n
         has_co = self.co_grids is not None and s_co is not None
         has_cr = self.cr_grids is not None and s_cr is not None
-        if out_co is None and (has_co or has_cr):
+        if out_co is None and has_co:
             out_co = torch.empty(shape, dtype=torch.complex128, device="cuda")
         if out_cr is None:
             out_cr = torch.empty(shape, dtype=torch.float64 if cr_abs else torch.complex128, device="cuda")
@@ -216,6 +216,12 @@ class InversionPlan:
         a.workspace, a.workspace_bytes = self._workspace.data_ptr(), self._workspace.numel()
         nat.check(L.xs_invert(self._handle, ctypes.byref(a), nat.stream_ptr()), "xs_invert")
         return out_co, out_cr, idx_co, idx_cr
+
+    def last_scan_ms(self) -> float:
+        """Device time of the last co-pol scan kernel (CUDA events on the launch stream)."""
+        ms = ctypes.c_float()
+        nat.check(nat.load().xs_plan_last_scan_ms(self._handle, ctypes.byref(ms)), "xs_plan_last_scan_ms")
+        return float(ms.value)
 
     def last_stats(self):
         s = (ctypes.c_int64 * 4)()

@@ -20,6 +20,7 @@
 //                  the band go to the exhaustive FP64 kernel.
 //   k_exact_list   exhaustive FP64 scan (warp per pixel) of the few pixels the fast path could not settle
 //   k_cross        cross-pol / dual-pol pass (windspeed.py:252-279), merge (:426-428), NaN classes
+#include <stdlib.h>
 #include <string.h>
 
 #include <cmath>
@@ -312,31 +313,31 @@ struct PixelSlot {  // per-pixel state kept in shared memory during a tile
     int pad;
 };
 
-template <int KP, int P>
+template <int KP, int P, int NW>
 struct ScanSmem {
     static constexpr int kRowFloats = 64 * KP;
     static constexpr int kChunkBytes = kChunkRows * kRowFloats * 4;
     alignas(128) float ring[kStages][kChunkRows * kRowFloats];
     alignas(16) uint64_t full[kStages];
     alignas(16) uint64_t empty[kStages];
-    PixelSlot px[kScanWarps * P];
+    PixelSlot px[NW * P];
 };
 
-template <int KP, int P>
-__global__ void __launch_bounds__(kScanWarps * 32, (KP <= 3 ? 2 : 1))
+template <int KP, int P, int NW, int MB>
+__global__ void __launch_bounds__(NW * 32, MB)
 k_scan_co(xs_plan pl, RasterArgs a, Workspace ws, double2 *out_co, int *idx_co) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    using Smem = ScanSmem<KP, P>;
+    using Smem = ScanSmem<KP, P, NW>;
     Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
     float2 *rowtab_s = reinterpret_cast<float2 *>(smem_raw + sizeof(Smem));  // [n_wspd_pad]
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    constexpr int TP = kScanWarps * P;  // pixels per tile
+    constexpr int TP = NW * P;  // pixels per tile
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) {
             mbar_init(&sm.full[s], 1);
-            mbar_init(&sm.empty[s], kScanWarps);
+            mbar_init(&sm.empty[s], NW);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -631,13 +632,13 @@ __global__ void __launch_bounds__(256) k_cross(xs_plan pl, RasterArgs a, int64_t
     }
 }
 
-template <int KP, int P>
+template <int KP, int P, int NW, int MB>
 static int launch_scan(const xs_plan *pl, const RasterArgs &ra, const Workspace &ws, double2 *out_co, int *idx_co,
                        void *stream) {
-    const size_t smem = sizeof(ScanSmem<KP, P>) + sizeof(float2) * (size_t)pl->n_wspd_pad;
+    const size_t smem = sizeof(ScanSmem<KP, P, NW>) + sizeof(float2) * (size_t)pl->n_wspd_pad;
     static bool configured = false;  // per instantiation
     if (!configured) {
-        XS_CUDA(cudaFuncSetAttribute(k_scan_co<KP, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        XS_CUDA(cudaFuncSetAttribute(k_scan_co<KP, P, NW, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         configured = true;
     }
     if (smem > 200 * 1024) {
@@ -645,12 +646,62 @@ static int launch_scan(const xs_plan *pl, const RasterArgs &ra, const Workspace 
         return XS_E_UNSUPPORTED;
     }
     int per_sm = 1;
-    XS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_scan_co<KP, P>, kScanWarps * 32, smem));
+    XS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_scan_co<KP, P, NW, MB>, NW * 32, smem));
     if (per_sm < 1) per_sm = 1;
     int sms = kNumSMs;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, pl->device);
-    XS_LAUNCH((k_scan_co<KP, P>), sms * per_sm, kScanWarps * 32, smem, stream, *pl, ra, ws, out_co, idx_co);
+    XS_LAUNCH((k_scan_co<KP, P, NW, MB>), sms * per_sm, NW * 32, smem, stream, *pl, ra, ws, out_co, idx_co);
     return XS_OK;
+}
+
+// Scan configuration: pixels per warp P, warps per CTA NW, CTAs per SM MB (register budget = 64K/(NW*32*MB)).
+// XS_SCAN_VARIANT (environment) selects one of the experimental configurations for KP == 3.
+struct ScanConfig {
+    int p, nw;
+};
+static int scan_variant() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("XS_SCAN_VARIANT");
+        v = e ? atoi(e) : 0;
+    }
+    return v;
+}
+static ScanConfig scan_config(int kp) {
+    if (kp >= 4) return {4, 8};
+    if (kp == 3) {
+        switch (scan_variant()) {
+            case 1: return {4, 8};
+            case 2: return {6, 8};
+            case 3: return {8, 12};
+            case 4: return {8, 6};
+            case 5: return {4, 8};
+            case 6: return {6, 6};
+            case 7: return {6, 10};
+            default: return {8, 8};
+        }
+    }
+    return {8, 8};
+}
+static int dispatch_scan(const xs_plan *pl, const RasterArgs &ra, const Workspace &ws, double2 *out_co, int *idx_co,
+                         void *stream) {
+    switch (pl->kp) {
+        case 1: return launch_scan<1, 8, 8, 2>(pl, ra, ws, out_co, idx_co, stream);
+        case 2: return launch_scan<2, 8, 8, 2>(pl, ra, ws, out_co, idx_co, stream);
+        case 3:
+            switch (scan_variant()) {
+                case 1: return launch_scan<3, 4, 8, 2>(pl, ra, ws, out_co, idx_co, stream);
+                case 2: return launch_scan<3, 6, 8, 2>(pl, ra, ws, out_co, idx_co, stream);
+                case 3: return launch_scan<3, 8, 12, 1>(pl, ra, ws, out_co, idx_co, stream);
+                case 4: return launch_scan<3, 8, 6, 2>(pl, ra, ws, out_co, idx_co, stream);
+                case 5: return launch_scan<3, 4, 8, 3>(pl, ra, ws, out_co, idx_co, stream);
+                case 6: return launch_scan<3, 6, 6, 2>(pl, ra, ws, out_co, idx_co, stream);
+                case 7: return launch_scan<3, 6, 10, 1>(pl, ra, ws, out_co, idx_co, stream);
+                default: return launch_scan<3, 8, 8, 2>(pl, ra, ws, out_co, idx_co, stream);
+            }
+        case 4: return launch_scan<4, 4, 8, 1>(pl, ra, ws, out_co, idx_co, stream);
+        default: return launch_scan<6, 4, 8, 1>(pl, ra, ws, out_co, idx_co, stream);
+    }
 }
 
 }  // namespace xs
@@ -685,6 +736,8 @@ extern "C" void xs_plan_destroy(xs_plan *pl) {
     cudaFree(pl->inc_cr_grid);
     cudaFree(pl->wspd_cr_grid);
     cudaFree(pl->stats);
+    if (pl->ev_scan0) cudaEventDestroy(pl->ev_scan0);
+    if (pl->ev_scan1) cudaEventDestroy(pl->ev_scan1);
     delete pl;
 }
 
@@ -723,6 +776,8 @@ extern "C" int xs_plan_create(const xs_plan_desc *d, void *stream, xs_plan **out
     };
     if ((rc = xs::check(cudaMalloc(&pl->stats, 8 * sizeof(unsigned long long)), "cudaMalloc stats")) != XS_OK) return fail(rc);
     cudaMemsetAsync(pl->stats, 0, 8 * sizeof(unsigned long long), st);
+    if ((rc = xs::check(cudaEventCreate(&pl->ev_scan0), "cudaEventCreate")) != XS_OK) return fail(rc);
+    if ((rc = xs::check(cudaEventCreate(&pl->ev_scan1), "cudaEventCreate")) != XS_OK) return fail(rc);
     if (has_co) {
         pl->n_inc = d->n_inc;
         pl->n_wspd = d->n_wspd;
@@ -842,19 +897,17 @@ extern "C" int xs_invert(const xs_plan *pl, const xs_invert_args *ar, void *stre
             ws_layout(pl->n_inc, n, (char *)ar->workspace, &ws);
             // counters + hist are contiguous at the start of the workspace
             XS_CUDA(cudaMemsetAsync(ws.counters, 0, (char *)ws.bin_start - (char *)ws.counters, st));
-            const int tile_px = kScanWarps * (pl->kp <= 3 ? 8 : 4);
+            const ScanConfig sc = scan_config(pl->kp);
+            const int tile_px = sc.nw * sc.p;
             const int bin_grid = (int)ceil_div(n, kBinPxPerCta);
             XS_LAUNCH(k_bin_count, bin_grid, kBinThreads, sizeof(unsigned) * pl->n_inc, st, *pl, ra, n, ws);
             XS_LAUNCH(k_bin_offsets, 1, 1024, 0, st, pl->n_inc, tile_px, ws);
             XS_LAUNCH(k_bin_scatter, bin_grid, kBinThreads, 2 * sizeof(unsigned) * pl->n_inc, st, *pl, ra, n, ws);
-            int rc;
-            switch (pl->kp) {
-                case 1: rc = launch_scan<1, 8>(pl, ra, ws, out_co, ar->idx_co, stream); break;
-                case 2: rc = launch_scan<2, 8>(pl, ra, ws, out_co, ar->idx_co, stream); break;
-                case 3: rc = launch_scan<3, 8>(pl, ra, ws, out_co, ar->idx_co, stream); break;
-                case 4: rc = launch_scan<4, 4>(pl, ra, ws, out_co, ar->idx_co, stream); break;
-                default: rc = launch_scan<6, 4>(pl, ra, ws, out_co, ar->idx_co, stream); break;
-            }
+            xs_plan *mpl = const_cast<xs_plan *>(pl);  // timing events are bookkeeping, not plan state
+            XS_CUDA(cudaEventRecord(mpl->ev_scan0, st));
+            const int rc = dispatch_scan(pl, ra, ws, out_co, ar->idx_co, stream);
+            XS_CUDA(cudaEventRecord(mpl->ev_scan1, st));
+            mpl->scan_timed = 1;
             if (rc != XS_OK) return rc;
             XS_LAUNCH(k_exact, sms * 8, 256, 0, st, *pl, ra, n, ws.fallback, ws.counters + 1, out_co, ar->idx_co);
             XS_CUDA(cudaMemcpyAsync(pl->stats, ws.counters, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
@@ -870,6 +923,16 @@ extern "C" int xs_invert(const xs_plan *pl, const xs_invert_args *ar, void *stre
         if (grid > cap) grid = cap;
         XS_LAUNCH(k_cross, (int)grid, 256, 0, st, *pl, ra, n, out_co, ar->out_cr, ar->idx_co, ar->idx_cr);
     }
+    return XS_OK;
+}
+
+extern "C" int xs_plan_last_scan_ms(const xs_plan *pl, float *ms) {
+    if (!pl || !ms || !pl->scan_timed) {
+        set_error("xs_plan_last_scan_ms: no scan has been launched on this plan");
+        return XS_E_INVALID;
+    }
+    XS_CUDA(cudaEventSynchronize(pl->ev_scan1));
+    XS_CUDA(cudaEventElapsedTime(ms, pl->ev_scan0, pl->ev_scan1));
     return XS_OK;
 }
 

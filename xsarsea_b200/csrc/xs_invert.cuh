@@ -29,6 +29,8 @@ struct xs_plan {
     // ---- counters of the last xs_invert (device) ----
     unsigned long long *stats;  // [8]
     int device;
+    cudaEvent_t ev_scan0, ev_scan1;  // around the last k_scan_co launch
+    int scan_timed;
 };
 
 namespace xs {
@@ -124,11 +126,14 @@ __device__ __forceinline__ Pixel load_pixel(const xs_plan &pl, const RasterArgs 
         const double s = load_real(a.s_co, i, a.dtype);
         p.s_co = db ? s : to_db(s);
     }
+    double s_cr_raw = CUDART_NAN;
     if (a.s_cr) {
-        const double s = load_real(a.s_cr, i, a.dtype);
-        p.s_cr = db ? s : to_db(s);
+        s_cr_raw = load_real(a.s_cr, i, a.dtype);
+        p.s_cr = db ? s_cr_raw : to_db(s_cr_raw);
     }
-    p.dsig_cr = a.dsig_cr ? load_real(a.dsig_cr, i, a.dtype) : a.dsig_cr_scalar;
+    // a scalar dsig_cr is `sigma0_cr * 0 + dsig_cr` in the reference (windspeed.py:122-123): NaN where sigma0_cr is
+    // not finite
+    p.dsig_cr = a.dsig_cr ? load_real(a.dsig_cr, i, a.dtype) : (isfinite(s_cr_raw) ? a.dsig_cr_scalar : CUDART_NAN);
     p.anc = a.anc ? load_cplx(a.anc, i, a.dtype) : make_double2(CUDART_NAN, CUDART_NAN);
     const bool anc_nan = cplx_abs_is_nan(p.anc);
     p.cls = 1;

@@ -1,3 +1,64 @@
-# placeholder, replaced below
-def sigma0_detrend(*a, **k):
-    raise NotImplementedError
+"""sigma0_detrend -- counterpart of xsarsea/detrend.py:9-68.
+
+The GMF profile of the first image line is evaluated on the device (`xs_gmf_eval` for analytic models, LUT
+interpolation for file-backed ones), normalised by its nanmean, and the raster is divided by it in one streaming
+pass (`xs_detrend`, HBM-bound).
+"""
+from __future__ import annotations
+
+import logging
+
+import numpy as np
+
+from . import _device as dev
+from . import _native as nat
+from . import _xr
+from .windspeed.models import get_model
+
+logger = logging.getLogger("xsarsea")
+
+
+def sigma0_detrend(sigma0, inc_angle, wind_speed_gmf=np.array([10.0]), wind_dir_gmf=np.array([45.0]),
+                   model="gmf_cmod5n"):
+    """compute `sigma0_detrend` from `sigma0` and `inc_angle` (detrend.py:9-68).
+
+    sigma0 : linear sigma0, dims (..., line, sample) -- a leading `pol` dim is allowed, every pol gets the same ratio
+    inc_angle : labelled incidence angle (deg) with a `line` dim; only its first line is used (detrend.py:55)
+    wind_speed_gmf, wind_dir_gmf : 0-D or size-1 numpy arrays (m/s, deg relative to antenna)
+    """
+    model = get_model(model)
+    if wind_speed_gmf.ndim > 1 or wind_dir_gmf.ndim > 1:
+        raise ValueError("wind_speed_gmf and wind_dir_gmf must be 0D or 1D")
+    for var in [wind_speed_gmf, wind_dir_gmf]:
+        if var.ndim == 1 and var.size > 1:
+            raise ValueError("wind_speed_gmf and wind_dir_gmf size must be 1 or 0")
+    inc_line = np.asarray(inc_angle.isel(line=0).data, dtype=np.float64).reshape(-1)  # needs a labelled array, like the reference
+    wspd = float(np.asarray(wind_speed_gmf).reshape(-1)[0])
+    phi = float(np.asarray(wind_dir_gmf).reshape(-1)[0])
+    torch = nat.torch_cuda()
+
+    t_inc = dev.to_device(inc_line)
+    if getattr(model, "_device_id", None) is not None:
+        t_w = torch.full_like(t_inc, wspd)
+        t_p = torch.full_like(t_inc, phi) if model.phi_range is not None else None
+        profile = dev.gmf_eval(model._device_id, t_inc, t_w, t_p)
+    else:
+        # LUT-backed or host-defined model: evaluate the profile through the model's own call
+        if model.phi_range is not None:
+            vals = model(inc_line, np.array([wspd]), np.array([phi]))
+        else:
+            vals = model(inc_line, np.array([wspd]))
+        profile = dev.to_device(np.asarray(vals, dtype=np.float64).reshape(-1))
+
+    s0 = np.asarray(sigma0.data if _xr.is_labelled(sigma0) else sigma0)
+    w = inc_line.size
+    if s0.shape[-1] != w:
+        raise ValueError(f"sigma0 sample axis ({s0.shape[-1]}) does not match inc_angle ({w})")
+    f32 = s0.dtype == np.float32
+    t_s0 = dev.to_device(np.ascontiguousarray(s0, dtype=np.float32 if f32 else np.float64).reshape(-1, w))
+    out = dev.detrend(t_s0, profile).cpu().numpy().reshape(s0.shape)
+    if _xr.is_labelled(sigma0):
+        res = _xr.like(sigma0, out, name=getattr(sigma0, "name", None), attrs=dict(getattr(sigma0, "attrs", {})))
+        res.attrs["comment"] = f"detrended with model {model.name}"
+        return res
+    return out
