@@ -25,6 +25,13 @@ def ws():
     return windspeed
 
 
+def reset_steps(m):
+    """`to_lut(**kwargs)` stores its steps on the model (reference behaviour, gmfs.py:367-379); back to the defaults."""
+    for k, v in dict(inc_step=0.1, wspd_step=0.1, phi_step=1.0, inc_step_lr=1.0, wspd_step_lr=0.2, phi_step_lr=2.5).items():
+        setattr(m, k, v)
+    return m
+
+
 def synth(n, seed=0, shape=None):
     rng = np.random.default_rng(seed)
     inc = rng.uniform(17, 49, n)
@@ -241,8 +248,9 @@ def test_config1_full_size_fast_equals_fp64(ws):
     from xsarsea_b200 import _native as nat
     from xsarsea_b200.windspeed import windspeed as impl
 
-    m = ws.get_model("gmf_cmod5n")
+    m = reset_steps(ws.get_model("gmf_cmod5n"))
     plan = impl._get_plan(m, None, 0.1, {})
+    assert plan.co_lut.shape == (501, 499, 181)
     g = torch.Generator(device="cuda").manual_seed(0)
     H = W = 1000
     f64 = dict(device="cuda", dtype=torch.float64)
@@ -267,7 +275,8 @@ def test_full_iw_scene_properties(ws):
     import bench
     from xsarsea_b200.windspeed import windspeed as impl
 
-    plan = impl._get_plan(ws.get_model("gmf_cmod5n"), ws.get_model("gmf_s1_v2"), 0.1, {})
+    plan = impl._get_plan(reset_steps(ws.get_model("gmf_cmod5n")), reset_steps(ws.get_model("gmf_s1_v2")), 0.1, {})
+    assert plan.co_lut.shape == (501, 499, 181) and plan.cr_lut.shape == (501, 771)
     rep, blk = 10, 1670
     inc, s_co, s_cr, anc = bench.synth_scene_device(blk, 25000, 1)
     tile = lambda t: t.repeat(rep, 1)

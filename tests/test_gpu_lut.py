@@ -83,7 +83,11 @@ def test_model_to_lut_matches_oracle_recipe(dev, name, kw):
     from xsarsea_b200 import windspeed
 
     m = windspeed.get_model(name)
-    saved = {k: getattr(m, k) for k in ("inc_step", "wspd_step", "phi_step", "inc_step_lr", "wspd_step_lr", "phi_step_lr")}
+    # `to_lut` stores the steps it is called with on the model, like the reference (gmfs.py:367-379): start from the
+    # registration defaults (models.py:42-48) whatever earlier tests did
+    saved = dict(inc_step=0.1, wspd_step=0.1, phi_step=1.0, inc_step_lr=1.0, wspd_step_lr=0.2, phi_step_lr=2.5)
+    for k, v in saved.items():
+        setattr(m, k, v)
     try:
         lut = m.to_lut(units="dB", **kw)
     finally:

@@ -163,7 +163,8 @@ class InversionPlan:
         return int(nat.load().xs_invert_workspace_bytes(self._handle, int(n_px)))
 
     def invert(self, inc, sigma0_co=None, sigma0_cr=None, dsig_cr=0.1, ancillary=None, *, sigma0_db=False,
-               merge_dual=False, cr_abs=False, mode=nat.MODE_FAST, want_idx=False, out_co=None, out_cr=None):
+               merge_dual=False, cr_abs=False, mode=nat.MODE_FAST, want_idx=False, out_co=None, out_cr=None,
+               need_co=False):
         """Run K1 on device tensors (all the same shape; float64/complex128 or float32/complex64).
 
         Returns (wind_co complex128 | None, wind_cr complex128 (float64 if cr_abs) | None, idx_co, idx_cr).
@@ -200,7 +201,7 @@ class InversionPlan:
         a.n_px = n
         has_co = self.co_grids is not None and s_co is not None
         has_cr = self.cr_grids is not None and s_cr is not None
-        if out_co is None and has_co:
+        if out_co is None and (has_co or need_co):
             out_co = torch.empty(shape, dtype=torch.complex128, device="cuda")
         if out_cr is None:
             out_cr = torch.empty(shape, dtype=torch.float64 if cr_abs else torch.complex128, device="cuda")

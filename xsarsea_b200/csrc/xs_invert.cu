@@ -162,6 +162,15 @@ __global__ void k_find_first_nan(xs_plan pl) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
         if (isnan(pl.co_lut[i])) atomicMin(&pl.first_nan[i / per_slab], (int)(i % per_slab));
 }
+__global__ void k_build_cr_tables(xs_plan pl) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < pl.n_wspd_cr) pl.wspd_cr_half[i] = 0.5 * pl.wspd_cr_grid[i];
+    if (i < pl.n_inc_cr) {
+        int ok = 1;
+        for (int w = 0; w < pl.n_wspd_cr; ++w) ok &= isfinite(pl.cr_lut[(int64_t)i * pl.n_wspd_cr + w]) ? 1 : 0;
+        pl.cr_finite[i] = ok;
+    }
+}
 __global__ void k_fix_first_nan(xs_plan pl) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < pl.n_inc && pl.first_nan[i] == 0x7f7f7f7f) pl.first_nan[i] = -1;
@@ -516,14 +525,31 @@ k_scan_co(xs_plan pl, RasterArgs a, Workspace ws, double2 *out_co, int *idx_co) 
                 const float E = 5.9604645e-8f * 1.5f * (3.f * T + 2.f * D * (lmax + Q + D) + (fabsf(m32) + 0.25f * A * A + T));
                 const float thr = m32 + 2.f * E;
                 const bool sane = (E < 0.25f) && (m32 < CUDART_INF_F);
-                const bool ambiguous = __any_sync(0xffffffffu, second[p] <= thr);
-                if (!sane || ambiguous) {
+                if (!sane) {  // warp-uniform: magnitudes outside the range the error bound was derived for
                     if (lane == 0) sl.state = 3;
                     continue;
                 }
                 unsigned cont = __ballot_sync(0xffffffffu, best[p] <= thr);
+                // lanes holding two or more chunks inside the band: every candidate of the lane is re-evaluated
+                unsigned wide = __ballot_sync(0xffffffffu, second[p] <= thr);
+                cont &= ~wide;
                 ArgMin am;
                 am.init();
+                while (wide) {
+                    const int L = __ffs(wide) - 1;
+                    wide &= wide - 1;
+                    for (int k = lane; k < pl.n_wspd * 2 * KP; k += 32) {
+                        const int iw = k / (2 * KP);
+                        const int slot = k % (2 * KP);
+                        const int ip = 2 * (L + 32 * (slot >> 1)) + (slot & 1);
+                        if (ip < pl.n_phi) {
+                            const double J = exact_cost_co(pl.wspd_grid[iw], pl.cos_phi[ip], pl.sin_phi[ip],
+                                                           slab64[(int64_t)iw * pl.n_phi + ip], sl.qa, sl.qb, sl.s, pl.dsig_co);
+                            am.feed(J, iw * pl.n_phi + ip);
+                        }
+                    }
+                    n_refined += n_chunks;
+                }
                 while (cont) {
                     const int L = __ffs(cont) - 1;
                     cont &= cont - 1;
@@ -564,6 +590,17 @@ k_scan_co(xs_plan pl, RasterArgs a, Workspace ws, double2 *out_co, int *idx_co) 
     }
 }
 
+// The reference's FP64 cross-pol cost of one candidate, operation for operation (windspeed.py:257-264).
+__device__ __forceinline__ double exact_cost_cr(double L, double s, double dsig, double w, double mag, bool has_co) {
+    const double ts = __ddiv_rn(__dsub_rn(L, s), dsig);
+    double J = __dmul_rn(ts, ts);
+    if (has_co) {
+        const double tw = __dmul_rn(__dsub_rn(w, mag), 0.5);
+        J = __dadd_rn(J, __dmul_rn(tw, tw));
+    }
+    return J;
+}
+
 // ---- cross-pol / dual-pol pass + NaN classes + merge --------------------------------------------------------
 // windspeed.py:198-207 (NaN classes), :250 (no co-pol), :252-279 (cross-pol argmin), :422-428 (abs / merge).
 // One warp per pixel.
@@ -589,14 +626,41 @@ __global__ void __launch_bounds__(256) k_cross(xs_plan pl, RasterArgs a, int64_t
                 const bool has_co = !isnan(mag);
                 ArgMin am;
                 am.init();
-                for (int w = lane; w < pl.n_wspd_cr; w += 32) {
-                    const double ts = __ddiv_rn(__dsub_rn(col[w], p.s_cr), p.dsig_cr);
-                    double J = __dmul_rn(ts, ts);
-                    if (has_co) {
-                        const double tw = __dmul_rn(__dsub_rn(pl.wspd_cr_grid[w], mag), 0.5);
-                        J = __dadd_rn(J, __dmul_rn(tw, tw));
+                const bool filter_ok = isfinite(p.s_cr) && isfinite(p.dsig_cr) && p.dsig_cr != 0.0 &&
+                                       (!has_co || isfinite(mag)) && pl.cr_finite[bin];
+                if (filter_ok) {
+                    // Filter pass: J' = ((L-s) * (1/dsig))^2 + (w/2 - mag/2)^2 with FMAs, within a few ulp of the
+                    // reference's J (all terms are non-negative, no cancellation); only candidates inside a 1e-13
+                    // relative band of the minimum are re-evaluated with the reference's exact operation order.
+                    const double r = 1.0 / p.dsig_cr, mag2 = 0.5 * mag;
+                    double best = CUDART_INF, second = CUDART_INF;
+                    int bidx = -1;
+                    for (int w = lane; w < pl.n_wspd_cr; w += 32) {
+                        const double ts = (col[w] - p.s_cr) * r;
+                        double J = ts * ts;
+                        if (has_co) {
+                            const double tw = pl.wspd_cr_half[w] - mag2;
+                            J = fma(tw, tw, J);
+                        }
+                        if (J < best) {
+                            second = best;
+                            best = J;
+                            bidx = w;
+                        } else
+                            second = fmin(second, J);
                     }
-                    am.feed(J, w);
+                    double m = best;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) m = fmin(m, __shfl_xor_sync(0xffffffffu, m, o));
+                    const double thr = m * (1.0 + 1e-13) + 1e-290;
+                    if (second <= thr) {  // several contenders in one lane (exact ties, flat cost): all of the lane's
+                        for (int w = lane; w < pl.n_wspd_cr; w += 32) am.feed(exact_cost_cr(col[w], p.s_cr, p.dsig_cr, pl.wspd_cr_grid[w], mag, has_co), w);
+                    } else if (best <= thr) {
+                        am.feed(exact_cost_cr(col[bidx], p.s_cr, p.dsig_cr, pl.wspd_cr_grid[bidx], mag, has_co), bidx);
+                    }
+                } else {
+                    for (int w = lane; w < pl.n_wspd_cr; w += 32)
+                        am.feed(exact_cost_cr(col[w], p.s_cr, p.dsig_cr, pl.wspd_cr_grid[w], mag, has_co), w);
                 }
                 am.warp_reduce();
                 ix = am.result();
@@ -735,6 +799,8 @@ extern "C" void xs_plan_destroy(xs_plan *pl) {
     cudaFree(pl->slab_absmax);
     cudaFree(pl->inc_cr_grid);
     cudaFree(pl->wspd_cr_grid);
+    cudaFree(pl->wspd_cr_half);
+    cudaFree(pl->cr_finite);
     cudaFree(pl->stats);
     if (pl->ev_scan0) cudaEventDestroy(pl->ev_scan0);
     if (pl->ev_scan1) cudaEventDestroy(pl->ev_scan1);
@@ -817,8 +883,14 @@ extern "C" int xs_plan_create(const xs_plan_desc *d, void *stream, xs_plan **out
         pl->inc_cr_sorted = strictly_ascending(d->inc_cr_grid_host, d->n_inc_cr);
         if ((rc = upload(&pl->inc_cr_grid, d->inc_cr_grid_host, d->n_inc_cr, st)) != XS_OK) return fail(rc);
         if ((rc = upload(&pl->wspd_cr_grid, d->wspd_cr_grid_host, d->n_wspd_cr, st)) != XS_OK) return fail(rc);
+        if ((rc = xs::check(cudaMalloc(&pl->wspd_cr_half, sizeof(double) * (size_t)d->n_wspd_cr), "cudaMalloc")) != XS_OK) return fail(rc);
+        if ((rc = xs::check(cudaMalloc(&pl->cr_finite, sizeof(int) * (size_t)d->n_inc_cr), "cudaMalloc")) != XS_OK) return fail(rc);
     }
     auto build = [&]() -> int {
+        if (has_cr) {
+            const int nmax = pl->n_wspd_cr > pl->n_inc_cr ? pl->n_wspd_cr : pl->n_inc_cr;
+            XS_LAUNCH(k_build_cr_tables, (int)ceil_div(nmax, 128), 128, 0, st, *pl);
+        }
         if (!has_co) return XS_OK;
         XS_CUDA(cudaMemsetAsync(pl->first_nan, 0x7f, sizeof(int) * (size_t)pl->n_inc, st));  // 0x7f7f7f7f > any index
         if (pl->fast_ok) {

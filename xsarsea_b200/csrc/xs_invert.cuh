@@ -25,6 +25,8 @@ struct xs_plan {
     int n_inc_cr, n_wspd_cr;
     const double *cr_lut;  // caller-owned [n_inc_cr][n_wspd_cr] dB
     double *inc_cr_grid, *wspd_cr_grid;
+    double *wspd_cr_half;  // [n_wspd_cr] w/2 (exact), for the filter pass of the cross-pol scan
+    int *cr_finite;        // [n_inc_cr] 1 if every LUT value of the incidence row is finite
     int inc_cr_sorted;
     // ---- counters of the last xs_invert (device) ----
     unsigned long long *stats;  // [8]
