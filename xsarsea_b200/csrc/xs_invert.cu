@@ -603,95 +603,127 @@ __device__ __forceinline__ double exact_cost_cr(double L, double s, double dsig,
 
 // ---- cross-pol / dual-pol pass + NaN classes + merge --------------------------------------------------------
 // windspeed.py:198-207 (NaN classes), :250 (no co-pol), :252-279 (cross-pol argmin), :422-428 (abs / merge).
-// One warp per pixel.
+// A warp takes 32 consecutive pixels: every lane does the per-pixel scalar work of its own pixel (dB prologue,
+// incidence bin, |wind_co|), then the warp scans the wspd grid of one pixel after the other cooperatively
+// (parameters broadcast by shuffle), and finally every lane writes its own pixel (coalesced).
 __global__ void __launch_bounds__(256) k_cross(xs_plan pl, RasterArgs a, int64_t n_px, double2 *out_co, void *out_cr,
                                                int *idx_co, int *idx_cr) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const double nan = CUDART_NAN;
-    for (int64_t px = warp; px < n_px; px += n_warps) {
-        const Pixel p = load_pixel(pl, a, px);
-        double2 co, dual;
-        int ix = -1;
-        if (p.cls == 0) {
-            co = make_double2(nan, 0.0);
-            dual = make_double2(nan, 0.0);
-        } else {
+    const unsigned full = 0xffffffffu;
+    for (int64_t base = warp * 32; base < n_px; base += n_warps * 32) {
+        const int64_t px = base + lane;
+        const bool valid = px < n_px;
+        Pixel p;
+        p.cls = 0;
+        p.co = 0;
+        p.s_cr = p.dsig_cr = p.inc = nan;
+        if (valid) p = load_pixel(pl, a, px);
+        double2 co = make_double2(nan, 0.0), dual = make_double2(nan, 0.0);
+        bool scan = false, has_co = false, filter_ok = false;
+        int bin = 0, ix = -1;
+        double mag = nan;
+        if (valid && p.cls != 0) {
             co = p.co ? out_co[px] : make_double2(nan, nan);
+            dual = make_double2(nan, nan);
             if (!isnan(p.s_cr) && !isnan(p.dsig_cr) && pl.n_inc_cr > 0) {
-                const int bin = nearest_bin(pl.inc_cr_grid, pl.n_inc_cr, p.inc, pl.inc_cr_sorted);
-                const double *col = pl.cr_lut + (int64_t)bin * pl.n_wspd_cr;
-                const double mag = hypot(co.x, co.y);
-                const bool has_co = !isnan(mag);
+                scan = true;
+                bin = nearest_bin(pl.inc_cr_grid, pl.n_inc_cr, p.inc, pl.inc_cr_sorted);
+                mag = hypot(co.x, co.y);
+                has_co = !isnan(mag);
+                filter_ok = isfinite(p.s_cr) && isfinite(p.dsig_cr) && p.dsig_cr != 0.0 && (!has_co || isfinite(mag)) &&
+                            pl.cr_finite[bin];
+            }
+        }
+        unsigned todo = __ballot_sync(full, scan);
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const double s_cr = __shfl_sync(full, p.s_cr, src), dsig = __shfl_sync(full, p.dsig_cr, src);
+            const double mg = __shfl_sync(full, mag, src);
+            const int b = __shfl_sync(full, bin, src);
+            const bool hc = __shfl_sync(full, (int)has_co, src), fok = __shfl_sync(full, (int)filter_ok, src);
+            const double *col = pl.cr_lut + (int64_t)b * pl.n_wspd_cr;
+            int res = -1;
+            bool settled = false;
+            if (fok) {
+                // Filter pass: J' = ((L-s) * (1/dsig))^2 + (w/2 - mag/2)^2 with FMAs, within a few ulp of the
+                // reference's J (all terms are non-negative, no cancellation).  A single candidate inside a 1e-13
+                // relative band of the minimum is the argmin; several are re-evaluated in the reference's order.
+                const double r = 1.0 / dsig, mag2 = 0.5 * mg;
+                double best = CUDART_INF, second = CUDART_INF;
+                int bidx = -1;
+                for (int w = lane; w < pl.n_wspd_cr; w += 32) {
+                    const double ts = (col[w] - s_cr) * r;
+                    double J = ts * ts;
+                    if (hc) {
+                        const double tw = pl.wspd_cr_half[w] - mag2;
+                        J = fma(tw, tw, J);
+                    }
+                    second = fmin(second, fmax(best, J));
+                    if (J < best) {
+                        best = J;
+                        bidx = w;
+                    }
+                }
+                double m = best;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) m = fmin(m, __shfl_xor_sync(full, m, o));
+                const double thr = m * (1.0 + 1e-13) + 1e-290;
+                const unsigned cont = __ballot_sync(full, best <= thr);
+                const unsigned wide = __ballot_sync(full, second <= thr);
+                if (!isfinite(m)) {
+                    // overflowed costs: leave it to the exhaustive pass
+                } else if (wide == 0 && __popc(cont) == 1) {
+                    res = __shfl_sync(full, bidx, __ffs(cont) - 1);
+                    settled = true;
+                } else if (wide == 0 && cont != 0) {
+                    ArgMin am;
+                    am.init();
+                    if (best <= thr) am.feed(exact_cost_cr(col[bidx], s_cr, dsig, pl.wspd_cr_grid[bidx], mg, hc), bidx);
+                    am.warp_reduce();
+                    res = am.result();
+                    settled = true;
+                }
+            }
+            if (!settled) {  // exhaustive, reference order (non-finite inputs, flat or tied costs)
                 ArgMin am;
                 am.init();
-                const bool filter_ok = isfinite(p.s_cr) && isfinite(p.dsig_cr) && p.dsig_cr != 0.0 &&
-                                       (!has_co || isfinite(mag)) && pl.cr_finite[bin];
-                if (filter_ok) {
-                    // Filter pass: J' = ((L-s) * (1/dsig))^2 + (w/2 - mag/2)^2 with FMAs, within a few ulp of the
-                    // reference's J (all terms are non-negative, no cancellation); only candidates inside a 1e-13
-                    // relative band of the minimum are re-evaluated with the reference's exact operation order.
-                    const double r = 1.0 / p.dsig_cr, mag2 = 0.5 * mag;
-                    double best = CUDART_INF, second = CUDART_INF;
-                    int bidx = -1;
-                    for (int w = lane; w < pl.n_wspd_cr; w += 32) {
-                        const double ts = (col[w] - p.s_cr) * r;
-                        double J = ts * ts;
-                        if (has_co) {
-                            const double tw = pl.wspd_cr_half[w] - mag2;
-                            J = fma(tw, tw, J);
-                        }
-                        if (J < best) {
-                            second = best;
-                            best = J;
-                            bidx = w;
-                        } else
-                            second = fmin(second, J);
-                    }
-                    double m = best;
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) m = fmin(m, __shfl_xor_sync(0xffffffffu, m, o));
-                    const double thr = m * (1.0 + 1e-13) + 1e-290;
-                    if (second <= thr) {  // several contenders in one lane (exact ties, flat cost): all of the lane's
-                        for (int w = lane; w < pl.n_wspd_cr; w += 32) am.feed(exact_cost_cr(col[w], p.s_cr, p.dsig_cr, pl.wspd_cr_grid[w], mag, has_co), w);
-                    } else if (best <= thr) {
-                        am.feed(exact_cost_cr(col[bidx], p.s_cr, p.dsig_cr, pl.wspd_cr_grid[bidx], mag, has_co), bidx);
-                    }
-                } else {
-                    for (int w = lane; w < pl.n_wspd_cr; w += 32)
-                        am.feed(exact_cost_cr(col[w], p.s_cr, p.dsig_cr, pl.wspd_cr_grid[w], mag, has_co), w);
-                }
+                for (int w = lane; w < pl.n_wspd_cr; w += 32)
+                    am.feed(exact_cost_cr(col[w], s_cr, dsig, pl.wspd_cr_grid[w], mg, hc), w);
                 am.warp_reduce();
-                ix = am.result();
-                const double wd = pl.wspd_cr_grid[ix];
-                if (has_co && mag > 0.0 && !isinf(mag))
-                    dual = make_double2(wd * (co.x / mag), wd * (co.y / mag));
-                else if (has_co && isinf(mag)) {
-                    const double ang = atan2(co.y, co.x);
-                    dual = make_double2(wd * cos(ang), wd * sin(ang));
-                } else
-                    dual = make_double2(wd, 0.0);  // angle(0) = 0, and phi_dual = 0 without co-pol
-            } else
-                dual = make_double2(nan, nan);
+                res = am.result();
+            }
+            if (lane == src) ix = res;
         }
-        if (lane == 0) {
-            if (!p.co && out_co) {
-                out_co[px] = co;
-                if (idx_co) idx_co[px] = -1;
+        if (!valid) continue;
+        if (scan) {
+            const double wd = pl.wspd_cr_grid[ix];
+            if (has_co && mag > 0.0 && !isinf(mag))
+                dual = make_double2(wd * (co.x / mag), wd * (co.y / mag));
+            else if (has_co && isinf(mag)) {
+                const double ang = atan2(co.y, co.x);
+                dual = make_double2(wd * cos(ang), wd * sin(ang));
+            } else
+                dual = make_double2(wd, 0.0);  // angle(0) = 0, and phi_dual = 0 without co-pol
+        }
+        if (!p.co && out_co) {
+            out_co[px] = co;
+            if (idx_co) idx_co[px] = -1;
+        }
+        if (idx_cr) idx_cr[px] = ix;
+        if (out_cr) {
+            double2 o = dual;
+            if (a.flags & XS_FLAG_MERGE_DUAL) {
+                const double aco = hypot(co.x, co.y), adu = hypot(dual.x, dual.y);
+                if (aco < 5.0 || adu < 5.0) o = co;
             }
-            if (idx_cr) idx_cr[px] = ix;
-            if (out_cr) {
-                double2 o = dual;
-                if (a.flags & XS_FLAG_MERGE_DUAL) {
-                    const double aco = hypot(co.x, co.y), adu = hypot(dual.x, dual.y);
-                    if (aco < 5.0 || adu < 5.0) o = co;
-                }
-                if (a.flags & XS_FLAG_CR_ABS)
-                    reinterpret_cast<double *>(out_cr)[px] = hypot(o.x, o.y);
-                else
-                    reinterpret_cast<double2 *>(out_cr)[px] = o;
-            }
+            if (a.flags & XS_FLAG_CR_ABS)
+                reinterpret_cast<double *>(out_cr)[px] = hypot(o.x, o.y);
+            else
+                reinterpret_cast<double2 *>(out_cr)[px] = o;
         }
     }
 }
@@ -989,7 +1021,7 @@ extern "C" int xs_invert(const xs_plan *pl, const xs_invert_args *ar, void *stre
         }
     }
     {
-        const int64_t warps_needed = n;
+        const int64_t warps_needed = ceil_div(n, 32);
         int64_t grid = ceil_div(warps_needed * 32, 256);
         const int64_t cap = (int64_t)sms * 16;
         if (grid > cap) grid = cap;
