@@ -134,13 +134,6 @@ def synth_scene_device(lines, samples, seed):
     return inc, s_co, s_cr, anc
 
 
-def cpu_sample(inc, s_co, s_cr, anc, n_lines=64, n_samples=1000):
-    """A bounded [n_lines, n_samples] crop across the whole swath (every k-th sample) for the CPU baseline."""
-    step = max(1, inc.shape[1] // n_samples)
-    sl = (slice(0, n_lines), slice(0, step * n_samples, step))
-    return tuple(t[sl].contiguous().cpu().numpy() for t in (inc, s_co, s_cr, anc))
-
-
 def make_cpu_port(threads=None):
     """The reference's CPU program shape (oracle/numba_port.py: the numba gufunc of windspeed.py:183-323 with the
     reference's decorator arguments) for the bench workload.  Returns run(sample) -> (px/s, threads, seconds)."""
@@ -173,26 +166,35 @@ def make_cpu_port(threads=None):
     return run
 
 
+def sized_cpu_lines(port, make_sample, target_s, lo=16, hi=4096):
+    """Number of 1000-sample lines that keeps one CPU pass near `target_s` seconds (probe with `lo` lines first)."""
+    rate, _, _ = port(make_sample(lo))
+    return int(min(hi, max(lo, round(target_s * rate / 1000.0 / 16) * 16)))
+
+
 def run_reference(args, rank, world):
     """`--impl reference`: the reference's CPU path on the box's host cores (rank 0 only)."""
     if rank != 0:
         return
     import oracle  # inputs of the reference arm are made on the host: none of our kernels on this path
 
-    lines = args.cpu_lines
-    rng = np.random.default_rng(args.seed)
-    inc = np.broadcast_to(np.linspace(INC_NEAR, INC_FAR, 1000), (lines, 1000)).copy()
-    w, p = rng.uniform(2, 25, inc.shape), rng.uniform(0, 360, inc.shape)
-    s_co = oracle.gmf_eval("gmf_cmod5n", inc, w, p) * np.exp(rng.normal(0, 0.05, inc.shape))
-    s_cr = oracle.gmf_eval("gmf_s1_v2", inc, w) * np.exp(rng.normal(0, 0.05, inc.shape))
-    anc = (w + rng.normal(0, 2, inc.shape)) * np.exp(1j * np.deg2rad(p + rng.normal(0, 20, inc.shape)))
-    land = rng.uniform(size=inc.shape) < 0.01
-    s_co[land] = np.nan
-    s_cr[land] = np.nan
-    sample = (inc, s_co, s_cr, anc)
+    def make_sample(lines):
+        rng = np.random.default_rng(args.seed)
+        inc = np.broadcast_to(np.linspace(INC_NEAR, INC_FAR, 1000), (lines, 1000)).copy()
+        w, p = rng.uniform(2, 25, inc.shape), rng.uniform(0, 360, inc.shape)
+        s_co = oracle.gmf_eval("gmf_cmod5n", inc, w, p) * np.exp(rng.normal(0, 0.05, inc.shape))
+        s_cr = oracle.gmf_eval("gmf_s1_v2", inc, w) * np.exp(rng.normal(0, 0.05, inc.shape))
+        anc = (w + rng.normal(0, 2, inc.shape)) * np.exp(1j * np.deg2rad(p + rng.normal(0, 20, inc.shape)))
+        land = rng.uniform(size=inc.shape) < 0.01
+        s_co[land] = np.nan
+        s_cr[land] = np.nan
+        return inc, s_co, s_cr, anc
+
+    port = make_cpu_port()
+    lines = args.cpu_lines or sized_cpu_lines(port, make_sample, args.cpu_seconds)
+    sample = make_sample(lines)
     rates, secs = [], []
     threads = None
-    port = make_cpu_port()
     for it in range(args.warmup + args.steps):
         r, threads, dt = port(sample)
         if it >= args.warmup:
@@ -220,7 +222,8 @@ def main():
     ap.add_argument("--lines", type=int, default=LINES)
     ap.add_argument("--samples", type=int, default=SAMPLES)
     ap.add_argument("--seed", type=int, default=0)
-    ap.add_argument("--cpu-lines", type=int, default=64, help="lines of the 1000-sample crop timed on the CPU")
+    ap.add_argument("--cpu-lines", type=int, default=0, help="lines of the 1000-sample crop timed on the CPU (0: sized for --cpu-seconds)")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target duration of one CPU pass")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -337,13 +340,19 @@ def main():
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
-        if cpu_src is not None:
-            step_s = max(1, args.samples // 1000)
-            sl = (slice(0, args.cpu_lines), slice(0, step_s * 1000, step_s))
-            sample = tuple(np.ascontiguousarray(a[sl]) for a in cpu_src)
-        else:
-            sample = cpu_sample(inc, s_co, s_cr, anc, args.cpu_lines, 1000)
-        r, threads, dt = make_cpu_port()(sample)
+        step_s = max(1, args.samples // 1000)
+
+        def make_sample(lines):
+            lines = min(lines, args.lines)
+            sl = (slice(0, lines), slice(0, step_s * 1000, step_s))
+            if cpu_src is not None:
+                return tuple(np.ascontiguousarray(a[sl]) for a in cpu_src)
+            return tuple(t[sl].contiguous().cpu().numpy() for t in (inc, s_co, s_cr, anc))
+
+        port = make_cpu_port()
+        lines = args.cpu_lines or sized_cpu_lines(port, make_sample, args.cpu_seconds)
+        sample = make_sample(lines)
+        r, threads, dt = port(sample)
         cpu = {"value": r, "unit": "px/s", "cores": threads, "kind": "port", "seconds": dt,
                "sample": f"{sample[0].shape[0]}x{sample[0].shape[1]} px crop across the swath of the same scene, numba "
                          f"gufunc with the reference's decorator arguments (oracle/numba_port.py), JIT excluded"}
