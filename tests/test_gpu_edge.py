@@ -1,0 +1,144 @@
+"""Edge cases of the GPU path: empty and tiny inputs, every scan-kernel instantiation (phi grids of 73, 181, 240, 361
+nodes), LUTs the FP32 scan does not support (falls back to the exhaustive FP64 kernel), out-of-range / infinite
+incidence, float32 rasters through the API, the CMOD7 table reader."""
+import warnings
+
+import numpy as np
+import pytest
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    import torch
+
+    from xsarsea_b200 import _device, _native
+
+    assert torch.cuda.is_available()
+    return torch, _device, _native
+
+
+def make_co_lut(n_phi, phi_max, n_inc=5, n_wspd=61):
+    gi = np.linspace(20.0, 40.0, n_inc)
+    gw = np.linspace(0.2, 50.0, n_wspd)
+    gp = np.linspace(0.0, phi_max, n_phi)
+    with np.errstate(all="ignore"):
+        lut = 10 * np.log10(oracle.lut_build("gmf_cmod5n", gi, gw, gp) + 1e-15)
+    return lut, gi, gw, gp
+
+
+def pixels(n, seed, gi):
+    rng = np.random.default_rng(seed)
+    inc = rng.uniform(gi[0] - 1, gi[-1] + 1, n)
+    w, p = rng.uniform(1, 30, n), rng.uniform(0, 360, n)
+    with np.errstate(all="ignore"):
+        s_db = 10 * np.log10(oracle.gmf_eval("gmf_cmod5n", np.clip(inc, 17, 60), w, p) * np.exp(rng.normal(0, 0.1, n)) + 1e-15)
+    anc = (w + rng.normal(0, 3, n)) * np.exp(1j * np.deg2rad(p + rng.normal(0, 30, n)))
+    return inc, s_db, anc
+
+
+@pytest.mark.parametrize("n_phi,phi_max", [(73, 180.0), (37, 180.0), (181, 180.0), (240, 358.5), (361, 360.0), (400, 359.1)])
+def test_every_phi_grid_size(dev, n_phi, phi_max):
+    """kp = 1, 2, 3, 4, 6 instantiations (mirrored and full-circle phi grids) and a 400-node grid that the FP32 scan
+    does not cover: all must equal the oracle index for index, and the two modes must agree."""
+    torch, D, nat = dev
+    lut, gi, gw, gp = make_co_lut(n_phi, phi_max)
+    inc, s_db, anc = pixels(3000, n_phi, gi)
+    plan = D.InversionPlan(co=(D.to_device(lut), gi, gw, gp))
+    args = (D.to_device(inc), D.to_device(s_db), None, 0.1, D.to_device(anc))
+    oc0, _, ic0, _ = plan.invert(*args, sigma0_db=True, want_idx=True)
+    st = plan.last_stats()
+    oc1, _, ic1, _ = plan.invert(*args, sigma0_db=True, want_idx=True, mode=nat.MODE_FP64)
+    o_co, _, o_ic, _ = oracle.invert(inc, s_db, np.nan, 0.1, anc, co_lut=lut, inc_grid=gi, wspd_grid=gw, phi_grid=gp)
+    assert np.array_equal(ic0.cpu().numpy(), o_ic) and np.array_equal(ic1.cpu().numpy(), o_ic)
+    got = oc0.cpu().numpy()
+    assert np.allclose(got, o_co, rtol=0, atol=1e-9, equal_nan=True)
+    if n_phi <= 384:
+        assert st["scan_pixels"] > 0.95 * len(inc)      # the FP32 scan did the work
+    else:
+        assert st["scan_pixels"] == 0                   # unsupported grid: exhaustive FP64 kernel
+
+
+def test_empty_single_and_ragged(dev, golden):
+    torch, D, nat = dev
+    d = golden("inv_small")
+    plan = D.InversionPlan(co=(D.to_device(d["co_lut_db"]), d["inc_grid"], d["wspd_grid"], d["phi_grid"]),
+                           cr=(D.to_device(d["cr_lut_db"]), d["inc_grid"], d["wspd_cr_grid"]))
+    z = lambda dt: torch.empty(0, dtype=dt, device="cuda")
+    oc, ox, _, _ = plan.invert(z(torch.float64), z(torch.float64), z(torch.float64), 0.1, z(torch.complex128), sigma0_db=True)
+    assert oc.numel() == 0 and ox.numel() == 0
+    for n in (1, 7, 65, 129):
+        sl = slice(100, 100 + n)
+        oc, ox, ic, ix = plan.invert(D.to_device(d["inc"][sl]), D.to_device(d["s0_co_db"][sl]), D.to_device(d["s0_cr_db"][sl]),
+                                     D.to_device(d["dsig_cr"][sl]), D.to_device(d["anc"][sl]), sigma0_db=True, want_idx=True)
+        assert np.allclose(oc.cpu().numpy(), d["out_co"][sl], rtol=0, atol=1e-9, equal_nan=True)
+        assert np.allclose(ox.cpu().numpy(), d["out_cr"][sl], rtol=0, atol=1e-9, equal_nan=True)
+
+
+def test_incidence_out_of_range_and_infinite(dev, golden):
+    torch, D, nat = dev
+    d = golden("inv_small")
+    n = 64
+    inc = np.array([np.inf, -np.inf, 1e6, -5.0, 16.0, 66.0, 16.49999, 16.5, 41.5, 41.50000000000001] + [30.0] * (n - 10))
+    s = np.full(n, -12.0)
+    anc = np.full(n, 6 + 3j)
+    plan = D.InversionPlan(co=(D.to_device(d["co_lut_db"]), d["inc_grid"], d["wspd_grid"], d["phi_grid"]))
+    oc, _, ic, _ = plan.invert(D.to_device(inc), D.to_device(s), None, 0.1, D.to_device(anc), sigma0_db=True, want_idx=True)
+    with np.errstate(all="ignore"):
+        o_co, _, o_ic, _ = oracle.invert(inc, s, np.nan, 0.1, anc, co_lut=d["co_lut_db"], inc_grid=d["inc_grid"],
+                                         wspd_grid=d["wspd_grid"], phi_grid=d["phi_grid"])
+    assert np.array_equal(ic.cpu().numpy(), o_ic)
+    assert np.allclose(oc.cpu().numpy(), o_co, rtol=0, atol=1e-9, equal_nan=True)
+
+
+def test_api_float32_rasters(dev):
+    from xsarsea_b200 import windspeed as ws
+
+    kw = dict(inc_step_lr=2.0, wspd_step_lr=1.0, phi_step_lr=10.0, inc_step=0.5, wspd_step=0.25, phi_step=2.5)
+    rng = np.random.default_rng(0)
+    n = 4000
+    inc = rng.uniform(17, 49, n).astype(np.float32)
+    w, p = rng.uniform(2, 25, n), rng.uniform(0, 360, n)
+    s_co = (oracle.gmf_eval("gmf_cmod5n", inc.astype(np.float64), w, p)).astype(np.float32)
+    anc = ((w + rng.normal(0, 2, n)) * np.exp(1j * np.deg2rad(p + rng.normal(0, 20, n)))).astype(np.complex64)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        a = ws.invert_from_model(inc, s_co, ancillary_wind=anc, model="gmf_cmod5n", **kw)
+        b = ws.invert_from_model(inc.astype(np.float64), s_co.astype(np.float64), ancillary_wind=anc.astype(np.complex128),
+                                 model="gmf_cmod5n", **kw)
+    assert a.dtype == np.complex128 and np.array_equal(a, b, equal_nan=True)   # f32 is promoted exactly
+
+
+def test_cmod7_table_reader(dev, tmp_path):
+    """cmod7.py:19-75: float32 little-endian Fortran record (head/tail markers), (wspd, phi, inc) Fortran order,
+    linear units, low resolution.  The KNMI file is not redistributable/available: a synthetic table with cmod5n values
+    exercises the reader, the alias priority (Cmod7 1 < Gmf 3) and the device interpolation."""
+    from xsarsea_b200 import windspeed as ws
+    from xsarsea_b200.windspeed.models import Model
+
+    wspd = np.arange(0.2, 50.0 + 0.2, 0.2)
+    inc = np.arange(16, 66 + 1, 1)
+    phi = np.arange(0, 180 + 2.5, 2.5)
+    assert (wspd.size, phi.size, inc.size) == (250, 73, 51)
+    table = oracle.lut_build("gmf_cmod5n", inc.astype(float), wspd, phi)             # [inc][wspd][phi]
+    fortran = np.transpose(table, (1, 2, 0)).astype("<f4")                           # (wspd, phi, inc)
+    rec = np.concatenate([[0.0], fortran.reshape(-1, order="F"), [0.0]]).astype("<f4")
+    d = tmp_path / "cmod7"
+    d.mkdir()
+    rec.tofile(str(d / "gmf_cmod7_vv.dat_little_endian"))
+    try:
+        ws.register_cmod7(str(d))
+        m = ws.get_model("gmf_cmod7")
+        assert m.pol == "VV" and m._priority == 1 and ws.get_model("cmod7") is m
+        low = m.to_lut(resolution="low")
+        assert low.dims == ("incidence", "wspd", "phi") and low.shape == (51, 250, 73) and low.attrs["units"] == "linear"
+        np.testing.assert_array_equal(np.asarray(low), table.astype(np.float32).astype(np.float64))
+        hi = m.to_lut(units="dB")
+        assert hi.shape == (501, 499, 181)
+        # node (inc 16, wspd 0.2, phi 0) is shared by both grids
+        assert abs(np.asarray(hi)[0, 0, 0] - 10 * np.log10(float(np.float32(table[0, 0, 0])) + 1e-15)) < 1e-9
+    finally:
+        Model._available_models.pop("gmf_cmod7", None)
