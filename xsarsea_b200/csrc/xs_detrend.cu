@@ -1,13 +1,15 @@
 // K7: sigma0 detrending (reference detrend.py:55-64): out[l][s] = sigma0[l][s] / (gmf[s] / nanmean(gmf)).
 // HBM-bound: one streaming read and one streaming write of the raster; the [W] ratio vector stays in L2.
 #include <math_constants.h>
+#include <stdlib.h>
 
 #include "xs_common.cuh"
 
 namespace xs {
 
 // ratio[s] = gmf[s] / nanmean(gmf); single CTA, FP64 tree reduction
-__global__ void __launch_bounds__(1024) k_detrend_ratio(const double *__restrict__ gmf, int64_t w, double *__restrict__ ratio) {
+__global__ void __launch_bounds__(1024) k_detrend_ratio(const double *__restrict__ gmf, int64_t w, double *__restrict__ ratio,
+                                                        double *__restrict__ rinv) {
     __shared__ double sh_sum[32];
     __shared__ long long sh_cnt[32];
     __shared__ double mean_s;
@@ -42,22 +44,51 @@ __global__ void __launch_bounds__(1024) k_detrend_ratio(const double *__restrict
     }
     __syncthreads();
     const double mean = mean_s;
-    for (int64_t i = threadIdx.x; i < w; i += blockDim.x) ratio[i] = gmf[i] / mean;
+    for (int64_t i = threadIdx.x; i < w; i += blockDim.x) {
+        const double r = gmf[i] / mean;
+        ratio[i] = r;
+        rinv[i] = 1.0 / r;
+    }
 }
 
-// VEC elements per thread per step (16-byte accesses); W % VEC == 0 on this path
-template <typename T, typename V, int VEC>
-__global__ void __launch_bounds__(256) k_detrend_vec(const V *__restrict__ s0, const double *__restrict__ ratio, int64_t h,
-                                                     int64_t wv, V *__restrict__ out) {
-    const int64_t n = h * wv;
+// Flat grid-stride pass over 16-byte words (VEC samples each), UNROLL independent loads in flight per thread.  The
+// sample index of a word is tracked incrementally (no integer division in the loop); the [W] ratio vector and its
+// reciprocal stay in L1/L2.  x / r is evaluated as q0 = x*(1/r) plus one Newton/Markstein correction
+// q = q0 + (x - q0*r)*(1/r) with the residual exact by FMA: the correctly rounded quotient but for rare double-rounding
+// cases (<= 1 ulp), at 3 FP64 operations instead of a full division per pixel.
+template <typename T, typename V, int VEC, int UNROLL>
+__global__ void __launch_bounds__(256) k_detrend_vec(const V *__restrict__ s0, const double *__restrict__ ratio,
+                                                     const double *__restrict__ rinv, int64_t n_words, int64_t wv,
+                                                     V *__restrict__ out) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const int64_t col = (i % wv) * VEC;
-        V v = __ldcs(&s0[i]);  // streaming: read once
-        T *e = reinterpret_cast<T *>(&v);
+    const int64_t step_col = stride % wv;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t col = i % wv;
+    for (; i < n_words; i += stride * UNROLL) {
+        V v[UNROLL];
+        int64_t c[UNROLL];
 #pragma unroll
-        for (int k = 0; k < VEC; ++k) e[k] = (T)((double)e[k] / ratio[col + k]);
-        __stcs(&out[i], v);
+        for (int q = 0; q < UNROLL; ++q) {
+            c[q] = col;
+            col += step_col;
+            if (col >= wv) col -= wv;
+            if (i + q * stride < n_words) v[q] = __ldcs(&s0[i + q * stride]);  // streaming: read once
+        }
+#pragma unroll
+        for (int q = 0; q < UNROLL; ++q)
+            if (i + q * stride < n_words) {
+                T *e = reinterpret_cast<T *>(&v[q]);
+#pragma unroll
+                for (int k = 0; k < VEC; ++k) {
+                    const double r = ratio[c[q] * VEC + k], ri = rinv[c[q] * VEC + k];
+                    const double x = (double)e[k];
+                    const double q0 = x * ri;
+                    const double res = fma(-q0, r, x);
+                    // non-finite operands (NaN/inf sigma0, zero or NaN ratio) take the plain division
+                    e[k] = (T)((isfinite(q0) && isfinite(ri)) ? fma(res, ri, q0) : x / r);
+                }
+                __stcs(&out[i + q * stride], v[q]);
+            }
     }
 }
 
@@ -82,8 +113,9 @@ extern "C" int xs_detrend(const void *sigma0, const double *gmf_line, int64_t n_
     if (n_lines == 0) return XS_OK;
     cudaStream_t st = (cudaStream_t)stream;
     double *ratio = nullptr;
-    XS_CUDA(cudaMallocAsync(&ratio, sizeof(double) * (size_t)n_samples, st));
-    XS_LAUNCH(k_detrend_ratio, 1, 1024, 0, stream, gmf_line, n_samples, ratio);
+    XS_CUDA(cudaMallocAsync(&ratio, 2 * sizeof(double) * (size_t)n_samples, st));
+    double *rinv = ratio + n_samples;
+    XS_LAUNCH(k_detrend_ratio, 1, 1024, 0, stream, gmf_line, n_samples, ratio, rinv);
     const int64_t n = n_lines * n_samples;
     const bool aligned = (((uintptr_t)sigma0 | (uintptr_t)out) & 15) == 0;
     auto grid_for = [](int64_t items) {
@@ -93,15 +125,15 @@ extern "C" int xs_detrend(const void *sigma0, const double *gmf_line, int64_t n_
     };
     if (dtype == XS_F64) {
         if (aligned && n_samples % 2 == 0)
-            XS_LAUNCH((k_detrend_vec<double, double2, 2>), grid_for(n / 2), 256, 0, stream, (const double2 *)sigma0, ratio,
-                      n_lines, n_samples / 2, (double2 *)out);
+            XS_LAUNCH((k_detrend_vec<double, double2, 2, 4>), grid_for(n / 2 / 4), 256, 0, stream, (const double2 *)sigma0,
+                      ratio, rinv, n / 2, n_samples / 2, (double2 *)out);
         else
             XS_LAUNCH(k_detrend_scalar<double>, grid_for(n), 256, 0, stream, (const double *)sigma0, ratio, n_lines, n_samples,
                       (double *)out);
     } else {
         if (aligned && n_samples % 4 == 0)
-            XS_LAUNCH((k_detrend_vec<float, float4, 4>), grid_for(n / 4), 256, 0, stream, (const float4 *)sigma0, ratio,
-                      n_lines, n_samples / 4, (float4 *)out);
+            XS_LAUNCH((k_detrend_vec<float, float4, 4, 4>), grid_for(n / 4 / 4), 256, 0, stream, (const float4 *)sigma0,
+                      ratio, rinv, n / 4, n_samples / 4, (float4 *)out);
         else
             XS_LAUNCH(k_detrend_scalar<float>, grid_for(n), 256, 0, stream, (const float *)sigma0, ratio, n_lines, n_samples,
                       (float *)out);

@@ -332,7 +332,7 @@ struct ScanSmem {
     PixelSlot px[NW * P];
 };
 
-template <int KP, int P, int NW, int MB>
+template <int KP, int P, int NW, int MB, bool kScalarMath = false>
 __global__ void __launch_bounds__(NW * 32, MB)
 k_scan_co(xs_plan pl, RasterArgs a, Workspace ws, double2 *out_co, int *idx_co) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -484,11 +484,20 @@ k_scan_co(xs_plan pl, RasterArgs a, Workspace ws, double2 *out_co, int *idx_co) 
                         const u64 q2 = pack2(nqs[p], nqs[p]);
 #pragma unroll
                         for (int j = 0; j < KP; ++j) {
-                            const u64 d = fadd2(L[j], q2);
-                            const u64 t = ffma2(nwh, g[p][j], w2q);
-                            const u64 J = ffma2(d, d, t);
                             float j0, j1;
-                            unpack2(J, j0, j1);
+                            if (kScalarMath) {  // experiment: scalar FADD/FFMA instead of the packed f32x2 forms
+                                float l0, l1, g0, g1;
+                                unpack2(L[j], l0, l1);
+                                unpack2(g[p][j], g0, g1);
+                                const float d0 = l0 + nqs[p], d1 = l1 + nqs[p];
+                                j0 = fmaf(d0, d0, fmaf(rt.x, g0, rt.y));
+                                j1 = fmaf(d1, d1, fmaf(rt.x, g1, rt.y));
+                            } else {
+                                const u64 d = fadd2(L[j], q2);
+                                const u64 t = ffma2(nwh, g[p][j], w2q);
+                                const u64 J = ffma2(d, d, t);
+                                unpack2(J, j0, j1);
+                            }
                             m[p] = fmin3(m[p], j0, j1);
                         }
                     }
@@ -728,13 +737,13 @@ __global__ void __launch_bounds__(256) k_cross(xs_plan pl, RasterArgs a, int64_t
     }
 }
 
-template <int KP, int P, int NW, int MB>
+template <int KP, int P, int NW, int MB, bool SC = false>
 static int launch_scan(const xs_plan *pl, const RasterArgs &ra, const Workspace &ws, double2 *out_co, int *idx_co,
                        void *stream) {
     const size_t smem = sizeof(ScanSmem<KP, P, NW>) + sizeof(float2) * (size_t)pl->n_wspd_pad;
     static bool configured = false;  // per instantiation
     if (!configured) {
-        XS_CUDA(cudaFuncSetAttribute(k_scan_co<KP, P, NW, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        XS_CUDA(cudaFuncSetAttribute(k_scan_co<KP, P, NW, MB, SC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         configured = true;
     }
     if (smem > 200 * 1024) {
@@ -742,11 +751,11 @@ static int launch_scan(const xs_plan *pl, const RasterArgs &ra, const Workspace 
         return XS_E_UNSUPPORTED;
     }
     int per_sm = 1;
-    XS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_scan_co<KP, P, NW, MB>, NW * 32, smem));
+    XS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_scan_co<KP, P, NW, MB, SC>, NW * 32, smem));
     if (per_sm < 1) per_sm = 1;
     int sms = kNumSMs;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, pl->device);
-    XS_LAUNCH((k_scan_co<KP, P, NW, MB>), sms * per_sm, NW * 32, smem, stream, *pl, ra, ws, out_co, idx_co);
+    XS_LAUNCH((k_scan_co<KP, P, NW, MB, SC>), sms * per_sm, NW * 32, smem, stream, *pl, ra, ws, out_co, idx_co);
     return XS_OK;
 }
 
@@ -774,6 +783,9 @@ static ScanConfig scan_config(int kp) {
             case 5: return {4, 8};
             case 6: return {6, 6};
             case 7: return {6, 10};
+            case 8: return {8, 8};
+            case 9: return {4, 8};
+            case 10: return {8, 12};
             default: return {8, 8};
         }
     }
@@ -793,6 +805,9 @@ static int dispatch_scan(const xs_plan *pl, const RasterArgs &ra, const Workspac
                 case 5: return launch_scan<3, 4, 8, 3>(pl, ra, ws, out_co, idx_co, stream);
                 case 6: return launch_scan<3, 6, 6, 2>(pl, ra, ws, out_co, idx_co, stream);
                 case 7: return launch_scan<3, 6, 10, 1>(pl, ra, ws, out_co, idx_co, stream);
+                case 8: return launch_scan<3, 8, 8, 2, true>(pl, ra, ws, out_co, idx_co, stream);
+                case 9: return launch_scan<3, 4, 8, 2, true>(pl, ra, ws, out_co, idx_co, stream);
+                case 10: return launch_scan<3, 8, 12, 1, true>(pl, ra, ws, out_co, idx_co, stream);
                 default: return launch_scan<3, 8, 8, 2>(pl, ra, ws, out_co, idx_co, stream);
             }
         case 4: return launch_scan<4, 4, 8, 1>(pl, ra, ws, out_co, idx_co, stream);
