@@ -142,3 +142,40 @@ def test_cmod7_table_reader(dev, tmp_path):
         assert abs(np.asarray(hi)[0, 0, 0] - 10 * np.log10(float(np.float32(table[0, 0, 0])) + 1e-15)) < 1e-9
     finally:
         Model._available_models.pop("gmf_cmod7", None)
+
+
+def test_fast_equals_fp64_adversarial_sweep(dev):
+    """The exactness claim of the FP32 scan + FP64 refinement at scale: 6 M pixels on the full-resolution cmod5n LUT
+    (501 x 499 x 181) with adversarial inputs -- ancillary winds exactly on candidate nodes (J_wind = 0 ties), sigma0
+    exactly equal to LUT nodes (J_sig = 0), strong winds, sigma0 far outside the LUT, mirrored pairs -- must give the
+    same argmin index as the exhaustive FP64 kernel on every pixel."""
+    torch, D, nat = dev
+    gi, gw, gp = np.linspace(16, 66, 501), np.linspace(0.2, 50, 499), np.linspace(0, 180, 181)
+    lut = D.lut_to_db(D.lut_build(nat.GMF_IDS["gmf_cmod5n"], gi, gw, gp))
+    plan = D.InversionPlan(co=(lut, gi, gw, gp))
+    g = torch.Generator(device="cuda").manual_seed(11)
+    n = 6_000_000
+    f64 = dict(device="cuda", dtype=torch.float64)
+    inc = 17 + 45 * torch.rand(n, generator=g, **f64)
+    ii = torch.randint(0, 501, (n,), generator=g, device="cuda")
+    iw = torch.randint(0, 499, (n,), generator=g, device="cuda")
+    ip = torch.randint(0, 181, (n,), generator=g, device="cuda")
+    tgi, tgw, tgp = (torch.as_tensor(a, device="cuda") for a in (gi, gw, gp))
+    node_s = lut[ii, iw, ip]                                   # sigma0 (dB) exactly on a LUT node of the pixel's slab
+    node_anc = torch.polar(tgw[iw], torch.deg2rad(tgp[ip]))    # ancillary exactly on a candidate
+    s_rand = -35 + 40 * torch.rand(n, generator=g, **f64)
+    a_rand = torch.polar(60 * torch.rand(n, generator=g, **f64), 2 * np.pi * torch.rand(n, generator=g, **f64) - np.pi)
+    kind = torch.randint(0, 6, (n,), generator=g, device="cuda")
+    inc = torch.where(kind == 0, tgi[ii], inc)                 # kind 0: everything on nodes (J = 0 at one candidate)
+    s = torch.where((kind == 0) | (kind == 1), node_s, s_rand)
+    anc = torch.where((kind == 0) | (kind == 2), node_anc, a_rand)
+    anc = torch.where(kind == 3, torch.conj(anc), anc)         # negative azimuth component (mirror branch)
+    s = torch.where(kind == 4, s_rand * 4 + 30, s)              # far outside the LUT range
+    anc = torch.where(kind == 5, anc * 0, anc)                  # zero ancillary wind
+    a, _, ia, _ = plan.invert(inc, s, None, 0.1, anc, sigma0_db=True, want_idx=True)
+    st = plan.last_stats()
+    b, _, ib, _ = plan.invert(inc, s, None, 0.1, anc, sigma0_db=True, want_idx=True, mode=nat.MODE_FP64)
+    bad = (ia != ib).nonzero().flatten()
+    assert bad.numel() == 0, f"{bad.numel()} mismatches, first {bad[:5].tolist()}"
+    assert torch.equal(torch.view_as_real(a), torch.view_as_real(b))
+    assert st["scan_pixels"] + st["exhaustive_pixels"] == n

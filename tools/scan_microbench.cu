@@ -12,6 +12,8 @@ __device__ __forceinline__ float fmin3(float a, float b, float c) { float d; asm
 constexpr int KP = 3, ROWS = 32;
 // MODE 0: as k_scan_co. 1: FMNMX3 -> 2x FMNMX. 2: t hoisted out of the row loop (2 FMA-pipe ops / pair).
 // 3: scalar FADD/FFMA/FFMA/FMNMX (no f32x2). 4: as 0 but nwh/w2q as packed pairs (no .F32 broadcast operand)
+// 8: hybrid A: t by two scalar FFMA (row constants hit the operand-reuse cache), d and J packed.
+// 9: hybrid B: t and d scalar, J packed.
 // 5: as 0 without the min (sum into m with FADD: all FMA pipe). 6: only the loads + FMNMX3 (no FMA-pipe work)
 template <int MODE, int P>
 __global__ void __launch_bounds__(256, 2) k(const float *__restrict__ src, const float2 *__restrict__ rowtab, float *out, int reps) {
@@ -25,10 +27,10 @@ __global__ void __launch_bounds__(256, 2) k(const float *__restrict__ src, const
     float nqs[P], m[P];
 #pragma unroll
     for (int p = 0; p < P; ++p) {
-        nqs[p] = 0.37f * p + 0.01f * lane;
+        nqs[p] = src[(p * 37 + lane) % 977];
         m[p] = 1e30f;
 #pragma unroll
-        for (int j = 0; j < KP; ++j) g[p][j] = pack2(0.1f * p + j, 0.2f * lane - j);
+        for (int j = 0; j < KP; ++j) g[p][j] = pack2(src[(p * 64 + j * 8 + lane) % 977], src[(p * 32 + j * 16 + lane + 3) % 977]);
     }
     const u64 *rows = reinterpret_cast<const u64 *>(ring);
     for (int rep = 0; rep < reps; ++rep) {
@@ -51,6 +53,21 @@ __global__ void __launch_bounds__(256, 2) k(const float *__restrict__ src, const
                         const float d0 = l0 + nqs[p], d1 = l1 + nqs[p];
                         const float t0 = fmaf(rt.x, g0, rt.y), t1 = fmaf(rt.x, g1, rt.y);
                         m[p] = fminf(fminf(m[p], fmaf(d0, d0, t0)), fmaf(d1, d1, t1));
+                    } else if (MODE == 8 || MODE == 9) {
+                        float g0, g1;
+                        unpack2(g[p][j], g0, g1);
+                        const u64 t = pack2(fmaf(rt.x, g0, rt.y), fmaf(rt.x, g1, rt.y));
+                        u64 d;
+                        if (MODE == 9) {
+                            float l0, l1;
+                            unpack2(L[j], l0, l1);
+                            d = pack2(l0 + nqs[p], l1 + nqs[p]);
+                        } else
+                            d = fadd2(L[j], q2);
+                        const u64 J = ffma2(d, d, t);
+                        float j0, j1;
+                        unpack2(J, j0, j1);
+                        m[p] = fmin3(m[p], j0, j1);
                     } else if (MODE == 6) {
                         float l0, l1;
                         unpack2(L[j], l0, l1);
@@ -89,10 +106,10 @@ __global__ void __launch_bounds__(256, 2) k7(const float *__restrict__ src, cons
     float nqs[P], m[P];
 #pragma unroll
     for (int p = 0; p < P; ++p) {
-        nqs[p] = 0.37f * p + 0.01f * lane;
+        nqs[p] = src[(p * 37 + lane) % 977];
         m[p] = 1e30f;
 #pragma unroll
-        for (int j = 0; j < 2 * KP; ++j) g[p][j] = 0.1f * p + j - 0.2f * lane;
+        for (int j = 0; j < 2 * KP; ++j) g[p][j] = src[(p * 64 + j * 8 + lane) % 977];
     }
     const u64 *rows = reinterpret_cast<const u64 *>(ring);
     for (int rep = 0; rep < reps; ++rep) {
@@ -179,6 +196,8 @@ int main() {
         run<5, 8>("sum instead of min (all fma pipe)", src, rt, out);
         run<6, 8>("LDS + FMNMX3 only", src, rt, out);
         run7<8>("pairs along wspd, g scalar", src, rt, out);
+        run<8, 8>("hybrid A: scalar t, packed d and J", src, rt, out);
+        run<9, 8>("hybrid B: scalar t and d, packed J", src, rt, out);
         run<0, 4>("as k_scan_co, P=4", src, rt, out);
         run<3, 4>("scalar, P=4", src, rt, out);
     }

@@ -330,9 +330,14 @@ struct ScanSmem {
     alignas(16) uint64_t full[kStages];
     alignas(16) uint64_t empty[kStages];
     PixelSlot px[NW * P];
+    // per-thread argmin bookkeeping, touched once per chunk: kept out of the register file so that the inner loop has
+    // registers left for instruction-level parallelism ([pixel][thread]: conflict-free)
+    float best[P][NW * 32];
+    float second[P][NW * 32];
+    int bchunk[P][NW * 32];
 };
 
-template <int KP, int P, int NW, int MB, bool kScalarMath = false>
+template <int KP, int P, int NW, int MB, int kMath = 0, bool kBookSmem = false>
 __global__ void __launch_bounds__(NW * 32, MB)
 k_scan_co(xs_plan pl, RasterArgs a, Workspace ws, double2 *out_co, int *idx_co) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -435,13 +440,22 @@ k_scan_co(xs_plan pl, RasterArgs a, Workspace ws, double2 *out_co, int *idx_co) 
                 nqs[p] = sl.state == 1 ? (float)(-(sl.s / pl.dsig_co)) : 0.f;
             }
 
-            float best[P], second[P], m[P];
+            float m[P];
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+                m[p] = CUDART_INF_F;
+                if (kBookSmem) {
+                    sm.best[p][threadIdx.x] = CUDART_INF_F;
+                    sm.second[p][threadIdx.x] = CUDART_INF_F;
+                    sm.bchunk[p][threadIdx.x] = 0;
+                }
+            }
+            float best[P], second[P];
             int bchunk[P];
 #pragma unroll
             for (int p = 0; p < P; ++p) {
                 best[p] = CUDART_INF_F;
                 second[p] = CUDART_INF_F;
-                m[p] = CUDART_INF_F;
                 bchunk[p] = 0;
             }
 
@@ -485,13 +499,23 @@ k_scan_co(xs_plan pl, RasterArgs a, Workspace ws, double2 *out_co, int *idx_co) 
 #pragma unroll
                         for (int j = 0; j < KP; ++j) {
                             float j0, j1;
-                            if (kScalarMath) {  // experiment: scalar FADD/FFMA instead of the packed f32x2 forms
+                            if (kMath == 1) {  // experiment: scalar FADD/FFMA instead of the packed f32x2 forms
                                 float l0, l1, g0, g1;
                                 unpack2(L[j], l0, l1);
                                 unpack2(g[p][j], g0, g1);
                                 const float d0 = l0 + nqs[p], d1 = l1 + nqs[p];
                                 j0 = fmaf(d0, d0, fmaf(rt.x, g0, rt.y));
                                 j1 = fmaf(d1, d1, fmaf(rt.x, g1, rt.y));
+                            } else if (kMath == 2) {
+                                // t by two scalar FFMA: their row constants (-w/2, w^2/4) are the same registers for
+                                // every pixel and phi pair of the row, so they are served by the operand-reuse cache
+                                // instead of the register file, which is what bounds this loop
+                                float g0, g1;
+                                unpack2(g[p][j], g0, g1);
+                                const u64 t = pack2(fmaf(rt.x, g0, rt.y), fmaf(rt.x, g1, rt.y));
+                                const u64 d = fadd2(L[j], q2);
+                                const u64 J = ffma2(d, d, t);
+                                unpack2(J, j0, j1);
                             } else {
                                 const u64 d = fadd2(L[j], q2);
                                 const u64 t = ffma2(nwh, g[p][j], w2q);
@@ -506,14 +530,31 @@ k_scan_co(xs_plan pl, RasterArgs a, Workspace ws, double2 *out_co, int *idx_co) 
                 if (lane == 0) mbar_arrive(&sm.empty[s]);
 #pragma unroll
                 for (int p = 0; p < P; ++p) {
-                    const bool lt = m[p] < best[p];
-                    second[p] = fminf(second[p], fmaxf(best[p], m[p]));
-                    best[p] = fminf(best[p], m[p]);
-                    bchunk[p] = lt ? c : bchunk[p];
+                    if (kBookSmem) {
+                        const float b = sm.best[p][threadIdx.x];
+                        sm.second[p][threadIdx.x] = fminf(sm.second[p][threadIdx.x], fmaxf(b, m[p]));
+                        if (m[p] < b) {
+                            sm.best[p][threadIdx.x] = m[p];
+                            sm.bchunk[p][threadIdx.x] = c;
+                        }
+                    } else {
+                        const bool lt = m[p] < best[p];
+                        second[p] = fminf(second[p], fmaxf(best[p], m[p]));
+                        best[p] = fminf(best[p], m[p]);
+                        bchunk[p] = lt ? c : bchunk[p];
+                    }
                     m[p] = CUDART_INF_F;
                 }
             }
             it += n_chunks;
+            if (kBookSmem) {
+#pragma unroll
+                for (int p = 0; p < P; ++p) {
+                    best[p] = sm.best[p][threadIdx.x];
+                    second[p] = sm.second[p][threadIdx.x];
+                    bchunk[p] = sm.bchunk[p][threadIdx.x];
+                }
+            }
 
             // ---- settle each pixel: warp-shuffle min, FP64 re-evaluation inside the error band ----
             const double *slab64 = pl.co_lut + (int64_t)bin * pl.n_wspd * pl.n_phi;
@@ -737,13 +778,13 @@ __global__ void __launch_bounds__(256) k_cross(xs_plan pl, RasterArgs a, int64_t
     }
 }
 
-template <int KP, int P, int NW, int MB, bool SC = false>
+template <int KP, int P, int NW, int MB, int SC = 0, bool BK = false>
 static int launch_scan(const xs_plan *pl, const RasterArgs &ra, const Workspace &ws, double2 *out_co, int *idx_co,
                        void *stream) {
     const size_t smem = sizeof(ScanSmem<KP, P, NW>) + sizeof(float2) * (size_t)pl->n_wspd_pad;
     static bool configured = false;  // per instantiation
     if (!configured) {
-        XS_CUDA(cudaFuncSetAttribute(k_scan_co<KP, P, NW, MB, SC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        XS_CUDA(cudaFuncSetAttribute(k_scan_co<KP, P, NW, MB, SC, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         configured = true;
     }
     if (smem > 200 * 1024) {
@@ -751,11 +792,11 @@ static int launch_scan(const xs_plan *pl, const RasterArgs &ra, const Workspace 
         return XS_E_UNSUPPORTED;
     }
     int per_sm = 1;
-    XS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_scan_co<KP, P, NW, MB, SC>, NW * 32, smem));
+    XS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_scan_co<KP, P, NW, MB, SC, BK>, NW * 32, smem));
     if (per_sm < 1) per_sm = 1;
     int sms = kNumSMs;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, pl->device);
-    XS_LAUNCH((k_scan_co<KP, P, NW, MB, SC>), sms * per_sm, NW * 32, smem, stream, *pl, ra, ws, out_co, idx_co);
+    XS_LAUNCH((k_scan_co<KP, P, NW, MB, SC, BK>), sms * per_sm, NW * 32, smem, stream, *pl, ra, ws, out_co, idx_co);
     return XS_OK;
 }
 
@@ -786,6 +827,17 @@ static ScanConfig scan_config(int kp) {
             case 8: return {8, 8};
             case 9: return {4, 8};
             case 10: return {8, 12};
+            case 11: return {8, 8};
+            case 12: return {8, 12};
+            case 13: return {6, 8};
+            case 14: return {4, 8};
+            case 15: return {4, 8};
+            case 16: return {8, 8};
+            case 17: return {8, 8};
+            case 18: return {4, 12};
+            case 19: return {8, 8};
+            case 20: return {8, 8};
+            case 21: return {8, 8};
             default: return {8, 8};
         }
     }
@@ -805,9 +857,20 @@ static int dispatch_scan(const xs_plan *pl, const RasterArgs &ra, const Workspac
                 case 5: return launch_scan<3, 4, 8, 3>(pl, ra, ws, out_co, idx_co, stream);
                 case 6: return launch_scan<3, 6, 6, 2>(pl, ra, ws, out_co, idx_co, stream);
                 case 7: return launch_scan<3, 6, 10, 1>(pl, ra, ws, out_co, idx_co, stream);
-                case 8: return launch_scan<3, 8, 8, 2, true>(pl, ra, ws, out_co, idx_co, stream);
-                case 9: return launch_scan<3, 4, 8, 2, true>(pl, ra, ws, out_co, idx_co, stream);
-                case 10: return launch_scan<3, 8, 12, 1, true>(pl, ra, ws, out_co, idx_co, stream);
+                case 8: return launch_scan<3, 8, 8, 2, 1>(pl, ra, ws, out_co, idx_co, stream);
+                case 9: return launch_scan<3, 4, 8, 2, 1>(pl, ra, ws, out_co, idx_co, stream);
+                case 10: return launch_scan<3, 8, 12, 1, 1>(pl, ra, ws, out_co, idx_co, stream);
+                case 11: return launch_scan<3, 8, 8, 2, 2>(pl, ra, ws, out_co, idx_co, stream);
+                case 12: return launch_scan<3, 8, 12, 1, 2>(pl, ra, ws, out_co, idx_co, stream);
+                case 13: return launch_scan<3, 6, 8, 2, 2>(pl, ra, ws, out_co, idx_co, stream);
+                case 14: return launch_scan<3, 4, 8, 2, 2>(pl, ra, ws, out_co, idx_co, stream);
+                case 15: return launch_scan<3, 4, 8, 3, 2>(pl, ra, ws, out_co, idx_co, stream);
+                case 16: return launch_scan<3, 8, 8, 1, 2>(pl, ra, ws, out_co, idx_co, stream);
+                case 17: return launch_scan<3, 8, 8, 1, 0>(pl, ra, ws, out_co, idx_co, stream);
+                case 18: return launch_scan<3, 4, 12, 2, 2>(pl, ra, ws, out_co, idx_co, stream);
+                case 19: return launch_scan<3, 8, 8, 2, 2, true>(pl, ra, ws, out_co, idx_co, stream);
+                case 20: return launch_scan<3, 8, 8, 2, 0, true>(pl, ra, ws, out_co, idx_co, stream);
+                case 21: return launch_scan<3, 8, 8, 2, 1, true>(pl, ra, ws, out_co, idx_co, stream);
                 default: return launch_scan<3, 8, 8, 2>(pl, ra, ws, out_co, idx_co, stream);
             }
         case 4: return launch_scan<4, 4, 8, 1>(pl, ra, ws, out_co, idx_co, stream);
