@@ -359,7 +359,7 @@ k_scan_co(xs_plan pl, RasterArgs a, Workspace ws, double2 *out_co, int *idx_co) 
     __syncthreads();
 
     const unsigned n_tiles = (unsigned)ws.counters[0];
-    const int n_chunks = pl.n_wspd_pad / kChunkRows;
+    const int n_chunks = (pl.n_wspd_pad + kChunkRows - 1) / kChunkRows;  // the last chunk may be shorter
     unsigned it = 0;  // chunks consumed so far by this CTA (ring position, continues across tiles)
     u64 n_scanned = 0, n_refined = 0;
 
@@ -467,8 +467,9 @@ k_scan_co(xs_plan pl, RasterArgs a, Workspace ws, double2 *out_co, int *idx_co) 
                     const unsigned g_it = it + c;
                     const int s = g_it % kStages;
                     if (g_it >= kStages) mbar_wait(&sm.empty[s], ((g_it / kStages) - 1) & 1);
-                    mbar_expect_tx(&sm.full[s], Smem::kChunkBytes);
-                    bulk_g2s(sm.ring[s], slab + (int64_t)c * kChunkRows * Smem::kRowFloats, Smem::kChunkBytes, &sm.full[s]);
+                    const uint32_t bytes = (uint32_t)min(kChunkRows, pl.n_wspd_pad - c * kChunkRows) * Smem::kRowFloats * 4;
+                    mbar_expect_tx(&sm.full[s], bytes);
+                    bulk_g2s(sm.ring[s], slab + (int64_t)c * kChunkRows * Smem::kRowFloats, bytes, &sm.full[s]);
                 }
             }
             // ---- main loop over 8-row chunks ----
@@ -479,15 +480,17 @@ k_scan_co(xs_plan pl, RasterArgs a, Workspace ws, double2 *out_co, int *idx_co) 
                     const unsigned n_it = g_it + kStages - 1;
                     const int ns = n_it % kStages;
                     if (n_it >= kStages) mbar_wait(&sm.empty[ns], ((n_it / kStages) - 1) & 1);
-                    mbar_expect_tx(&sm.full[ns], Smem::kChunkBytes);
-                    bulk_g2s(sm.ring[ns], slab + (int64_t)(c + kStages - 1) * kChunkRows * Smem::kRowFloats,
-                             Smem::kChunkBytes, &sm.full[ns]);
+                    const int nc = c + kStages - 1;
+                    const uint32_t bytes = (uint32_t)min(kChunkRows, pl.n_wspd_pad - nc * kChunkRows) * Smem::kRowFloats * 4;
+                    mbar_expect_tx(&sm.full[ns], bytes);
+                    bulk_g2s(sm.ring[ns], slab + (int64_t)nc * kChunkRows * Smem::kRowFloats, bytes, &sm.full[ns]);
                 }
                 __syncwarp();
                 mbar_wait(&sm.full[s], (g_it / kStages) & 1);
                 const u64 *rows = reinterpret_cast<const u64 *>(sm.ring[s]);
+                const int rows_here = min(kChunkRows, pl.n_wspd_pad - c * kChunkRows);  // even (n_wspd_pad is a multiple of 8)
 #pragma unroll 2
-                for (int r = 0; r < kChunkRows; ++r) {
+                for (int r = 0; r < rows_here; ++r) {
                     const float2 rt = rowtab_s[c * kChunkRows + r];
                     const u64 nwh = pack2(rt.x, rt.x), w2q = pack2(rt.y, rt.y);
                     u64 L[KP];
@@ -563,6 +566,13 @@ k_scan_co(xs_plan pl, RasterArgs a, Workspace ws, double2 *out_co, int *idx_co) 
             for (int p = 0; p < P; ++p) {
                 PixelSlot &sl = sm.px[warp * P + p];
                 if (sl.state != 1) continue;  // warp-uniform
+                if (kMath == 3) {  // measurement-only variant: no refinement (results are NOT exact)
+                    if (lane == 0) {
+                        sl.idx = bchunk[p] * kChunkRows * pl.n_phi;
+                        sl.state = 2;
+                    }
+                    continue;
+                }
                 float m32 = best[p];
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) m32 = fminf(m32, __shfl_xor_sync(0xffffffffu, m32, o));
@@ -835,6 +845,7 @@ static ScanConfig scan_config(int kp) {
             case 16: return {8, 8};
             case 17: return {8, 8};
             case 18: return {4, 12};
+            case 30: return {8, 8};
             case 19: return {8, 8};
             case 20: return {8, 8};
             case 21: return {8, 8};
@@ -868,6 +879,7 @@ static int dispatch_scan(const xs_plan *pl, const RasterArgs &ra, const Workspac
                 case 16: return launch_scan<3, 8, 8, 1, 2>(pl, ra, ws, out_co, idx_co, stream);
                 case 17: return launch_scan<3, 8, 8, 1, 0>(pl, ra, ws, out_co, idx_co, stream);
                 case 18: return launch_scan<3, 4, 12, 2, 2>(pl, ra, ws, out_co, idx_co, stream);
+                case 30: return launch_scan<3, 8, 8, 2, 3>(pl, ra, ws, out_co, idx_co, stream);
                 case 19: return launch_scan<3, 8, 8, 2, 2, true>(pl, ra, ws, out_co, idx_co, stream);
                 case 20: return launch_scan<3, 8, 8, 2, 0, true>(pl, ra, ws, out_co, idx_co, stream);
                 case 21: return launch_scan<3, 8, 8, 2, 1, true>(pl, ra, ws, out_co, idx_co, stream);
@@ -976,7 +988,7 @@ extern "C" int xs_plan_create(const xs_plan_desc *d, void *stream, xs_plan **out
         const bool kp_ok = kp == 1 || kp == 2 || kp == 3 || kp == 4 || kp == 6;
         pl->kp = kp;
         pl->nph_pad = 64 * kp;
-        pl->n_wspd_pad = (d->n_wspd + kChunkRows - 1) / kChunkRows * kChunkRows;
+        pl->n_wspd_pad = (d->n_wspd + kRowPad - 1) / kRowPad * kRowPad;
         pl->fast_ok = kp_ok && std::isfinite(d->dsig_co) && d->dsig_co != 0.0 && std::isfinite(wmax) &&
                       d->n_inc <= kMaxIncBins && pl->n_wspd_pad <= 16384;
         if (pl->fast_ok) {
