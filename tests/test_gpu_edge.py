@@ -179,3 +179,47 @@ def test_fast_equals_fp64_adversarial_sweep(dev):
     assert bad.numel() == 0, f"{bad.numel()} mismatches, first {bad[:5].tolist()}"
     assert torch.equal(torch.view_as_real(a), torch.view_as_real(b))
     assert st["scan_pixels"] + st["exhaustive_pixels"] == n
+
+
+def test_cross_pol_filter_adversarial(dev, golden):
+    """The FP32 filter of the cross-pol scan against the oracle on inputs chosen to break a sloppy error bound: dsig_cr
+    from 1e-8 (SNR 100 in (1.25/SNR)**4) to 1e4, sigma0 exactly on LUT nodes (J_sig = 0), |wind_co| exactly on wspd
+    nodes, exact midpoints between nodes (ties -> first index), zero / negative / infinite dsig."""
+    torch, D, nat = dev
+    d = golden("inv_slabs")
+    gi, gwc, cr = d["inc_grid"], d["wspd_cr_grid"], d["cr_lut_db"]
+    rng = np.random.default_rng(21)
+    n = 200_000
+    b = rng.integers(0, gi.size, n)
+    inc = gi[b] + rng.uniform(-0.01, 0.01, n)
+    k = rng.integers(0, gwc.size - 1, n)
+    kind = rng.integers(0, 6, n)
+    s = rng.uniform(-45, -5, n)
+    s = np.where(kind == 0, cr[b, k], s)                                   # on a node
+    s = np.where(kind == 1, 0.5 * (cr[b, k] + cr[b, k + 1]), s)            # midpoint of two nodes
+    dsig = 10.0 ** rng.uniform(-8, 4, n)
+    dsig = np.where(kind == 2, 0.1, dsig)
+    dsig[::997] = 0.0
+    dsig[1::997] = -0.3
+    dsig[2::997] = np.inf
+    plan = D.InversionPlan(cr=(D.to_device(cr), gi, gwc))
+    _, ox, _, ix = plan.invert(D.to_device(inc), None, D.to_device(s), D.to_device(dsig), None, sigma0_db=True, want_idx=True)
+    with np.errstate(all="ignore"):
+        _, o_du, _, o_ix = oracle.invert(inc, np.nan, s, dsig, np.nan + 0j, cr_lut=cr, inc_cr_grid=gi, wspd_cr_grid=gwc)
+    assert np.array_equal(ix.cpu().numpy(), o_ix), np.flatnonzero(ix.cpu().numpy() != o_ix)[:10]
+    assert np.allclose(ox.cpu().numpy(), o_du, rtol=0, atol=1e-9, equal_nan=True)
+    # dual-pol: the first-guess term ((w - |wind_co|)/2)**2 with |wind_co| on and between nodes
+    co_lut, gw, gp = d["co_lut_db"], d["wspd_grid"], d["phi_grid"]
+    m = 60_000
+    sl = slice(0, m)
+    s_co = rng.uniform(-25, -5, m)
+    anc = rng.uniform(3, 30, m) * np.exp(1j * rng.uniform(-np.pi, np.pi, m))
+    plan2 = D.InversionPlan(co=(D.to_device(co_lut), gi, gw, gp), cr=(D.to_device(cr), gi, gwc))
+    oc, ox, ic, ix = plan2.invert(D.to_device(inc[sl]), D.to_device(s_co), D.to_device(s[sl]), D.to_device(dsig[sl]),
+                                  D.to_device(anc), sigma0_db=True, want_idx=True)
+    with np.errstate(all="ignore"):
+        o_co, o_du, o_ic, o_ix = oracle.invert(inc[sl], s_co, s[sl], dsig[sl], anc, co_lut=co_lut, inc_grid=gi, wspd_grid=gw,
+                                               phi_grid=gp, cr_lut=cr, inc_cr_grid=gi, wspd_cr_grid=gwc)
+    assert np.array_equal(ic.cpu().numpy(), o_ic)
+    bad = np.flatnonzero(ix.cpu().numpy() != o_ix)
+    assert bad.size == 0, bad[:10]

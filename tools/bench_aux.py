@@ -16,7 +16,9 @@ HBM_GBS = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED
     if os.path.exists(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")) else 6650.0
 
 
-def timeit(fn, warm=3, reps=5):
+def timeit(fn, warm=3, reps=5, inner=1):
+    """best / mean over `reps` timings of `inner` back-to-back calls (inner > 1 for sub-millisecond operations, so
+    that launch latency is not what is measured)."""
     for _ in range(warm):
         fn()
     ts = []
@@ -24,10 +26,11 @@ def timeit(fn, warm=3, reps=5):
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        fn()
+        for _ in range(inner):
+            fn()
         e1.record()
         torch.cuda.synchronize()
-        ts.append(e0.elapsed_time(e1))
+        ts.append(e0.elapsed_time(e1) / inner)
     return float(np.min(ts)), float(np.mean(ts))
 
 
@@ -61,11 +64,11 @@ H, W = 10000, 10400
 s0 = torch.rand(H, W, dtype=torch.float64, device="cuda") * 0.2 + 0.01
 prof = D.gmf_eval(nat.GMF_IDS["gmf_cmod5n"], torch.linspace(19, 47, W, dtype=torch.float64, device="cuda"),
                   torch.full((W,), 10.0, dtype=torch.float64, device="cuda"), torch.full((W,), 45.0, dtype=torch.float64, device="cuda"))
-best, mean = timeit(lambda: D.detrend(s0, prof))
+best, mean = timeit(lambda: D.detrend(s0, prof), inner=10)
 out["detrend_f64_10000x10400"] = dict(ms=best, ms_mean=mean, GBps=16 * H * W / best / 1e6, frac_of_measured_hbm=16 * H * W / best / 1e6 / HBM_GBS,
                                       Gpx_per_s=H * W / best / 1e6)
 s32 = s0.float()
-best, mean = timeit(lambda: D.detrend(s32, prof))
+best, mean = timeit(lambda: D.detrend(s32, prof), inner=10)
 out["detrend_f32_10000x10400"] = dict(ms=best, ms_mean=mean, GBps=8 * H * W / best / 1e6, frac_of_measured_hbm=8 * H * W / best / 1e6 / HBM_GBS)
 del s0, s32
 

@@ -164,11 +164,18 @@ __global__ void k_find_first_nan(xs_plan pl) {
 }
 __global__ void k_build_cr_tables(xs_plan pl) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < pl.n_wspd_cr) pl.wspd_cr_half[i] = 0.5 * pl.wspd_cr_grid[i];
+    if (i < pl.n_wspd_cr) pl.wspd_cr_half[i] = (float)(0.5 * pl.wspd_cr_grid[i]);
     if (i < pl.n_inc_cr) {
         int ok = 1;
-        for (int w = 0; w < pl.n_wspd_cr; ++w) ok &= isfinite(pl.cr_lut[(int64_t)i * pl.n_wspd_cr + w]) ? 1 : 0;
+        float amax = 0.f;
+        for (int w = 0; w < pl.n_wspd_cr; ++w) {
+            const double v = pl.cr_lut[(int64_t)i * pl.n_wspd_cr + w];
+            ok &= isfinite(v) ? 1 : 0;
+            pl.cr_scan[(int64_t)i * pl.n_wspd_cr + w] = (float)v;
+            if (isfinite(v)) amax = fmaxf(amax, (float)fabs(v) * 1.0000002f);
+        }
         pl.cr_finite[i] = ok;
+        pl.cr_absmax[i] = amax;
     }
 }
 __global__ void k_fix_first_nan(xs_plan pl) {
@@ -709,40 +716,52 @@ __global__ void __launch_bounds__(256) k_cross(xs_plan pl, RasterArgs a, int64_t
             int res = -1;
             bool settled = false;
             if (fok) {
-                // Filter pass: J' = ((L-s) * (1/dsig))^2 + (w/2 - mag/2)^2 with FMAs, within a few ulp of the
-                // reference's J (all terms are non-negative, no cancellation).  A single candidate inside a 1e-13
-                // relative band of the minimum is the argmin; several are re-evaluated in the reference's order.
-                const double r = 1.0 / dsig, mag2 = 0.5 * mg;
-                double best = CUDART_INF, second = CUDART_INF;
+                // FP32 filter pass: J32 = ((L32 - s32) * r32)^2 + (w32/2 - mag32/2)^2.  E bounds |J32 - J| (J = the
+                // reference's FP64 cost) for every candidate whose cost is within the band of the minimum, so the true
+                // argmin has J32 <= m + 2E: a single candidate in the band is the argmin, several are re-evaluated in
+                // FP64 with the reference's operation order.
+                const float *colf = pl.cr_scan + (int64_t)b * pl.n_wspd_cr;
+                const float s32 = (float)s_cr, r32 = (float)(1.0 / dsig), mg2 = hc ? (float)(0.5 * mg) : 0.f;
+                float best = CUDART_INF_F, second = CUDART_INF_F;
                 int bidx = -1;
                 for (int w = lane; w < pl.n_wspd_cr; w += 32) {
-                    const double ts = (col[w] - s_cr) * r;
-                    double J = ts * ts;
+                    const float ts = (colf[w] - s32) * r32;
+                    float J = ts * ts;
                     if (hc) {
-                        const double tw = pl.wspd_cr_half[w] - mag2;
-                        J = fma(tw, tw, J);
+                        const float tw = pl.wspd_cr_half[w] - mg2;
+                        J = fmaf(tw, tw, J);
                     }
-                    second = fmin(second, fmax(best, J));
+                    second = fminf(second, fmaxf(best, J));
                     if (J < best) {
                         best = J;
                         bidx = w;
                     }
                 }
-                double m = best;
+                float m = best;
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) m = fmin(m, __shfl_xor_sync(full, m, o));
-                const double thr = m * (1.0 + 1e-13) + 1e-290;
+                for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(full, m, o));
+                const float u = 5.9604645e-8f;
+                const float R2 = 1.01f * m + 1.0f, Rp = sqrtf(R2);
+                const float E = 1.5f * u * (2.f * Rp * fabsf(r32) * (pl.cr_absmax[b] + fabsf(s32)) * 1.0000002f +
+                                            2.f * Rp * ((float)(0.5 * pl.w_cr_absmax) + fabsf(mg2)) * 1.0000002f + 8.f * R2 + 2.f * m);
+                const float thr = m + 2.f * E;
+                const bool sane = isfinite(m) && isfinite(E) && (2.f * E <= 0.01f * m + 1.0f) && isfinite(r32);
                 const unsigned cont = __ballot_sync(full, best <= thr);
                 const unsigned wide = __ballot_sync(full, second <= thr);
-                if (!isfinite(m)) {
-                    // overflowed costs: leave it to the exhaustive pass
+                if (!sane) {
+                    // magnitudes outside the range of the bound: leave it to the exhaustive pass
                 } else if (wide == 0 && __popc(cont) == 1) {
                     res = __shfl_sync(full, bidx, __ffs(cont) - 1);
                     settled = true;
-                } else if (wide == 0 && cont != 0) {
+                } else if (cont != 0) {
                     ArgMin am;
                     am.init();
-                    if (best <= thr) am.feed(exact_cost_cr(col[bidx], s_cr, dsig, pl.wspd_cr_grid[bidx], mg, hc), bidx);
+                    if (second <= thr) {  // several contenders in this lane: all of the lane's candidates
+                        for (int w = lane; w < pl.n_wspd_cr; w += 32)
+                            am.feed(exact_cost_cr(col[w], s_cr, dsig, pl.wspd_cr_grid[w], mg, hc), w);
+                    } else if (best <= thr && bidx >= 0) {
+                        am.feed(exact_cost_cr(col[bidx], s_cr, dsig, pl.wspd_cr_grid[bidx], mg, hc), bidx);
+                    }
                     am.warp_reduce();
                     res = am.result();
                     settled = true;
@@ -922,6 +941,8 @@ extern "C" void xs_plan_destroy(xs_plan *pl) {
     cudaFree(pl->inc_cr_grid);
     cudaFree(pl->wspd_cr_grid);
     cudaFree(pl->wspd_cr_half);
+    cudaFree(pl->cr_scan);
+    cudaFree(pl->cr_absmax);
     cudaFree(pl->cr_finite);
     cudaFree(pl->stats);
     if (pl->ev_scan0) cudaEventDestroy(pl->ev_scan0);
@@ -1005,7 +1026,12 @@ extern "C" int xs_plan_create(const xs_plan_desc *d, void *stream, xs_plan **out
         pl->inc_cr_sorted = strictly_ascending(d->inc_cr_grid_host, d->n_inc_cr);
         if ((rc = upload(&pl->inc_cr_grid, d->inc_cr_grid_host, d->n_inc_cr, st)) != XS_OK) return fail(rc);
         if ((rc = upload(&pl->wspd_cr_grid, d->wspd_cr_grid_host, d->n_wspd_cr, st)) != XS_OK) return fail(rc);
-        if ((rc = xs::check(cudaMalloc(&pl->wspd_cr_half, sizeof(double) * (size_t)d->n_wspd_cr), "cudaMalloc")) != XS_OK) return fail(rc);
+        if ((rc = xs::check(cudaMalloc(&pl->wspd_cr_half, sizeof(float) * (size_t)d->n_wspd_cr), "cudaMalloc")) != XS_OK) return fail(rc);
+        if ((rc = xs::check(cudaMalloc(&pl->cr_scan, sizeof(float) * (size_t)d->n_wspd_cr * d->n_inc_cr), "cudaMalloc")) != XS_OK) return fail(rc);
+        if ((rc = xs::check(cudaMalloc(&pl->cr_absmax, sizeof(float) * (size_t)d->n_inc_cr), "cudaMalloc")) != XS_OK) return fail(rc);
+        double wcmax = 0;
+        for (int i = 0; i < d->n_wspd_cr; ++i) wcmax = fmax(wcmax, fabs(d->wspd_cr_grid_host[i]));
+        pl->w_cr_absmax = wcmax;
         if ((rc = xs::check(cudaMalloc(&pl->cr_finite, sizeof(int) * (size_t)d->n_inc_cr), "cudaMalloc")) != XS_OK) return fail(rc);
     }
     auto build = [&]() -> int {

@@ -25,7 +25,10 @@ struct xs_plan {
     int n_inc_cr, n_wspd_cr;
     const double *cr_lut;  // caller-owned [n_inc_cr][n_wspd_cr] dB
     double *inc_cr_grid, *wspd_cr_grid;
-    double *wspd_cr_half;  // [n_wspd_cr] w/2 (exact), for the filter pass of the cross-pol scan
+    float *wspd_cr_half;   // [n_wspd_cr] (float)(w/2), for the FP32 filter pass of the cross-pol scan
+    float *cr_scan;        // [n_inc_cr][n_wspd_cr] (float) LUT dB
+    float *cr_absmax;      // [n_inc_cr] max |LUT dB| of the incidence row
+    double w_cr_absmax;    // max |wspd_cr grid|
     int *cr_finite;        // [n_inc_cr] 1 if every LUT value of the incidence row is finite
     int inc_cr_sorted;
     // ---- counters of the last xs_invert (device) ----
