@@ -47,6 +47,23 @@ def peaks():
                 "148 SM x 128 lanes x 2 x 1965 MHz (fallback: MEASURED_PEAKS.json absent)")
 
 
+def profiled_traffic_per_px():
+    """DRAM bytes per pixel of k_scan_co from the committed `ncu --set full` capture (profiles/): that capture was taken
+    on `bench.py --lines 400` (10 Mpx per launch); traffic is proportional to the pixel count (rasters in, results out,
+    4 B/px of pixel list), so it is reported scaled to this run's launch size."""
+    path = os.path.join(ROOT, "profiles", "r1_k_scan_co_ncu_raw_selected.csv")
+    try:
+        vals = {}
+        for line in open(path):
+            f = line.strip().split(",")
+            if f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[f[1]]
+                vals[f[0]] = float(f[2]) * scale
+        return (vals["dram__bytes_read.sum"] + vals["dram__bytes_write.sum"]) / (400 * 25000)
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
 
@@ -303,6 +320,7 @@ def main():
     scan_avg_ms = float(np.mean(scan_ms))
     pk = peaks()
     achieved = FLOP_PER_PX * n_px / (scan_avg_ms * 1e-3) / 1e12
+    bpp = profiled_traffic_per_px()
 
     # ---- end to end through the public API with pinned host arrays ----
     e2e = None
@@ -369,7 +387,11 @@ def main():
                        "sharding": "one scene per GPU, no data-path collective", "lut_build_s": lut_s},
             "roofline": {"bound": "fp32 cuda-core (FMA pipe)", "kernel": "k_scan_co", "achieved": achieved,
                          "peak": pk["fp32_tflops"], "unit": "TFLOP/s", "frac": achieved / pk["fp32_tflops"],
-                         "traffic": None, "peak_source": pk["source"], "scan_ms_per_launch": scan_avg_ms,
+                         "traffic": None if bpp is None else bpp * n_px,
+                         "traffic_note": "DRAM read+write bytes per launch, scaled by pixel count from the ncu --set full "
+                                         "capture of a 10 Mpx launch (profiles/r1_k_scan_co_ncu_raw_selected.csv: %s B/px; "
+                                         "algorithmic 40 B/px in + 16 B/px out + 4 B/px list)" % (None if bpp is None else round(bpp, 1)),
+                         "peak_source": pk["source"], "scan_ms_per_launch": scan_avg_ms,
                          "flop_per_px": FLOP_PER_PX, "px_per_launch": n_px,
                          "share_of_step": scan_avg_ms / (ms / args.steps)},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,

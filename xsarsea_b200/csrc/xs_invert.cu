@@ -829,8 +829,10 @@ static int launch_scan(const xs_plan *pl, const RasterArgs &ra, const Workspace 
     return XS_OK;
 }
 
-// Scan configuration: pixels per warp P, warps per CTA NW, CTAs per SM MB (register budget = 64K/(NW*32*MB)).
-// XS_SCAN_VARIANT (environment) selects one of the experimental configurations for KP == 3.
+// Scan configuration: pixels per warp P, warps per CTA NW, CTAs per SM MB (register budget = 64K/(NW*32*MB)), math
+// flavour (0 packed f32x2, 1 scalar, 2 scalar t + packed d/J, 3 packed without refinement = measurement only) and
+// where the per-lane argmin bookkeeping lives.  XS_SCAN_VARIANT (environment) selects one of the experimental
+// configurations for KP == 3 that DESIGN.md section 4.1 reports on; 0 (default) is the shipped one.
 struct ScanConfig {
     int p, nw;
 };
@@ -847,27 +849,7 @@ static ScanConfig scan_config(int kp) {
     if (kp == 3) {
         switch (scan_variant()) {
             case 1: return {4, 8};
-            case 2: return {6, 8};
             case 3: return {8, 12};
-            case 4: return {8, 6};
-            case 5: return {4, 8};
-            case 6: return {6, 6};
-            case 7: return {6, 10};
-            case 8: return {8, 8};
-            case 9: return {4, 8};
-            case 10: return {8, 12};
-            case 11: return {8, 8};
-            case 12: return {8, 12};
-            case 13: return {6, 8};
-            case 14: return {4, 8};
-            case 15: return {4, 8};
-            case 16: return {8, 8};
-            case 17: return {8, 8};
-            case 18: return {4, 12};
-            case 30: return {8, 8};
-            case 19: return {8, 8};
-            case 20: return {8, 8};
-            case 21: return {8, 8};
             default: return {8, 8};
         }
     }
@@ -880,28 +862,12 @@ static int dispatch_scan(const xs_plan *pl, const RasterArgs &ra, const Workspac
         case 2: return launch_scan<2, 8, 8, 2>(pl, ra, ws, out_co, idx_co, stream);
         case 3:
             switch (scan_variant()) {
-                case 1: return launch_scan<3, 4, 8, 2>(pl, ra, ws, out_co, idx_co, stream);
-                case 2: return launch_scan<3, 6, 8, 2>(pl, ra, ws, out_co, idx_co, stream);
-                case 3: return launch_scan<3, 8, 12, 1>(pl, ra, ws, out_co, idx_co, stream);
-                case 4: return launch_scan<3, 8, 6, 2>(pl, ra, ws, out_co, idx_co, stream);
-                case 5: return launch_scan<3, 4, 8, 3>(pl, ra, ws, out_co, idx_co, stream);
-                case 6: return launch_scan<3, 6, 6, 2>(pl, ra, ws, out_co, idx_co, stream);
-                case 7: return launch_scan<3, 6, 10, 1>(pl, ra, ws, out_co, idx_co, stream);
-                case 8: return launch_scan<3, 8, 8, 2, 1>(pl, ra, ws, out_co, idx_co, stream);
-                case 9: return launch_scan<3, 4, 8, 2, 1>(pl, ra, ws, out_co, idx_co, stream);
-                case 10: return launch_scan<3, 8, 12, 1, 1>(pl, ra, ws, out_co, idx_co, stream);
-                case 11: return launch_scan<3, 8, 8, 2, 2>(pl, ra, ws, out_co, idx_co, stream);
-                case 12: return launch_scan<3, 8, 12, 1, 2>(pl, ra, ws, out_co, idx_co, stream);
-                case 13: return launch_scan<3, 6, 8, 2, 2>(pl, ra, ws, out_co, idx_co, stream);
-                case 14: return launch_scan<3, 4, 8, 2, 2>(pl, ra, ws, out_co, idx_co, stream);
-                case 15: return launch_scan<3, 4, 8, 3, 2>(pl, ra, ws, out_co, idx_co, stream);
-                case 16: return launch_scan<3, 8, 8, 1, 2>(pl, ra, ws, out_co, idx_co, stream);
-                case 17: return launch_scan<3, 8, 8, 1, 0>(pl, ra, ws, out_co, idx_co, stream);
-                case 18: return launch_scan<3, 4, 12, 2, 2>(pl, ra, ws, out_co, idx_co, stream);
-                case 30: return launch_scan<3, 8, 8, 2, 3>(pl, ra, ws, out_co, idx_co, stream);
-                case 19: return launch_scan<3, 8, 8, 2, 2, true>(pl, ra, ws, out_co, idx_co, stream);
-                case 20: return launch_scan<3, 8, 8, 2, 0, true>(pl, ra, ws, out_co, idx_co, stream);
-                case 21: return launch_scan<3, 8, 8, 2, 1, true>(pl, ra, ws, out_co, idx_co, stream);
+                case 1: return launch_scan<3, 4, 8, 2>(pl, ra, ws, out_co, idx_co, stream);           // P = 4
+                case 3: return launch_scan<3, 8, 12, 1>(pl, ra, ws, out_co, idx_co, stream);          // 12 warps, 168 regs
+                case 8: return launch_scan<3, 8, 8, 2, 1>(pl, ra, ws, out_co, idx_co, stream);        // scalar math
+                case 11: return launch_scan<3, 8, 8, 2, 2>(pl, ra, ws, out_co, idx_co, stream);       // hybrid math
+                case 20: return launch_scan<3, 8, 8, 2, 0, true>(pl, ra, ws, out_co, idx_co, stream); // smem bookkeeping
+                case 30: return launch_scan<3, 8, 8, 2, 3>(pl, ra, ws, out_co, idx_co, stream);       // NOT exact: no refinement
                 default: return launch_scan<3, 8, 8, 2>(pl, ra, ws, out_co, idx_co, stream);
             }
         case 4: return launch_scan<4, 4, 8, 1>(pl, ra, ws, out_co, idx_co, stream);
