@@ -46,4 +46,5 @@ for dual in (False, True):
         st = plan.last_stats()
         print(json.dumps(dict(dual=dual, H=H, W=W, ms=ms, Mpx_s=H * W / ms / 1e3, **st,
                               frac_fp32_peak=H * W * (727178 if dual else 722552) / (ms * 1e-3) / 74.4e12)), flush=True)
+print("debug counters", plan.debug_counters())
 print("mean |co|", torch.nanmean(oc.abs()).item(), "launches", nat.launch_count())

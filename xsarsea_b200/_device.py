@@ -224,6 +224,11 @@ class InversionPlan:
         nat.check(nat.load().xs_plan_last_scan_ms(self._handle, ctypes.byref(ms)), "xs_plan_last_scan_ms")
         return float(ms.value)
 
+    def debug_counters(self):
+        c = (ctypes.c_uint64 * 8)()
+        nat.check(nat.load().xs_plan_debug_counters(self._handle, c), "xs_plan_debug_counters")
+        return [int(v) for v in c]
+
     def last_stats(self):
         s = (ctypes.c_int64 * 4)()
         nat.check(nat.load().xs_plan_last_stats(self._handle, s), "xs_plan_last_stats")

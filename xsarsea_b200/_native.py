@@ -40,7 +40,7 @@ GMF_IDS = {
 EXPORTS = [
     "xs_abi_version", "xs_last_error", "xs_launch_count", "xs_gmf_eval", "xs_lut_build", "xs_lut_interp_axis",
     "xs_lut_to_db", "xs_lut_to_linear", "xs_plan_create", "xs_plan_destroy", "xs_invert_workspace_bytes",
-    "xs_invert", "xs_plan_last_stats", "xs_plan_last_scan_ms", "xs_detrend",
+    "xs_invert", "xs_plan_last_stats", "xs_plan_last_scan_ms", "xs_plan_debug_counters", "xs_detrend",
 ]
 
 
@@ -147,6 +147,8 @@ def load():
         L.xs_plan_last_stats.argtypes = [vp, ctypes.POINTER(i64)]
         L.xs_plan_last_scan_ms.restype = i32
         L.xs_plan_last_scan_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_float)]
+        L.xs_plan_debug_counters.restype = i32
+        L.xs_plan_debug_counters.argtypes = [vp, ctypes.POINTER(ctypes.c_uint64)]
         L.xs_detrend.restype = i32
         L.xs_detrend.argtypes = [vp, vp, i64, i64, i32, vp, vp]
         if L.xs_abi_version() != 1:

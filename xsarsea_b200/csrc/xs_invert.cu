@@ -344,6 +344,16 @@ struct ScanSmem {
     int bchunk[P][NW * 32];
 };
 
+// kMath == 4: instrumented build (clock64 per phase, summed over warps into ws.counters[4..7]); math as flavour 0
+#define XS_TICK(slot)                                              \
+    do {                                                           \
+        if (kMath == 4) {                                          \
+            const long long _now = clock64();                      \
+            if (lane == 0) t_acc[slot] += (u64)(_now - t_last);    \
+            t_last = _now;                                         \
+        }                                                          \
+    } while (0)
+
 template <int KP, int P, int NW, int MB, int kMath = 0, bool kBookSmem = false>
 __global__ void __launch_bounds__(NW * 32, MB)
 k_scan_co(xs_plan pl, RasterArgs a, Workspace ws, double2 *out_co, int *idx_co) {
@@ -370,6 +380,8 @@ k_scan_co(xs_plan pl, RasterArgs a, Workspace ws, double2 *out_co, int *idx_co) 
     unsigned it = 0;  // chunks consumed so far by this CTA (ring position, continues across tiles)
     u64 n_scanned = 0, n_refined = 0;
 
+    u64 t_acc[4] = {0, 0, 0, 0};  // prologue (incl. barriers), main loop, refinement, write-out (incl. barrier)
+    long long t_last = clock64();
     for (unsigned tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         // tile -> (bin, pixel range): last bin with tile_start[bin] <= tile
         int lo = 0, hi = pl.n_inc;
@@ -479,7 +491,8 @@ k_scan_co(xs_plan pl, RasterArgs a, Workspace ws, double2 *out_co, int *idx_co) 
                     bulk_g2s(sm.ring[s], slab + (int64_t)c * kChunkRows * Smem::kRowFloats, bytes, &sm.full[s]);
                 }
             }
-            // ---- main loop over 8-row chunks ----
+            XS_TICK(0);
+            // ---- main loop over 16-row chunks ----
             for (int c = 0; c < n_chunks; ++c) {
                 const unsigned g_it = it + c;
                 const int s = g_it % kStages;
@@ -557,6 +570,7 @@ k_scan_co(xs_plan pl, RasterArgs a, Workspace ws, double2 *out_co, int *idx_co) 
                 }
             }
             it += n_chunks;
+            XS_TICK(1);
             if (kBookSmem) {
 #pragma unroll
                 for (int p = 0; p < P; ++p) {
@@ -641,6 +655,7 @@ k_scan_co(xs_plan pl, RasterArgs a, Workspace ws, double2 *out_co, int *idx_co) 
                 ++n_scanned;
             }
         }
+        XS_TICK(2);
         __syncthreads();
         // ---- write results / queue leftovers ----
         if (threadIdx.x < TP) {
@@ -650,10 +665,13 @@ k_scan_co(xs_plan pl, RasterArgs a, Workspace ws, double2 *out_co, int *idx_co) 
             else if (sl.state == 3)
                 ws.fallback[atomicAdd(&ws.counters[1], 1ull)] = sl.px;
         }
+        XS_TICK(3);
     }
     if (lane == 0) {
         if (n_scanned) atomicAdd(&ws.counters[2], n_scanned);
         if (n_refined) atomicAdd(&ws.counters[3], n_refined);
+        if (kMath == 4)
+            for (int k = 0; k < 4; ++k) atomicAdd(&ws.counters[4 + k], t_acc[k]);
     }
 }
 
@@ -868,6 +886,7 @@ static int dispatch_scan(const xs_plan *pl, const RasterArgs &ra, const Workspac
                 case 11: return launch_scan<3, 8, 8, 2, 2>(pl, ra, ws, out_co, idx_co, stream);       // hybrid math
                 case 20: return launch_scan<3, 8, 8, 2, 0, true>(pl, ra, ws, out_co, idx_co, stream); // smem bookkeeping
                 case 30: return launch_scan<3, 8, 8, 2, 3>(pl, ra, ws, out_co, idx_co, stream);       // NOT exact: no refinement
+                case 40: return launch_scan<3, 8, 8, 2, 4>(pl, ra, ws, out_co, idx_co, stream);       // phase timers
                 default: return launch_scan<3, 8, 8, 2>(pl, ra, ws, out_co, idx_co, stream);
             }
         case 4: return launch_scan<4, 4, 8, 1>(pl, ra, ws, out_co, idx_co, stream);
@@ -1119,6 +1138,13 @@ extern "C" int xs_plan_last_scan_ms(const xs_plan *pl, float *ms) {
     }
     XS_CUDA(cudaEventSynchronize(pl->ev_scan1));
     XS_CUDA(cudaEventElapsedTime(ms, pl->ev_scan0, pl->ev_scan1));
+    return XS_OK;
+}
+
+// Raw device counters of the last xs_invert (development aid; layout in the Workspace comment above).
+extern "C" int xs_plan_debug_counters(const xs_plan *pl, unsigned long long out[8]) {
+    if (!pl || !out) return XS_E_INVALID;
+    XS_CUDA(cudaMemcpy(out, pl->stats, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     return XS_OK;
 }
 
