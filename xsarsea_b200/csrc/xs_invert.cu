@@ -54,6 +54,12 @@ __device__ __forceinline__ float fmin3(float a, float b, float c) {
     return d;
 }
 
+// g(phi) = a cos(phi) + b sin(phi) rounded to FP32; one definition so that the scan and the refinement that re-creates
+// the scan's FP32 costs use bit-identical values
+__device__ __forceinline__ float g32(double qa, double qb, double c, double s) {
+    return (float)__fma_rn(qa, c, __dmul_rn(qb, s));
+}
+
 // ---- mbarrier / bulk-async copy (TMA) ----------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
@@ -85,9 +91,9 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
 
 // ---- workspace layout ----------------------------------------------------------------------------------------
 // counters (u64): [0] n_tiles, [1] fallback count, [2] pixels scanned by k_scan_co, [3] chunks re-evaluated in
-// FP64, [4] tiles skipped through the NaN-slab shortcut
+// FP64, [4..7] phase timers of the instrumented variant, [8] dynamic tile counter
 struct Workspace {
-    u64 *counters;         // [8]
+    u64 *counters;         // [16]
     unsigned *hist;        // [n_inc]
     unsigned *bin_start;   // [n_inc + 1]
     unsigned *cursor;      // [n_inc]
@@ -103,7 +109,7 @@ static size_t ws_layout(int n_inc, int64_t n_px, char *base, Workspace *w) {
         off += align_up(bytes, 256);
         return p;
     };
-    char *c = take(8 * sizeof(u64));
+    char *c = take(16 * sizeof(u64));
     char *h = take(sizeof(unsigned) * (size_t)(n_inc + 1));
     char *bs = take(sizeof(unsigned) * (size_t)(n_inc + 1));
     char *cu = take(sizeof(unsigned) * (size_t)(n_inc + 1));
@@ -326,7 +332,7 @@ struct PixelSlot {  // per-pixel state kept in shared memory during a tile
     unsigned px;
     int state;  // 0: empty slot, 1: scan, 2: result known (NaN-slab shortcut), 3: exhaustive FP64 needed
     int idx;
-    int pad;
+    float amag;  // |ancillary| rounded up (error-bound input)
 };
 
 template <int KP, int P, int NW>
@@ -337,6 +343,7 @@ struct ScanSmem {
     alignas(16) uint64_t full[kStages];
     alignas(16) uint64_t empty[kStages];
     PixelSlot px[NW * P];
+    unsigned next_tile;
     // per-thread argmin bookkeeping, touched once per chunk: kept out of the register file so that the inner loop has
     // registers left for instruction-level parallelism ([pixel][thread]: conflict-free)
     float best[P][NW * 32];
@@ -382,7 +389,14 @@ k_scan_co(xs_plan pl, RasterArgs a, Workspace ws, double2 *out_co, int *idx_co) 
 
     u64 t_acc[4] = {0, 0, 0, 0};  // prologue (incl. barriers), main loop, refinement, write-out (incl. barrier)
     long long t_last = clock64();
-    for (unsigned tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    // Tiles are handed out dynamically (one atomic per tile): CTAs do not all progress at the same speed, and a static
+    // round-robin left ~13 % of the SM time idle at the end of the kernel.
+    for (;;) {
+        __syncthreads();  // previous tile's slots and sm.next_tile are no longer read
+        if (threadIdx.x == 0) sm.next_tile = (unsigned)atomicAdd(&ws.counters[8], 1ull);
+        __syncthreads();
+        const unsigned tile = sm.next_tile;
+        if (tile >= n_tiles) break;
         // tile -> (bin, pixel range): last bin with tile_start[bin] <= tile
         int lo = 0, hi = pl.n_inc;
         while (hi - lo > 1) {
@@ -398,14 +412,13 @@ k_scan_co(xs_plan pl, RasterArgs a, Workspace ws, double2 *out_co, int *idx_co) 
         const int nan_idx = pl.first_nan[bin];
 
         // ---- load the tile's pixels (one thread per pixel) ----
-        __syncthreads();  // previous tile's slots are no longer read
         if (threadIdx.x < TP) {
             PixelSlot sl;
             sl.state = 0;
             sl.px = 0;
             sl.idx = -1;
             sl.qa = sl.qb = sl.s = sl.anc_im = 0.0;
-            sl.pad = 0;
+            sl.amag = 0.f;
             const unsigned e = first + threadIdx.x;
             if (e < last) {
                 const unsigned px = ws.list[e];
@@ -415,6 +428,7 @@ k_scan_co(xs_plan pl, RasterArgs a, Workspace ws, double2 *out_co, int *idx_co) 
                 sl.anc_im = p.anc.y;
                 sl.qb = pl.phi_180 ? fabs(p.anc.y) : p.anc.y;
                 sl.s = p.s_co;
+                sl.amag = (float)hypot(sl.qa, sl.qb) * 1.0000002f;
                 const bool finite_q = isfinite(sl.qa) && isfinite(sl.qb) && isfinite(sl.s);
                 if (!finite_q)
                     sl.state = 3;
@@ -448,8 +462,8 @@ k_scan_co(xs_plan pl, RasterArgs a, Workspace ws, double2 *out_co, int *idx_co) 
                 for (int p = 0; p < P; ++p) {
                     const PixelSlot &sl = sm.px[warp * P + p];
                     const bool on = sl.state == 1;
-                    const float g0 = on ? (float)(sl.qa * c0 + sl.qb * s0) : 0.f;
-                    const float g1 = on ? (float)(sl.qa * c1 + sl.qb * s1) : 0.f;
+                    const float g0 = on ? g32(sl.qa, sl.qb, c0, s0) : 0.f;
+                    const float g1 = on ? g32(sl.qa, sl.qb, c1, s1) : 0.f;
                     g[p][j] = pack2(g0, g1);
                 }
             }
@@ -580,77 +594,156 @@ k_scan_co(xs_plan pl, RasterArgs a, Workspace ws, double2 *out_co, int *idx_co) 
                 }
             }
 
-            // ---- settle each pixel: warp-shuffle min, FP64 re-evaluation inside the error band ----
+            // ---- settle the warp's pixels ---------------------------------------------------------------------
+            // m32 = warp-shuffle min of the FP32 costs; E bounds |J'_fp32 - J'_exact| for every candidate that can still
+            // win, so the reference's FP64 argmin lies in S = {c : J'_fp32(c) <= m32 + 2E}.  S is collected by
+            // re-creating the FP32 costs (bit-identical operations) of the (lane, chunk) cells whose minimum is inside
+            // the band.  |S| = 1 settles the pixel with no FP64 work (9 pixels in 10); otherwise the members of S are
+            // evaluated in FP64 with the reference's operation order and reduced lexicographically on (J, flat index).
+            // The work is organised in phases across the P pixels so that their dependent loads overlap.
             const double *slab64 = pl.co_lut + (int64_t)bin * pl.n_wspd * pl.n_phi;
+            const float *slab32 = pl.scan + (int64_t)bin * pl.n_wspd_pad * pl.nph_pad;
             const float lmax = pl.slab_absmax[bin];
+            constexpr int kCand = kChunkRows * 2 * KP;  // candidates of one (lane, chunk) cell
+            constexpr int kIter = (kCand + 31) / 32;
+
+            // FP32 cost of candidate k of cell (L, row0) for pixel slot sl, exactly as the scan computed it
+            auto member = [&](const PixelSlot &sl, float nq, float thr, int L, int row0, int k, int n_cand, int &flat) {
+                const int iw = row0 + k / (2 * KP);
+                const int slot = k % (2 * KP);
+                const int ip = 2 * (L + 32 * (slot >> 1)) + (slot & 1);
+                flat = iw * pl.n_phi + ip;
+                if (k >= n_cand || iw >= pl.n_wspd || ip >= pl.n_phi) return false;
+                const float2 rt = rowtab_s[iw];
+                const float d = __fadd_rn(slab32[(int64_t)iw * pl.nph_pad + ip], nq);
+                const float t = __fmaf_rn(rt.x, g32(sl.qa, sl.qb, pl.cos_phi[ip], pl.sin_phi[ip]), rt.y);
+                return __fmaf_rn(d, d, t) <= thr;
+            };
+
+            // phase A: band of every pixel, contender masks
+            float thr[P];
+            unsigned cont[P], wide[P];
+            bool act[P];
 #pragma unroll
             for (int p = 0; p < P; ++p) {
                 PixelSlot &sl = sm.px[warp * P + p];
-                if (sl.state != 1) continue;  // warp-uniform
+                act[p] = sl.state == 1;  // warp-uniform
+                cont[p] = wide[p] = 0;
+                thr[p] = 0.f;
+                if (!act[p]) continue;
                 if (kMath == 3) {  // measurement-only variant: no refinement (results are NOT exact)
                     if (lane == 0) {
                         sl.idx = bchunk[p] * kChunkRows * pl.n_phi;
                         sl.state = 2;
                     }
+                    act[p] = false;
                     continue;
                 }
                 float m32 = best[p];
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) m32 = fminf(m32, __shfl_xor_sync(0xffffffffu, m32, o));
-                // rigorous bound E on |J'_fp32 - J'_exact| for every candidate that can still win
-                const float A = (float)hypot(sl.qa, sl.qb) * 1.0000002f;
+                // rigorous bound E
+                const float A = sl.amag;
                 const float W = (float)pl.w_absmax * 1.0000002f;
                 const float T = W * A + 0.25f * W * W;
                 const float D = sqrtf(fmaxf(m32, 0.f) + 0.25f * A * A + 1.0f);
                 const float Q = fabsf(nqs[p]);
                 const float E = 5.9604645e-8f * 1.5f * (3.f * T + 2.f * D * (lmax + Q + D) + (fabsf(m32) + 0.25f * A * A + T));
-                const float thr = m32 + 2.f * E;
+                thr[p] = m32 + 2.f * E;
                 const bool sane = (E < 0.25f) && (m32 < CUDART_INF_F);
                 if (!sane) {  // warp-uniform: magnitudes outside the range the error bound was derived for
                     if (lane == 0) sl.state = 3;
+                    act[p] = false;
                     continue;
                 }
-                unsigned cont = __ballot_sync(0xffffffffu, best[p] <= thr);
-                // lanes holding two or more chunks inside the band: every candidate of the lane is re-evaluated
-                unsigned wide = __ballot_sync(0xffffffffu, second[p] <= thr);
-                cont &= ~wide;
-                ArgMin am;
-                am.init();
-                while (wide) {
-                    const int L = __ffs(wide) - 1;
-                    wide &= wide - 1;
-                    for (int k = lane; k < pl.n_wspd * 2 * KP; k += 32) {
-                        const int iw = k / (2 * KP);
-                        const int slot = k % (2 * KP);
-                        const int ip = 2 * (L + 32 * (slot >> 1)) + (slot & 1);
-                        if (ip < pl.n_phi) {
-                            const double J = exact_cost_co(pl.wspd_grid[iw], pl.cos_phi[ip], pl.sin_phi[ip],
-                                                           slab64[(int64_t)iw * pl.n_phi + ip], sl.qa, sl.qb, sl.s, pl.dsig_co);
-                            am.feed(J, iw * pl.n_phi + ip);
-                        }
-                    }
-                    n_refined += n_chunks;
+                cont[p] = __ballot_sync(0xffffffffu, best[p] <= thr[p]);
+                // lanes holding two or more chunks inside the band: all of the lane's candidates are looked at
+                wide[p] = __ballot_sync(0xffffffffu, second[p] <= thr[p]);
+                cont[p] &= ~wide[p];
+            }
+            // phase B: membership in S of the candidates of the first contender cell of every pixel (loads batched)
+            bool in0[P][kIter];
+            int flat0[P][kIter];
+            unsigned rest[P];  // contender cells not looked at yet
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+                rest[p] = cont[p];
+#pragma unroll
+                for (int q = 0; q < kIter; ++q) {
+                    in0[p][q] = false;
+                    flat0[p][q] = 0;
                 }
-                while (cont) {
-                    const int L = __ffs(cont) - 1;
-                    cont &= cont - 1;
-                    const int ch = __shfl_sync(0xffffffffu, bchunk[p], L);
-                    for (int k = lane; k < kChunkRows * 2 * KP; k += 32) {
-                        const int iw = ch * kChunkRows + k / (2 * KP);
-                        const int slot = k % (2 * KP);
-                        const int ip = 2 * (L + 32 * (slot >> 1)) + (slot & 1);
-                        if (iw < pl.n_wspd && ip < pl.n_phi) {
-                            const double J = exact_cost_co(pl.wspd_grid[iw], pl.cos_phi[ip], pl.sin_phi[ip],
-                                                           slab64[(int64_t)iw * pl.n_phi + ip], sl.qa, sl.qb, sl.s, pl.dsig_co);
-                            am.feed(J, iw * pl.n_phi + ip);
-                        }
-                    }
+                if (act[p] && cont[p]) {  // warp-uniform
+                    const int L = __ffs(cont[p]) - 1;
+                    rest[p] &= rest[p] - 1;
+                    const int row0 = __shfl_sync(0xffffffffu, bchunk[p], L) * kChunkRows;
+#pragma unroll
+                    for (int q = 0; q < kIter; ++q)
+                        in0[p][q] = member(sm.px[warp * P + p], nqs[p], thr[p], L, row0, lane + 32 * q, kCand, flat0[p][q]);
                     ++n_refined;
                 }
-                am.warp_reduce();
+            }
+            // phase C: count the members, look at the remaining cells (rare), settle
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+                if (!act[p]) continue;
+                PixelSlot &sl = sm.px[warp * P + p];
+                int n_in = 0, one_idx = -1;
+#pragma unroll
+                for (int q = 0; q < kIter; ++q) {
+                    const unsigned mk = __ballot_sync(0xffffffffu, in0[p][q]);
+                    if (mk) {
+                        n_in += __popc(mk);
+                        one_idx = __shfl_sync(0xffffffffu, flat0[p][q], __ffs(mk) - 1);
+                    }
+                }
+                ArgMin am;
+                am.init();
+                // generic walk over cell (L, row0, n_cand): count members (exact == false) or FP64 argmin (true)
+                auto visit = [&](int L, int row0, int n_cand, bool exact) {
+                    for (int k0 = 0; k0 < n_cand; k0 += 32) {
+                        int flat;
+                        const bool in = member(sl, nqs[p], thr[p], L, row0, k0 + lane, n_cand, flat);
+                        if (!exact) {
+                            const unsigned mk = __ballot_sync(0xffffffffu, in);
+                            if (mk) {
+                                n_in += __popc(mk);
+                                one_idx = __shfl_sync(0xffffffffu, flat, __ffs(mk) - 1);
+                            }
+                        } else if (in) {
+                            const int iw = flat / pl.n_phi, ip = flat - iw * pl.n_phi;
+                            am.feed(exact_cost_co(pl.wspd_grid[iw], pl.cos_phi[ip], pl.sin_phi[ip], slab64[flat], sl.qa, sl.qb,
+                                                  sl.s, pl.dsig_co), flat);
+                        }
+                    }
+                };
+                auto sweep = [&](unsigned cells, unsigned lanes, bool exact) {
+                    while (cells) {
+                        const int L = __ffs(cells) - 1;
+                        cells &= cells - 1;
+                        visit(L, __shfl_sync(0xffffffffu, bchunk[p], L) * kChunkRows, kCand, exact);
+                        if (!exact) ++n_refined;
+                    }
+                    while (lanes) {
+                        const int L = __ffs(lanes) - 1;
+                        lanes &= lanes - 1;
+                        visit(L, 0, pl.n_wspd * 2 * KP, exact);
+                        if (!exact) n_refined += n_chunks;
+                    }
+                };
+                if (rest[p] | wide[p]) sweep(rest[p], wide[p], false);
+                int result = one_idx;
+                if (n_in > 1) {
+                    sweep(cont[p], wide[p], true);
+                    am.warp_reduce();
+                    result = am.result();
+                }
                 if (lane == 0) {
-                    sl.idx = am.result();
-                    sl.state = 2;
+                    if (n_in >= 1) {
+                        sl.idx = result;
+                        sl.state = 2;
+                    } else
+                        sl.state = 3;  // cannot happen if the re-created costs equal the scan's; be safe
                 }
                 ++n_scanned;
             }
