@@ -335,20 +335,29 @@ struct PixelSlot {  // per-pixel state kept in shared memory during a tile
     float amag;  // |ancillary| rounded up (error-bound input)
 };
 
-template <int KP, int P, int NW>
+template <int P, int NT, bool ON>
+struct BookSmem {  // per-thread argmin bookkeeping in shared memory (experimental variant)
+    float best[P][NT];
+    float second[P][NT];
+    int bchunk[P][NT];
+};
+template <int P, int NT>
+struct BookSmem<P, NT, false> {
+    float best[1][1];
+    float second[1][1];
+    int bchunk[1][1];
+};
+
+template <int KP, int P, int NW, int NS, bool BK>
 struct ScanSmem {
     static constexpr int kRowFloats = 64 * KP;
     static constexpr int kChunkBytes = kChunkRows * kRowFloats * 4;
-    alignas(128) float ring[kStages][kChunkRows * kRowFloats];
-    alignas(16) uint64_t full[kStages];
-    alignas(16) uint64_t empty[kStages];
+    alignas(128) float ring[NS][kChunkRows * kRowFloats];
+    alignas(16) uint64_t full[NS];
+    alignas(16) uint64_t empty[NS];
     PixelSlot px[NW * P];
     unsigned next_tile;
-    // per-thread argmin bookkeeping, touched once per chunk: kept out of the register file so that the inner loop has
-    // registers left for instruction-level parallelism ([pixel][thread]: conflict-free)
-    float best[P][NW * 32];
-    float second[P][NW * 32];
-    int bchunk[P][NW * 32];
+    BookSmem<P, NW * 32, BK> book;
 };
 
 // kMath == 4: instrumented build (clock64 per phase, summed over warps into ws.counters[4..7]); math as flavour 0
@@ -361,11 +370,11 @@ struct ScanSmem {
         }                                                          \
     } while (0)
 
-template <int KP, int P, int NW, int MB, int kMath = 0, bool kBookSmem = false>
+template <int KP, int P, int NW, int MB, int kMath = 0, bool kBookSmem = false, int NS = kStages>
 __global__ void __launch_bounds__(NW * 32, MB)
 k_scan_co(xs_plan pl, RasterArgs a, Workspace ws, double2 *out_co, int *idx_co) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    using Smem = ScanSmem<KP, P, NW>;
+    using Smem = ScanSmem<KP, P, NW, NS, kBookSmem>;
     Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
     float2 *rowtab_s = reinterpret_cast<float2 *>(smem_raw + sizeof(Smem));  // [n_wspd_pad]
 
@@ -373,7 +382,7 @@ k_scan_co(xs_plan pl, RasterArgs a, Workspace ws, double2 *out_co, int *idx_co) 
     constexpr int TP = NW * P;  // pixels per tile
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; ++s) {
+        for (int s = 0; s < NS; ++s) {
             mbar_init(&sm.full[s], 1);
             mbar_init(&sm.empty[s], NW);
         }
@@ -478,9 +487,9 @@ k_scan_co(xs_plan pl, RasterArgs a, Workspace ws, double2 *out_co, int *idx_co) 
             for (int p = 0; p < P; ++p) {
                 m[p] = CUDART_INF_F;
                 if (kBookSmem) {
-                    sm.best[p][threadIdx.x] = CUDART_INF_F;
-                    sm.second[p][threadIdx.x] = CUDART_INF_F;
-                    sm.bchunk[p][threadIdx.x] = 0;
+                    sm.book.best[kBookSmem ? p : 0][kBookSmem ? threadIdx.x : 0] = CUDART_INF_F;
+                    sm.book.second[kBookSmem ? p : 0][kBookSmem ? threadIdx.x : 0] = CUDART_INF_F;
+                    sm.book.bchunk[kBookSmem ? p : 0][kBookSmem ? threadIdx.x : 0] = 0;
                 }
             }
             float best[P], second[P];
@@ -495,11 +504,11 @@ k_scan_co(xs_plan pl, RasterArgs a, Workspace ws, double2 *out_co, int *idx_co) 
             const float *slab = pl.scan + (int64_t)bin * pl.n_wspd_pad * pl.nph_pad;
             // ---- producer prologue: fill the ring ----
             if (threadIdx.x == 0) {
-                const int pre = min(kStages - 1, n_chunks);
+                const int pre = min(NS - 1, n_chunks);
                 for (int c = 0; c < pre; ++c) {
                     const unsigned g_it = it + c;
-                    const int s = g_it % kStages;
-                    if (g_it >= kStages) mbar_wait(&sm.empty[s], ((g_it / kStages) - 1) & 1);
+                    const int s = g_it % NS;
+                    if (g_it >= NS) mbar_wait(&sm.empty[s], ((g_it / NS) - 1) & 1);
                     const uint32_t bytes = (uint32_t)min(kChunkRows, pl.n_wspd_pad - c * kChunkRows) * Smem::kRowFloats * 4;
                     mbar_expect_tx(&sm.full[s], bytes);
                     bulk_g2s(sm.ring[s], slab + (int64_t)c * kChunkRows * Smem::kRowFloats, bytes, &sm.full[s]);
@@ -509,18 +518,18 @@ k_scan_co(xs_plan pl, RasterArgs a, Workspace ws, double2 *out_co, int *idx_co) 
             // ---- main loop over 16-row chunks ----
             for (int c = 0; c < n_chunks; ++c) {
                 const unsigned g_it = it + c;
-                const int s = g_it % kStages;
-                if (threadIdx.x == 0 && c + kStages - 1 < n_chunks) {  // refill the slot consumed last iteration
-                    const unsigned n_it = g_it + kStages - 1;
-                    const int ns = n_it % kStages;
-                    if (n_it >= kStages) mbar_wait(&sm.empty[ns], ((n_it / kStages) - 1) & 1);
-                    const int nc = c + kStages - 1;
+                const int s = g_it % NS;
+                if (threadIdx.x == 0 && c + NS - 1 < n_chunks) {  // refill the slot consumed last iteration
+                    const unsigned n_it = g_it + NS - 1;
+                    const int ns = n_it % NS;
+                    if (n_it >= NS) mbar_wait(&sm.empty[ns], ((n_it / NS) - 1) & 1);
+                    const int nc = c + NS - 1;
                     const uint32_t bytes = (uint32_t)min(kChunkRows, pl.n_wspd_pad - nc * kChunkRows) * Smem::kRowFloats * 4;
                     mbar_expect_tx(&sm.full[ns], bytes);
                     bulk_g2s(sm.ring[ns], slab + (int64_t)nc * kChunkRows * Smem::kRowFloats, bytes, &sm.full[ns]);
                 }
                 __syncwarp();
-                mbar_wait(&sm.full[s], (g_it / kStages) & 1);
+                mbar_wait(&sm.full[s], (g_it / NS) & 1);
                 const u64 *rows = reinterpret_cast<const u64 *>(sm.ring[s]);
                 const int rows_here = min(kChunkRows, pl.n_wspd_pad - c * kChunkRows);  // even (n_wspd_pad is a multiple of 8)
 #pragma unroll 2
@@ -568,11 +577,11 @@ k_scan_co(xs_plan pl, RasterArgs a, Workspace ws, double2 *out_co, int *idx_co) 
 #pragma unroll
                 for (int p = 0; p < P; ++p) {
                     if (kBookSmem) {
-                        const float b = sm.best[p][threadIdx.x];
-                        sm.second[p][threadIdx.x] = fminf(sm.second[p][threadIdx.x], fmaxf(b, m[p]));
+                        const float b = sm.book.best[kBookSmem ? p : 0][kBookSmem ? threadIdx.x : 0];
+                        sm.book.second[kBookSmem ? p : 0][kBookSmem ? threadIdx.x : 0] = fminf(sm.book.second[kBookSmem ? p : 0][kBookSmem ? threadIdx.x : 0], fmaxf(b, m[p]));
                         if (m[p] < b) {
-                            sm.best[p][threadIdx.x] = m[p];
-                            sm.bchunk[p][threadIdx.x] = c;
+                            sm.book.best[kBookSmem ? p : 0][kBookSmem ? threadIdx.x : 0] = m[p];
+                            sm.book.bchunk[kBookSmem ? p : 0][kBookSmem ? threadIdx.x : 0] = c;
                         }
                     } else {
                         const bool lt = m[p] < best[p];
@@ -588,9 +597,9 @@ k_scan_co(xs_plan pl, RasterArgs a, Workspace ws, double2 *out_co, int *idx_co) 
             if (kBookSmem) {
 #pragma unroll
                 for (int p = 0; p < P; ++p) {
-                    best[p] = sm.best[p][threadIdx.x];
-                    second[p] = sm.second[p][threadIdx.x];
-                    bchunk[p] = sm.bchunk[p][threadIdx.x];
+                    best[p] = sm.book.best[kBookSmem ? p : 0][kBookSmem ? threadIdx.x : 0];
+                    second[p] = sm.book.second[kBookSmem ? p : 0][kBookSmem ? threadIdx.x : 0];
+                    bchunk[p] = sm.book.bchunk[kBookSmem ? p : 0][kBookSmem ? threadIdx.x : 0];
                 }
             }
 
@@ -688,29 +697,27 @@ k_scan_co(xs_plan pl, RasterArgs a, Workspace ws, double2 *out_co, int *idx_co) 
             for (int p = 0; p < P; ++p) {
                 if (!act[p]) continue;
                 PixelSlot &sl = sm.px[warp * P + p];
-                int n_in = 0, one_idx = -1;
+                // members of S seen by this lane so far (count, and the flat index of one of them)
+                int n_loc = 0, one_loc = -1;
 #pragma unroll
-                for (int q = 0; q < kIter; ++q) {
-                    const unsigned mk = __ballot_sync(0xffffffffu, in0[p][q]);
-                    if (mk) {
-                        n_in += __popc(mk);
-                        one_idx = __shfl_sync(0xffffffffu, flat0[p][q], __ffs(mk) - 1);
+                for (int q = 0; q < kIter; ++q)
+                    if (in0[p][q]) {
+                        ++n_loc;
+                        one_loc = flat0[p][q];
                     }
-                }
                 ArgMin am;
                 am.init();
-                // generic walk over cell (L, row0, n_cand): count members (exact == false) or FP64 argmin (true)
+                // generic walk over cell (L, row0, n_cand): note members (exact == false) or FP64 argmin (true);
+                // no warp synchronisation inside, so the loads of successive iterations overlap
                 auto visit = [&](int L, int row0, int n_cand, bool exact) {
                     for (int k0 = 0; k0 < n_cand; k0 += 32) {
                         int flat;
                         const bool in = member(sl, nqs[p], thr[p], L, row0, k0 + lane, n_cand, flat);
+                        if (!in) continue;
                         if (!exact) {
-                            const unsigned mk = __ballot_sync(0xffffffffu, in);
-                            if (mk) {
-                                n_in += __popc(mk);
-                                one_idx = __shfl_sync(0xffffffffu, flat, __ffs(mk) - 1);
-                            }
-                        } else if (in) {
+                            ++n_loc;
+                            one_loc = flat;
+                        } else {
                             const int iw = flat / pl.n_phi, ip = flat - iw * pl.n_phi;
                             am.feed(exact_cost_co(pl.wspd_grid[iw], pl.cos_phi[ip], pl.sin_phi[ip], slab64[flat], sl.qa, sl.qb,
                                                   sl.s, pl.dsig_co), flat);
@@ -732,7 +739,8 @@ k_scan_co(xs_plan pl, RasterArgs a, Workspace ws, double2 *out_co, int *idx_co) 
                     }
                 };
                 if (rest[p] | wide[p]) sweep(rest[p], wide[p], false);
-                int result = one_idx;
+                const int n_in = __reduce_add_sync(0xffffffffu, n_loc);
+                int result = __reduce_max_sync(0xffffffffu, one_loc);  // the member itself when n_in == 1
                 if (n_in > 1) {
                     sweep(cont[p], wide[p], true);
                     am.warp_reduce();
@@ -918,13 +926,13 @@ __global__ void __launch_bounds__(256) k_cross(xs_plan pl, RasterArgs a, int64_t
     }
 }
 
-template <int KP, int P, int NW, int MB, int SC = 0, bool BK = false>
+template <int KP, int P, int NW, int MB, int SC = 0, bool BK = false, int NS = kStages>
 static int launch_scan(const xs_plan *pl, const RasterArgs &ra, const Workspace &ws, double2 *out_co, int *idx_co,
                        void *stream) {
-    const size_t smem = sizeof(ScanSmem<KP, P, NW>) + sizeof(float2) * (size_t)pl->n_wspd_pad;
+    const size_t smem = sizeof(ScanSmem<KP, P, NW, NS, BK>) + sizeof(float2) * (size_t)pl->n_wspd_pad;
     static bool configured = false;  // per instantiation
     if (!configured) {
-        XS_CUDA(cudaFuncSetAttribute(k_scan_co<KP, P, NW, MB, SC, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        XS_CUDA(cudaFuncSetAttribute(k_scan_co<KP, P, NW, MB, SC, BK, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         configured = true;
     }
     if (smem > 200 * 1024) {
@@ -932,11 +940,11 @@ static int launch_scan(const xs_plan *pl, const RasterArgs &ra, const Workspace 
         return XS_E_UNSUPPORTED;
     }
     int per_sm = 1;
-    XS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_scan_co<KP, P, NW, MB, SC, BK>, NW * 32, smem));
+    XS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_scan_co<KP, P, NW, MB, SC, BK, NS>, NW * 32, smem));
     if (per_sm < 1) per_sm = 1;
     int sms = kNumSMs;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, pl->device);
-    XS_LAUNCH((k_scan_co<KP, P, NW, MB, SC, BK>), sms * per_sm, NW * 32, smem, stream, *pl, ra, ws, out_co, idx_co);
+    XS_LAUNCH((k_scan_co<KP, P, NW, MB, SC, BK, NS>), sms * per_sm, NW * 32, smem, stream, *pl, ra, ws, out_co, idx_co);
     return XS_OK;
 }
 
@@ -961,16 +969,18 @@ static ScanConfig scan_config(int kp) {
         switch (scan_variant()) {
             case 1: return {4, 8};
             case 3: return {8, 12};
-            default: return {8, 8};
+            case 8: case 11: case 20: case 30: case 40: case 60: return {8, 8};
+            case 52: return {8, 2};
+            default: return {8, 4};
         }
     }
-    return {8, 8};
+    return {8, 4};
 }
 static int dispatch_scan(const xs_plan *pl, const RasterArgs &ra, const Workspace &ws, double2 *out_co, int *idx_co,
                          void *stream) {
     switch (pl->kp) {
-        case 1: return launch_scan<1, 8, 8, 2>(pl, ra, ws, out_co, idx_co, stream);
-        case 2: return launch_scan<2, 8, 8, 2>(pl, ra, ws, out_co, idx_co, stream);
+        case 1: return launch_scan<1, 8, 4, 4, 0, false, 3>(pl, ra, ws, out_co, idx_co, stream);
+        case 2: return launch_scan<2, 8, 4, 4, 0, false, 3>(pl, ra, ws, out_co, idx_co, stream);
         case 3:
             switch (scan_variant()) {
                 case 1: return launch_scan<3, 4, 8, 2>(pl, ra, ws, out_co, idx_co, stream);           // P = 4
@@ -980,7 +990,10 @@ static int dispatch_scan(const xs_plan *pl, const RasterArgs &ra, const Workspac
                 case 20: return launch_scan<3, 8, 8, 2, 0, true>(pl, ra, ws, out_co, idx_co, stream); // smem bookkeeping
                 case 30: return launch_scan<3, 8, 8, 2, 3>(pl, ra, ws, out_co, idx_co, stream);       // NOT exact: no refinement
                 case 40: return launch_scan<3, 8, 8, 2, 4>(pl, ra, ws, out_co, idx_co, stream);       // phase timers
-                default: return launch_scan<3, 8, 8, 2>(pl, ra, ws, out_co, idx_co, stream);
+                case 51: return launch_scan<3, 8, 4, 4, 0, false, 4>(pl, ra, ws, out_co, idx_co, stream);
+                case 52: return launch_scan<3, 8, 2, 8, 0, false, 3>(pl, ra, ws, out_co, idx_co, stream);  // 8 CTAs x 2 warps
+                case 60: return launch_scan<3, 8, 8, 2>(pl, ra, ws, out_co, idx_co, stream);          // 2 CTAs x 8 warps, 4 stages
+                default: return launch_scan<3, 8, 4, 4, 0, false, 3>(pl, ra, ws, out_co, idx_co, stream);  // shipped
             }
         case 4: return launch_scan<4, 4, 8, 1>(pl, ra, ws, out_co, idx_co, stream);
         default: return launch_scan<6, 4, 8, 1>(pl, ra, ws, out_co, idx_co, stream);
