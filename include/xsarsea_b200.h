@@ -167,7 +167,7 @@ int xs_plan_last_stats(const xs_plan *plan, int64_t stats[4]);
 /* Raw device counters of the last xs_invert on this plan (development aid): [0] tiles, [1] pixels queued for the
  * exhaustive kernel, [2] pixels settled by the scan, [3] chunks re-evaluated in FP64, [4..7] clock64 sums per phase
  * (prologue, main loop, refinement, write-out) when the instrumented scan variant is selected, else 0. */
-int xs_plan_debug_counters(const xs_plan *plan, unsigned long long out[8]);
+int xs_plan_debug_counters(const xs_plan *plan, unsigned long long out[16]);
 
 /* Device time in ms of the co-pol scan kernel (k_scan_co) of the last xs_invert on this plan, from CUDA events
  * recorded around that launch on the caller's stream (waits for the kernel to finish).  Used by bench.py for the

@@ -225,7 +225,7 @@ class InversionPlan:
         return float(ms.value)
 
     def debug_counters(self):
-        c = (ctypes.c_uint64 * 8)()
+        c = (ctypes.c_uint64 * 16)()
         nat.check(nat.load().xs_plan_debug_counters(self._handle, c), "xs_plan_debug_counters")
         return [int(v) for v in c]
 

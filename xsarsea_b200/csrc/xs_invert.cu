@@ -396,7 +396,7 @@ k_scan_co(xs_plan pl, RasterArgs a, Workspace ws, double2 *out_co, int *idx_co) 
     unsigned it = 0;  // chunks consumed so far by this CTA (ring position, continues across tiles)
     u64 n_scanned = 0, n_refined = 0;
 
-    u64 t_acc[4] = {0, 0, 0, 0};  // prologue (incl. barriers), main loop, refinement, write-out (incl. barrier)
+    u64 t_acc[6] = {0, 0, 0, 0, 0, 0};  // prologue (incl. barriers), main loop, refinement C, write-out (incl. barrier), refinement A, B
     long long t_last = clock64();
     // Tiles are handed out dynamically (one atomic per tile): CTAs do not all progress at the same speed, and a static
     // round-robin left ~13 % of the SM time idle at the end of the kernel.
@@ -670,6 +670,7 @@ k_scan_co(xs_plan pl, RasterArgs a, Workspace ws, double2 *out_co, int *idx_co) 
                 wide[p] = __ballot_sync(0xffffffffu, second[p] <= thr[p]);
                 cont[p] &= ~wide[p];
             }
+            XS_TICK(4);
             // phase B: membership in S of the candidates of the first contender cell of every pixel (loads batched)
             bool in0[P][kIter];
             int flat0[P][kIter];
@@ -692,6 +693,7 @@ k_scan_co(xs_plan pl, RasterArgs a, Workspace ws, double2 *out_co, int *idx_co) 
                     ++n_refined;
                 }
             }
+            XS_TICK(5);
             // phase C: count the members, look at the remaining cells (rare), settle
 #pragma unroll
             for (int p = 0; p < P; ++p) {
@@ -772,7 +774,11 @@ k_scan_co(xs_plan pl, RasterArgs a, Workspace ws, double2 *out_co, int *idx_co) 
         if (n_scanned) atomicAdd(&ws.counters[2], n_scanned);
         if (n_refined) atomicAdd(&ws.counters[3], n_refined);
         if (kMath == 4)
+        {
             for (int k = 0; k < 4; ++k) atomicAdd(&ws.counters[4 + k], t_acc[k]);
+            atomicAdd(&ws.counters[9], t_acc[4]);
+            atomicAdd(&ws.counters[10], t_acc[5]);
+        }
     }
 }
 
@@ -990,6 +996,7 @@ static int dispatch_scan(const xs_plan *pl, const RasterArgs &ra, const Workspac
                 case 20: return launch_scan<3, 8, 8, 2, 0, true>(pl, ra, ws, out_co, idx_co, stream); // smem bookkeeping
                 case 30: return launch_scan<3, 8, 8, 2, 3>(pl, ra, ws, out_co, idx_co, stream);       // NOT exact: no refinement
                 case 40: return launch_scan<3, 8, 8, 2, 4>(pl, ra, ws, out_co, idx_co, stream);       // phase timers
+                case 41: return launch_scan<3, 8, 4, 4, 4, false, 3>(pl, ra, ws, out_co, idx_co, stream);  // phase timers, shipped shape
                 case 51: return launch_scan<3, 8, 4, 4, 0, false, 4>(pl, ra, ws, out_co, idx_co, stream);
                 case 52: return launch_scan<3, 8, 2, 8, 0, false, 3>(pl, ra, ws, out_co, idx_co, stream);  // 8 CTAs x 2 warps
                 case 60: return launch_scan<3, 8, 8, 2>(pl, ra, ws, out_co, idx_co, stream);          // 2 CTAs x 8 warps, 4 stages
@@ -1074,8 +1081,8 @@ extern "C" int xs_plan_create(const xs_plan_desc *d, void *stream, xs_plan **out
         xs_plan_destroy(pl);
         return code;
     };
-    if ((rc = xs::check(cudaMalloc(&pl->stats, 8 * sizeof(unsigned long long)), "cudaMalloc stats")) != XS_OK) return fail(rc);
-    cudaMemsetAsync(pl->stats, 0, 8 * sizeof(unsigned long long), st);
+    if ((rc = xs::check(cudaMalloc(&pl->stats, 16 * sizeof(unsigned long long)), "cudaMalloc stats")) != XS_OK) return fail(rc);
+    cudaMemsetAsync(pl->stats, 0, 16 * sizeof(unsigned long long), st);
     if ((rc = xs::check(cudaEventCreate(&pl->ev_scan0), "cudaEventCreate")) != XS_OK) return fail(rc);
     if ((rc = xs::check(cudaEventCreate(&pl->ev_scan1), "cudaEventCreate")) != XS_OK) return fail(rc);
     if (has_co) {
@@ -1191,7 +1198,7 @@ extern "C" int xs_invert(const xs_plan *pl, const xs_invert_args *ar, void *stre
     int sms = kNumSMs;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, pl->device);
 
-    XS_CUDA(cudaMemsetAsync(pl->stats, 0, 8 * sizeof(unsigned long long), st));
+    XS_CUDA(cudaMemsetAsync(pl->stats, 0, 16 * sizeof(unsigned long long), st));
     if (co_run) {
         const bool fast = ar->mode == XS_MODE_FAST && pl->fast_ok;
         if (fast) {
@@ -1221,7 +1228,7 @@ extern "C" int xs_invert(const xs_plan *pl, const xs_invert_args *ar, void *stre
             mpl->scan_timed = 1;
             if (rc != XS_OK) return rc;
             XS_LAUNCH(k_exact, sms * 8, 256, 0, st, *pl, ra, n, ws.fallback, ws.counters + 1, out_co, ar->idx_co);
-            XS_CUDA(cudaMemcpyAsync(pl->stats, ws.counters, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
+            XS_CUDA(cudaMemcpyAsync(pl->stats, ws.counters, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
         } else {
             XS_LAUNCH(k_exact, sms * 8, 256, 0, st, *pl, ra, n, (const unsigned *)nullptr, (const u64 *)nullptr, out_co,
                       ar->idx_co);
@@ -1248,9 +1255,9 @@ extern "C" int xs_plan_last_scan_ms(const xs_plan *pl, float *ms) {
 }
 
 // Raw device counters of the last xs_invert (development aid; layout in the Workspace comment above).
-extern "C" int xs_plan_debug_counters(const xs_plan *pl, unsigned long long out[8]) {
+extern "C" int xs_plan_debug_counters(const xs_plan *pl, unsigned long long out[16]) {
     if (!pl || !out) return XS_E_INVALID;
-    XS_CUDA(cudaMemcpy(out, pl->stats, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    XS_CUDA(cudaMemcpy(out, pl->stats, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     return XS_OK;
 }
 
