@@ -37,7 +37,7 @@ def timeit(fn, warm=3, reps=5, inner=1):
 out = {}
 # ---- LUT generation (config 2): direct high-res evaluation and the default low-res + interpolation path ----
 gi, gw, gp = np.linspace(16, 66, 501), np.linspace(0.2, 50, 499), np.linspace(0, 180, 181)
-best, mean = timeit(lambda: D.lut_build(nat.GMF_IDS["gmf_cmod5n"], gi, gw, gp))
+best, mean = timeit(lambda: D.lut_build(nat.GMF_IDS["gmf_cmod5n"], gi, gw, gp), warm=5, reps=7, inner=5)
 out["lut_build_cmod5n_high_501x499x181"] = dict(ms=best, ms_mean=mean, Gevals_per_s=gi.size * gw.size * gp.size / best / 1e6,
                                                  reference_cpu_s=12.6)
 li, lw, lp = np.linspace(16, 66, 51), np.linspace(0.2, 50, 250), np.linspace(0, 180, 73)
@@ -51,7 +51,7 @@ def default_path():
     return D.lut_to_db(lut)
 
 
-best, mean = timeit(default_path)
+best, mean = timeit(default_path, warm=5, reps=7, inner=5)
 out["to_lut_default_path_cmod5n_dB"] = dict(ms=best, ms_mean=mean, reference_cpu_s=6.2)
 co = default_path()
 gwc = np.linspace(3, 80, 771)
@@ -64,11 +64,11 @@ H, W = 10000, 10400
 s0 = torch.rand(H, W, dtype=torch.float64, device="cuda") * 0.2 + 0.01
 prof = D.gmf_eval(nat.GMF_IDS["gmf_cmod5n"], torch.linspace(19, 47, W, dtype=torch.float64, device="cuda"),
                   torch.full((W,), 10.0, dtype=torch.float64, device="cuda"), torch.full((W,), 45.0, dtype=torch.float64, device="cuda"))
-best, mean = timeit(lambda: D.detrend(s0, prof), inner=10)
+best, mean = timeit(lambda: D.detrend(s0, prof), warm=10, reps=7, inner=20)
 out["detrend_f64_10000x10400"] = dict(ms=best, ms_mean=mean, GBps=16 * H * W / best / 1e6, frac_of_measured_hbm=16 * H * W / best / 1e6 / HBM_GBS,
                                       Gpx_per_s=H * W / best / 1e6)
 s32 = s0.float()
-best, mean = timeit(lambda: D.detrend(s32, prof), inner=10)
+best, mean = timeit(lambda: D.detrend(s32, prof), warm=10, reps=7, inner=20)
 out["detrend_f32_10000x10400"] = dict(ms=best, ms_mean=mean, GBps=8 * H * W / best / 1e6, frac_of_measured_hbm=8 * H * W / best / 1e6 / HBM_GBS)
 del s0, s32
 
