@@ -223,3 +223,45 @@ def test_cross_pol_filter_adversarial(dev, golden):
     assert np.array_equal(ic.cpu().numpy(), o_ic)
     bad = np.flatnonzero(ix.cpu().numpy() != o_ix)
     assert bad.size == 0, bad[:10]
+
+
+def test_plan_lifecycle_and_api_latency(dev):
+    """Plans can be created and destroyed repeatedly without leaking device memory, and a cached-plan API call on the
+    config-1 raster (1000 x 1000 from host memory) stays within a small multiple of its kernel time."""
+    import time
+
+    torch, D, nat = dev
+    lut, gi, gw, gp = make_co_lut(181, 180.0, n_inc=21, n_wspd=200)
+    t_lut = D.to_device(lut)
+    torch.cuda.synchronize()
+    D.InversionPlan(co=(t_lut, gi, gw, gp)).close()
+    torch.cuda.synchronize()
+    free0 = torch.cuda.mem_get_info()[0]
+    for _ in range(30):
+        pl = D.InversionPlan(co=(t_lut, gi, gw, gp))
+        pl.close()
+    torch.cuda.synchronize()
+    assert abs(torch.cuda.mem_get_info()[0] - free0) < (64 << 20)
+
+    from xsarsea_b200 import windspeed as ws
+
+    m = ws.get_model("gmf_cmod5n")
+    for k, v in dict(inc_step=0.1, wspd_step=0.1, phi_step=1.0, inc_step_lr=1.0, wspd_step_lr=0.2, phi_step_lr=2.5).items():
+        setattr(m, k, v)
+    rng = np.random.default_rng(0)
+    H = W = 1000
+    inc = np.broadcast_to(np.linspace(17.5, 49.5, W), (H, W)).copy()
+    w, p = rng.uniform(2, 25, (H, W)), rng.uniform(0, 360, (H, W))
+    s0 = np.clip(0.02 * w / 10 * (1 + 0.5 * np.cos(np.deg2rad(p))), 1e-4, None)
+    anc = w * np.exp(1j * np.deg2rad(p))
+    import warnings
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ws.invert_from_model(inc, s0, ancillary_wind=anc, model="gmf_cmod5n")      # builds LUT + plan
+        t0 = time.perf_counter()
+        out = ws.invert_from_model(inc, s0, ancillary_wind=anc, model="gmf_cmod5n")
+        dt = time.perf_counter() - t0
+    assert out.shape == (H, W) and np.isfinite(out).mean() > 0.99
+    assert dt < 0.25, f"cached-plan call on 1 Mpx took {dt:.3f} s"   # kernel ~12 ms + 72 MB of PCIe traffic
+    print(f"invert_from_model 1000x1000 from host: {1e3 * dt:.1f} ms")
