@@ -160,8 +160,8 @@ size_t xs_invert_workspace_bytes(const xs_plan *plan, int64_t n_px);
 int xs_invert(const xs_plan *plan, const xs_invert_args *args, void *stream);
 
 /* Statistics of the last xs_invert on this plan (device counters, read synchronously):
- * stats[0] = co-pol pixels scanned, [1] = candidate blocks re-evaluated in FP64,
- * [2] = pixels that fell back to the exhaustive FP64 scan, [3] = co-pol tiles launched. */
+ * stats[0] = co-pol pixels settled by the FP32 scan, [1] = (lane, chunk) cells re-examined by the refinement,
+ * [2] = pixels sent to the exhaustive FP64 scan, [3] = co-pol tiles. */
 int xs_plan_last_stats(const xs_plan *plan, int64_t stats[4]);
 
 /* Raw device counters of the last xs_invert on this plan (development aid): [0] tiles, [1] pixels queued for the

@@ -10,15 +10,16 @@
 //
 // Pipeline of one xs_invert call (all on the caller's stream, no host synchronisation):
 //   k_bin_count / k_bin_offsets / k_bin_scatter   counting sort of the co-pol pixels by incidence bin
-//   k_scan_co      persistent CTAs; a tile = 64 pixels of one bin; the bin's slab (scan image, FP32) is
-//                  streamed through a 4-stage shared-memory ring by bulk-async (TMA) copies, 8 rows at a
-//                  time; lane l owns the phi pairs {2(l+32j), 2(l+32j)+1}; each warp scans 8 pixels at once
-//                  keeping per lane and pixel the best 8-row chunk and the runner-up chunk minimum;
-//                  then per pixel: warp-shuffle min, FP64 re-evaluation (reference operation order) of every
-//                  chunk whose FP32 minimum lies within the rigorous FP32 error band of the warp minimum,
-//                  warp-shuffle lexicographic (J, index) argmin.  Pixels where one lane holds two chunks inside
-//                  the band go to the exhaustive FP64 kernel.
-//   k_exact_list   exhaustive FP64 scan (warp per pixel) of the few pixels the fast path could not settle
+//   k_scan_co      persistent CTAs (4 per SM, 4 warps each) taking tiles from an atomic counter; a tile = 32 pixels
+//                  of one bin; the bin's slab (scan image, FP32) is streamed through a 3-stage shared-memory ring by
+//                  bulk-async (TMA) copies, 16 rows at a time; lane l owns the phi pairs {2(l+32j), 2(l+32j)+1}; each
+//                  warp scans 8 pixels at once keeping per lane and pixel the best 16-row chunk and the runner-up
+//                  chunk minimum; then per pixel: warp-shuffle min, rigorous FP32 error band, the candidates inside
+//                  the band are found by re-creating the FP32 costs of the contending (lane, chunk) cells; a single
+//                  member settles the pixel, several are re-evaluated in FP64 (reference operation order) and reduced
+//                  by a warp-shuffle lexicographic (J, index) argmin.
+//   k_exact        exhaustive FP64 scan (warp per pixel) of the pixels the fast path cannot handle (non-finite
+//                  inputs, magnitudes outside the error bound's range) and of XS_MODE_FP64
 //   k_cross        cross-pol / dual-pol pass (windspeed.py:252-279), merge (:426-428), NaN classes
 #include <stdlib.h>
 #include <string.h>

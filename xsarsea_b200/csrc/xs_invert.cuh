@@ -42,7 +42,6 @@ namespace xs {
 
 constexpr int kChunkRows = 16;     // wspd rows per staged chunk = granularity of the argmin bookkeeping
 constexpr int kRowPad = 8;         // the scan image pads the wspd axis to a multiple of this (+inf rows)
-constexpr int kScanWarps = 8;      // warps per CTA of the co-pol scan
 constexpr int kStages = 4;         // shared-memory ring depth
 constexpr int kMaxIncBins = 8192;  // bins that fit the shared-memory histograms
 
