@@ -219,3 +219,16 @@ def test_row_sharded_gather_gloo_world2():
     for p in procs:
         p.join(60)
     assert res == [(0, True), (1, True)]
+
+
+def test_direction_helpers():
+    import xsarsea_b200 as x
+
+    a = np.array([-190.0, -180.0, 0.0, 179.0, 180.0, 370.0])
+    np.testing.assert_allclose(x.dir_to_180(a), [170.0, -180.0, 0.0, 179.0, -180.0, 10.0])
+    np.testing.assert_allclose(x.dir_to_360(a), [170.0, 180.0, 0.0, 179.0, 180.0, 10.0])
+    np.testing.assert_allclose(x.dir_oceano_to_meteo(x.dir_meteo_to_oceano(a)), x.dir_to_360(a))
+    assert x.dir_sample_to_meteo(30.0, 350.0) == 410.0                     # detrend.py: 90 - sample_dir + heading
+    assert abs(x.dir_meteo_to_sample(100.0, 10.0) - 0.0) < 1e-15           # pi/2 - deg2rad(meteo - heading)
+    back = x.dir_sample_to_meteo(np.rad2deg(x.dir_meteo_to_sample(a, 12.0)), 12.0)
+    np.testing.assert_allclose(back, a)

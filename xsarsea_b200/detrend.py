@@ -62,3 +62,37 @@ def sigma0_detrend(sigma0, inc_angle, wind_speed_gmf=np.array([10.0]), wind_dir_
         res.attrs["comment"] = f"detrended with model {model.name}"
         return res
     return out
+
+
+# ---- direction-convention helpers (reference detrend.py:96-201) --------------------------
+# One-line conversions applied by callers to the inversion output (antenna convention <-> meteorological /
+# oceanographic conventions).  Host-side numpy: they work on scalars, numpy arrays and labelled arrays alike.
+
+def dir_meteo_to_sample(meteo_dir, ground_heading):
+    """Meteorological N/S direction (deg, clockwise from north, "from") -> image (sample-axis) convention, radians."""
+    return np.pi / 2 - np.deg2rad(meteo_dir - ground_heading)
+
+
+def dir_sample_to_meteo(sample_dir, ground_heading):
+    """Image convention (deg, relative to the sample axis) -> meteorological direction (deg)."""
+    return 90 - sample_dir + ground_heading
+
+
+def dir_meteo_to_oceano(meteo_dir):
+    """Meteorological ("from") -> oceanographic ("to") convention, degrees in [0, 360)."""
+    return (meteo_dir + 180) % 360
+
+
+def dir_oceano_to_meteo(oceano_dir):
+    """Oceanographic ("to") -> meteorological ("from") convention, degrees in [0, 360)."""
+    return (oceano_dir - 180) % 360
+
+
+def dir_to_180(angle):
+    """Wrap an angle in degrees to [-180, 180)."""
+    return (angle + 180) % 360 - 180
+
+
+def dir_to_360(angle):
+    """Wrap an angle in degrees to [0, 360)."""
+    return (angle + 360) % 360
