@@ -14,6 +14,8 @@ constexpr int KP = 3, ROWS = 32;
 // 3: scalar FADD/FFMA/FFMA/FMNMX (no f32x2). 4: as 0 but nwh/w2q as packed pairs (no .F32 broadcast operand)
 // 8: hybrid A: t by two scalar FFMA (row constants hit the operand-reuse cache), d and J packed.
 // 9: hybrid B: t and d scalar, J packed.
+// 10: centred expansion: per pair Lc = L - c and M = Lc^2 + w2q are shared by the P pixels; per pixel two FFMA2
+//     (a = k_p*Lc + M, J = nwh*g + a) and FMNMX3.
 // 5: as 0 without the min (sum into m with FADD: all FMA pipe). 6: only the loads + FMNMX3 (no FMA-pipe work)
 template <int MODE, int P>
 __global__ void __launch_bounds__(256, 2) k(const float *__restrict__ src, const float2 *__restrict__ rowtab, float *out, int reps) {
@@ -41,12 +43,26 @@ __global__ void __launch_bounds__(256, 2) k(const float *__restrict__ src, const
             u64 L[KP];
 #pragma unroll
             for (int j = 0; j < KP; ++j) L[j] = rows[r * (32 * KP) + lane + 32 * j];
+            u64 Lc[KP], M[KP];
+            if (MODE == 10) {
+#pragma unroll
+                for (int j = 0; j < KP; ++j) {
+                    Lc[j] = fadd2(L[j], pack2(rt.y, rt.y));
+                    M[j] = ffma2(Lc[j], Lc[j], w2q);
+                }
+            }
 #pragma unroll
             for (int p = 0; p < P; ++p) {
                 const u64 q2 = pack2(nqs[p], nqs[p]);
 #pragma unroll
                 for (int j = 0; j < KP; ++j) {
-                    if (MODE == 3) {
+                    if (MODE == 10) {
+                        const u64 a = ffma2(q2, Lc[j], M[j]);
+                        const u64 J = ffma2(nwh, g[p][j], a);
+                        float j0, j1;
+                        unpack2(J, j0, j1);
+                        m[p] = fmin3(m[p], j0, j1);
+                    } else if (MODE == 3) {
                         float l0, l1, g0, g1;
                         unpack2(L[j], l0, l1);
                         unpack2(g[p][j], g0, g1);
@@ -198,6 +214,7 @@ int main() {
         run7<8>("pairs along wspd, g scalar", src, rt, out);
         run<8, 8>("hybrid A: scalar t, packed d and J", src, rt, out);
         run<9, 8>("hybrid B: scalar t and d, packed J", src, rt, out);
+        run<10, 8>("centred expansion: 2 FFMA2 + FMNMX3 per pixel pair", src, rt, out);
         run<0, 4>("as k_scan_co, P=4", src, rt, out);
         run<3, 4>("scalar, P=4", src, rt, out);
     }
