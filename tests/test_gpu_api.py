@@ -293,3 +293,90 @@ def test_full_iw_scene_properties(ws):
     assert torch.equal(torch.view_as_real(du2).nan_to_num(-1.0), du_r[0, :k].nan_to_num(-1.0))
     w = co.abs()
     assert torch.isnan(w).float().mean().item() < 0.02 and 2 < torch.nanmean(w).item() < 30
+
+
+def _sample_vs_oracle(idx, inc, s_co_db, s_cr_db, dsig, anc, co, cr, got_co, got_x):
+    """Compare the pixels `idx` of a large device result with the oracle run on the same LUTs."""
+    h = lambda t: None if t is None else t.reshape(-1)[idx].cpu().numpy()
+    kw = {}
+    if co is not None:
+        kw.update(co_lut=co[0], inc_grid=co[1], wspd_grid=co[2], phi_grid=co[3])
+    if cr is not None:
+        kw.update(cr_lut=cr[0], inc_cr_grid=cr[1], wspd_cr_grid=cr[2])
+    n = idx.numel()
+    nan = np.full(n, np.nan)
+    with np.errstate(all="ignore"):
+        o_co, o_x, _, _ = oracle.invert(h(inc), nan if s_co_db is None else h(s_co_db), nan if s_cr_db is None else h(s_cr_db),
+                                        h(dsig) if hasattr(dsig, "reshape") else dsig, nan + 0j if anc is None else h(anc), **kw)
+    if got_co is not None:
+        assert np.allclose(h(got_co), o_co, rtol=0, atol=1e-9, equal_nan=True)
+    return h(got_x), o_x
+
+
+def test_config4_cross_pol_only_full_size(ws):
+    """BASELINE.json configs[3] at full size (10 000 x 10 000 cross-pol only, NetCDF-style LUT 331 x 771, no ancillary
+    wind): a 30 000-pixel sample equals the oracle (dB inputs, uploaded LUT -> exact), the run is deterministic, and the
+    wind speeds are LUT grid values."""
+    import torch
+
+    import bench
+    from xsarsea_b200 import _device as D
+
+    gi, gwc = np.linspace(17.0, 50.0, 331), np.linspace(3.0, 80.0, 771)
+    cr = 10 * np.log10(oracle.lut_build("gmf_s1_v2", gi, gwc) + 1e-15)
+    plan = D.InversionPlan(cr=(D.to_device(cr), gi, gwc))
+    g = torch.Generator(device="cuda").manual_seed(4)
+    H = W = 10000
+    f64 = dict(device="cuda", dtype=torch.float64)
+    inc = (20 + 29 * torch.arange(W, **f64) / (W - 1)).expand(H, W).contiguous()
+    s_db = -38 + 30 * torch.rand(H, W, generator=g, **f64)          # spans below / inside / above the LUT range
+    s_db[torch.rand(H, W, generator=g, device="cuda") < 0.01] = float("nan")
+    a, _, _, _ = None, None, None, None
+    _, w1, _, _ = plan.invert(inc, None, s_db, 0.1, None, sigma0_db=True, cr_abs=True)
+    _, w2, _, _ = plan.invert(inc, None, s_db, 0.1, None, sigma0_db=True, cr_abs=True)
+    assert torch.equal(w1.nan_to_num(-1.0), w2.nan_to_num(-1.0))
+    idx = torch.randint(0, H * W, (30000,), generator=g, device="cuda")
+    got, want = _sample_vs_oracle(idx, inc, None, s_db, 0.1, None, None, (cr, gi, gwc), None, w1)
+    assert np.allclose(got, np.abs(want), rtol=0, atol=1e-12, equal_nan=True)
+    vals = w1[~torch.isnan(w1)][:200000].cpu().numpy()
+    assert np.isin(vals, gwc).all()
+
+
+def test_config5_ew_scene_dual_pol_with_dsig_raster_and_detrend(ws):
+    """BASELINE.json configs[4], one of the 8 EW scenes (10 000 x 10 400, inc 19-47 deg): dual-pol inversion with the
+    dsig_cr raster of windspeed/utils.py:82-86 ((1.25/(sigma0_cr/nesz))**4, spanning 1e-9 .. 1e3) checked on a sample
+    against the oracle, and sigma0_detrend's round trip out * ratio == sigma0."""
+    import torch
+
+    from xsarsea_b200 import _device as D
+    from xsarsea_b200 import _native as nat
+    from xsarsea_b200.windspeed import windspeed as impl
+
+    m_co, m_cr = reset_steps(ws.get_model("gmf_cmod5n")), reset_steps(ws.get_model("gmf_s1_v2"))
+    plan = impl._get_plan(m_co, m_cr, 0.1, {})
+    H, W = 10000, 10400
+    g = torch.Generator(device="cuda").manual_seed(5)
+    f64 = dict(device="cuda", dtype=torch.float64)
+    inc = (19 + 28 * torch.arange(W, **f64) / (W - 1)).expand(H, W).contiguous()
+    w = 2 + 23 * torch.rand(H, W, generator=g, **f64)
+    p = 360 * torch.rand(H, W, generator=g, **f64)
+    s_co = D.gmf_eval(nat.GMF_IDS["gmf_cmod5n"], inc, w, p) * torch.exp(0.05 * torch.randn(H, W, generator=g, **f64))
+    s_cr = D.gmf_eval(nat.GMF_IDS["gmf_s1_v2"], inc, w, None) * torch.exp(0.05 * torch.randn(H, W, generator=g, **f64))
+    anc = torch.polar((w + 2 * torch.randn(H, W, generator=g, **f64)).abs(), torch.deg2rad(p + 20 * torch.randn(H, W, generator=g, **f64)))
+    dsig = (1.25 / (s_cr / 10 ** -3.2)) ** 4.0
+    co, du, _, _ = plan.invert(inc, s_co, s_cr, dsig, anc)
+    # oracle on a sample, with the device-built LUTs downloaded (removes the libm difference), dB computed by numpy
+    idx = torch.randint(0, H * W, (8000,), generator=g, device="cuda")
+    co_l, cr_l = plan.co_lut.cpu().numpy(), plan.cr_lut.cpu().numpy()
+    hs = lambda t: t.reshape(-1)[idx].cpu().numpy()
+    with np.errstate(all="ignore"):
+        o_co, o_du, _, _ = oracle.invert(hs(inc), 10 * np.log10(hs(s_co) + 1e-15), 10 * np.log10(hs(s_cr) + 1e-15), hs(dsig), hs(anc),
+                                         co_lut=co_l, inc_grid=plan.co_grids[0], wspd_grid=plan.co_grids[1], phi_grid=plan.co_grids[2],
+                                         cr_lut=cr_l, inc_cr_grid=plan.cr_grids[0], wspd_cr_grid=plan.cr_grids[1])
+    assert (np.abs(hs(co) - o_co) > 1e-9).mean() < 1e-3       # fused log10 prologue: ulp-level near-ties only
+    assert (np.abs(hs(du) - o_du) > 1e-9).mean() < 1e-3
+    # detrend round trip on the same raster
+    prof = D.gmf_eval(nat.GMF_IDS["gmf_cmod5n"], inc[0].contiguous(), torch.full((W,), 10.0, **f64), torch.full((W,), 45.0, **f64))
+    out = D.detrend(s_co, prof)
+    ratio = prof / prof.mean()
+    assert torch.allclose(out * ratio, s_co, rtol=1e-14, atol=0)
