@@ -1,27 +1,26 @@
-"""windspeed module, for retrieving wind speed from sigma0 and models (B200 implementation).
+"""Wind retrieval from sigma0 and geophysical models -- B200 implementation of the `xsarsea.windspeed` namespace.
 
-Mirrors the names exported by xsarsea/windspeed/__init__.py:5-34 (register_pickle_luts excepted: the legacy
-sarwing pickle format is out of scope).
+The public names are those of the reference package for this path (`register_pickle_luts` excepted: the legacy
+sarwing pickle format is out of scope):
+
+    inversion        invert_from_model
+    model registry   Model, GmfModel, available_models, get_model, register_luts, register_nc_luts, register_cmod7
+    dsig helpers     get_dsig, get_dsig_wspd, nesz_flattening
+    submodules       gmfs (GmfModel and its decorator), gmfs_impl (the 13 built-in GMFs, evaluated on the device)
 """
-__all__ = [
-    "invert_from_model",
-    "available_models",
-    "get_model",
-    "register_cmod7",
-    "register_nc_luts",
-    "register_luts",
-    "nesz_flattening",
-    "GmfModel",
-    "Model",
-    "gmfs",
-    "gmfs_impl",
-    "get_dsig",
-    "get_dsig_wspd",
-]
+from . import gmfs, gmfs_impl, models, utils
+from . import cmod7 as _cmod7
+from . import windspeed as _inversion
 
-from . import gmfs, gmfs_impl  # noqa: F401
-from .cmod7 import register_cmod7
-from .gmfs import GmfModel
-from .models import Model, available_models, get_model, register_luts, register_nc_luts
-from .utils import get_dsig, get_dsig_wspd, nesz_flattening
-from .windspeed import invert_from_model
+Model = models.Model
+GmfModel = gmfs.GmfModel
+available_models, get_model = models.available_models, models.get_model
+register_luts, register_nc_luts = models.register_luts, models.register_nc_luts
+register_cmod7 = _cmod7.register_cmod7
+get_dsig, get_dsig_wspd, nesz_flattening = utils.get_dsig, utils.get_dsig_wspd, utils.nesz_flattening
+invert_from_model = _inversion.invert_from_model
+
+__all__ = sorted([
+    "invert_from_model", "available_models", "get_model", "register_cmod7", "register_nc_luts", "register_luts",
+    "nesz_flattening", "GmfModel", "Model", "gmfs", "gmfs_impl", "get_dsig", "get_dsig_wspd",
+])

@@ -102,33 +102,18 @@ class Model:
         (incidence, wspd, phi -- the order xarray.interp applies scipy interp1d in)."""
         if lut.units not in ("linear", "dB"):
             raise ValueError(f"Unknown lut units '{lut.units}'. Allowed are '['linear', 'dB']'")
-        resolution = kwargs.pop("resolution", "high")
-        if resolution is None:
-            resolution = "high"
-        lut_resolution = lut.resolution
-        if resolution == "high" and lut_resolution == "high":
-            do_interp = self.inc_step != kwargs.get("inc_step", self.inc_step) or self.wspd_step != kwargs.get(
-                "wspd_step", self.wspd_step)
-            if self.iscopol:
-                do_interp = do_interp or self.phi_step != kwargs.get("phi_step", self.phi_step)
-        elif resolution == "low" and lut_resolution == "low":
-            do_interp = self.inc_step_lr != kwargs.get("inc_step_lr", self.inc_step_lr) or self.wspd_step_lr != kwargs.get(
-                "wspd_step_lr", self.wspd_step_lr)
-            if self.iscopol:
-                do_interp = do_interp or self.phi_step_lr != kwargs.get("phi_step_lr", self.phi_step_lr)
-        else:
-            do_interp = False
-        if resolution != lut_resolution or do_interp:
-            if resolution == "high":
-                inc_step = kwargs.pop("inc_step", self.inc_step)
-                wspd_step = kwargs.pop("wspd_step", self.wspd_step)
-                phi_step = kwargs.pop("phi_step", self.phi_step)
-            elif resolution == "low":
-                inc_step = kwargs.pop("inc_step_lr", self.inc_step_lr)
-                wspd_step = kwargs.pop("wspd_step_lr", self.wspd_step_lr)
-                phi_step = kwargs.pop("phi_step_lr", self.phi_step_lr)
-            else:
-                raise ValueError(f"unknown resolution {resolution!r}")
+        resolution = kwargs.pop("resolution", "high") or "high"
+        if resolution not in ("high", "low"):
+            raise ValueError(f"unknown resolution {resolution!r}")
+        sfx = "" if resolution == "high" else "_lr"          # the step attributes that apply: *_step or *_step_lr
+        axes = ("inc", "wspd") + (("phi",) if self.iscopol else ())
+        names = [f"{a}_step{sfx}" for a in axes]
+        # a LUT that already has the requested resolution is re-interpolated only if a step is overridden (:119-135)
+        same_res = resolution == lut.resolution
+        overridden = any(getattr(self, n) != kwargs.get(n, getattr(self, n)) for n in names)
+        if not same_res or overridden:
+            inc_step, wspd_step, phi_step = (kwargs.pop(f"{a}_step{sfx}", getattr(self, f"{a}_step{sfx}"))
+                                             for a in ("inc", "wspd", "phi"))
             inc, wspd = _grid(self.inc_range, inc_step), _grid(self.wspd_range, wspd_step)
             phi = _grid(self.phi_range, phi_step) if lut.phi is not None else None
             data = lut.data
