@@ -16,6 +16,7 @@ constexpr int KP = 3, ROWS = 32;
 // 9: hybrid B: t and d scalar, J packed.
 // 10: centred expansion: per pair Lc = L - c and M = Lc^2 + w2q are shared by the P pixels; per pixel two FFMA2
 //     (a = k_p*Lc + M, J = nwh*g + a) and FMNMX3.
+// 11: w^2/4 folded out of the per-candidate work: t' = nwh*g (FMUL2), J = d*d + t', row minimum r, then m = min(m, r + w2q).
 // 5: as 0 without the min (sum into m with FADD: all FMA pipe). 6: only the loads + FMNMX3 (no FMA-pipe work)
 template <int MODE, int P>
 __global__ void __launch_bounds__(256, 2) k(const float *__restrict__ src, const float2 *__restrict__ rowtab, float *out, int reps) {
@@ -43,6 +44,25 @@ __global__ void __launch_bounds__(256, 2) k(const float *__restrict__ src, const
             u64 L[KP];
 #pragma unroll
             for (int j = 0; j < KP; ++j) L[j] = rows[r * (32 * KP) + lane + 32 * j];
+            if (MODE == 11) {
+#pragma unroll
+                for (int p = 0; p < P; ++p) {
+                    const u64 q2 = pack2(nqs[p], nqs[p]);
+                    float rmin;
+#pragma unroll
+                    for (int j = 0; j < KP; ++j) {
+                        const u64 d = fadd2(L[j], q2);
+                        u64 tp;
+                        asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(tp) : "l"(nwh), "l"(g[p][j]));
+                        const u64 J = ffma2(d, d, tp);
+                        float j0, j1;
+                        unpack2(J, j0, j1);
+                        rmin = j == 0 ? fminf(j0, j1) : fmin3(rmin, j0, j1);
+                    }
+                    m[p] = fminf(m[p], rmin + rt.y);
+                }
+                continue;
+            }
             u64 Lc[KP], M[KP];
             if (MODE == 10) {
 #pragma unroll
@@ -215,6 +235,7 @@ int main() {
         run<8, 8>("hybrid A: scalar t, packed d and J", src, rt, out);
         run<9, 8>("hybrid B: scalar t and d, packed J", src, rt, out);
         run<10, 8>("centred expansion: 2 FFMA2 + FMNMX3 per pixel pair", src, rt, out);
+        run<11, 8>("w2q folded out: FADD2 + FMUL2 + FFMA2 + row min", src, rt, out);
         run<0, 4>("as k_scan_co, P=4", src, rt, out);
         run<3, 4>("scalar, P=4", src, rt, out);
     }
