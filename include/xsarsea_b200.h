@@ -181,6 +181,41 @@ int xs_plan_last_scan_ms(const xs_plan *plan, float *ms);
 int xs_detrend(const void *sigma0_dev, const double *gmf_line_dev, int64_t n_lines, int64_t n_samples, int dtype,
                void *out_dev, void *stream);
 
+/* ---- dsig_cr pre-processors --------------------------------------- */
+
+/* dsig_cr formulas of windspeed/utils.py:66-86, selected by the model name the reference switches on */
+enum xs_dsig_id {
+    XS_DSIG_GMF_S1_V2 = 0,    /* "gmf_s1_v2": 1/sqrt((s/n)**c(inc)), utils.py:66-76 */
+    XS_DSIG_GMF_RS2_V2 = 1,   /* "gmf_rs2_v2": 1/sqrt((s/n)**8), utils.py:78-81 */
+    XS_DSIG_CMODMS1AHW = 2,   /* "sarwing_lut_cmodms1ahw" / "nc_lut_cmodms1ahw": (1.25/(s/n))**4, utils.py:83-87 */
+    XS_DSIG_COUNT = 3
+};
+/* co/cross blending weights of windspeed/utils.py:26-42 */
+enum xs_dsig_wspd_id {
+    XS_DSIG_WSPD_RS2_V3 = 0,
+    XS_DSIG_WSPD_S1_EW_REC_V3 = 1,
+    XS_DSIG_WSPD_RCM_V3 = 2,
+    XS_DSIG_WSPD_COUNT = 3
+};
+
+/* Replaces get_dsig(name, inc, sigma0_cr, nesz_cr), windspeed/utils.py:47-91: element-wise over n already-broadcast
+ * device elements of type `dtype` (promoted to f64 on load); out is float64.  inc_dev may be NULL unless
+ * dsig_id == XS_DSIG_GMF_S1_V2. */
+int xs_dsig(int dsig_id, int dtype, const void *inc_dev, const void *sigma0_cr_dev, const void *nesz_cr_dev,
+            double *out_dev, int64_t n, void *stream);
+
+/* Replaces get_dsig_wspd(name, U_crosspol, SNR_cr), windspeed/utils.py:18-44.  out is float64 in [0, 1] (NaN kept). */
+int xs_dsig_wspd(int dsig_wspd_id, int dtype, const void *u_crosspol_dev, const void *snr_cr_dev, double *out_dev,
+                 int64_t n, void *stream);
+
+/* Replaces nesz_flattening(noise, inc), windspeed/utils.py:94-163: noise [n_lines][n_samples] linear NESZ, NaN filled
+ * with the column nanmean, converted to dB, fitted per line by an order-1 polynomial of the column-mean incidence
+ * (np.polyfit over the finite points), out = 10**((inc_mean*a + b - 1)/10) float64 [n_lines][n_samples]; a line with
+ * no finite point is NaN.  workspace >= xs_nesz_flatten_workspace_bytes(). */
+size_t xs_nesz_flatten_workspace_bytes(int64_t n_lines, int64_t n_samples);
+int xs_nesz_flatten(const void *noise_dev, const void *inc_dev, int64_t n_lines, int64_t n_samples, int dtype,
+                    double *out_dev, void *workspace, size_t workspace_bytes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

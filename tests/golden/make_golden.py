@@ -1,7 +1,7 @@
 """Generate golden vectors from the REAL reference arithmetic (dev-time; needs /root/reference + numba).
 
 Run:  python tests/golden/make_golden.py
-Writes tests/golden/gmf_points.npz, inv_small.npz, inv_slabs.npz, inv_ifr2.npz.
+Writes tests/golden/gmf_points.npz, inv_small.npz, inv_slabs.npz, inv_ifr2.npz, dsig_utils.npz.
 
 Everything numerical in these files comes out of the reference's own code, executed through
 tests/golden/_refload.py: the numba-compiled scalar GMFs (gmfs.py:206-230 over gmfs_impl.py) and the
@@ -223,8 +223,57 @@ def inv_ifr2():
     print("inv_ifr2.npz")
 
 
+def dsig_utils():
+    """Outputs of the reference's own windspeed/utils.py: get_dsig (:47-91), get_dsig_wspd (:18-44),
+    nesz_flattening (:94-163) on seeded inputs with the edge cases the formulas have (negative / zero / NaN sigma0,
+    NaN holes and an all-NaN line in the noise, a non-positive noise sample, constant incidence)."""
+    import warnings
+
+    from xsarsea.windspeed import utils as ref
+
+    rng = np.random.default_rng(7)
+    n = 4000
+    inc = rng.uniform(17.0, 50.0, n)
+    nesz = 10 ** rng.uniform(-3.6, -2.6, n)
+    s_cr = nesz * 10 ** rng.uniform(-0.5, 2.0, n)
+    s_cr[:8] = [0.0, -1e-4, np.nan, 1e-12, np.inf, 1e3, 1e-3, 1e-3]
+    nesz[5:8] = [1e-3, np.nan, 0.0]
+    out = dict(inc=inc, sigma0_cr=s_cr, nesz_cr=nesz)
+    with warnings.catch_warnings(), np.errstate(all="ignore"):
+        warnings.simplefilter("ignore")
+        for name in ("gmf_s1_v2", "gmf_rs2_v2", "nc_lut_cmodms1ahw", "sarwing_lut_cmodms1ahw"):
+            out["dsig__" + name] = ref.get_dsig(name, inc, s_cr, nesz)
+        u = rng.uniform(0.0, 80.0, n)
+        snr = rng.uniform(-5.0, 25.0, n)
+        u[:4] = [np.nan, 30.0, 0.0, 1e3]
+        snr[4:6] = [np.nan, 1e3]
+        out.update(u_crosspol=u, snr_cr=snr)
+        for name in ("dsig_wspd_rs2_v3", "dsig_wspd_s1_ew_rec_v3", "dsig_wspd_rcm_v3"):
+            out["wspd__" + name] = ref.get_dsig_wspd(name, u, snr)
+        # nesz_flattening: an EW-like noise field (scalloped in range, slowly varying in azimuth)
+        h, w = 96, 700
+        incg = np.broadcast_to(np.linspace(19.0, 47.0, w), (h, w)) + rng.normal(0, 1e-3, (h, w))
+        noise = 10 ** ((-28.0 - 0.12 * (incg - 19.0) + 0.6 * np.sin(incg * 1.7) + rng.normal(0, 0.15, (h, w))) / 10.0)
+        noise[rng.random((h, w)) < 0.02] = np.nan
+        noise[5, :] = np.nan                 # a whole line missing: filled from the column means
+        noise[:, 11] = np.nan                # a whole column missing: stays NaN -> excluded from every fit
+        noise[7, 20] = 0.0                   # log10(0) = -inf: excluded
+        noise[8, 21] = -1e-3                 # log10(<0) = nan: excluded
+        incg[9, 30] = np.nan                 # NaN incidence only enters through the column nanmean
+        out.update(noise=noise, inc2d=incg, noise_flat=ref.nesz_flattening(noise, incg))
+        # degenerate: every column missing -> np.polyfit TypeError -> NaN lines
+        nn = np.full((3, 16), np.nan)
+        out.update(noise_allnan_flat=ref.nesz_flattening(nn, incg[:3, :16].copy()))
+    np.savez_compressed(os.path.join(HERE, "dsig_utils.npz"), **out)
+    print("dsig_utils.npz")
+
+
 if __name__ == "__main__":
+    if sys.argv[1:] == ["dsig_utils"]:
+        dsig_utils()
+        sys.exit(0)
     gmf_points()
     inv_small()
     inv_slabs()
     inv_ifr2()
+    dsig_utils()

@@ -130,3 +130,28 @@ def test_detrend_oracle():
     want = s0 / (prof / np.nanmean(prof))
     got = oracle.detrend(s0, prof)
     np.testing.assert_allclose(got, want, rtol=1e-14, equal_nan=True)
+
+
+def test_dsig_oracle_bit_exact_against_reference_outputs(golden):
+    """oracle/dsig.py against outputs of the reference's own windspeed/utils.py (tests/golden/make_golden.py::dsig_utils):
+    same numpy calls in the same order -> bit-identical, NaN positions included."""
+    import warnings
+
+    from oracle import dsig as od
+
+    g = golden("dsig_utils")
+    with warnings.catch_warnings(), np.errstate(all="ignore"):
+        warnings.simplefilter("ignore")
+        for key in g:
+            if key.startswith("dsig__"):
+                got = od.get_dsig(key[6:], g["inc"], g["sigma0_cr"], g["nesz_cr"])
+            elif key.startswith("wspd__"):
+                got = od.get_dsig_wspd(key[6:], g["u_crosspol"], g["snr_cr"])
+            else:
+                continue
+            assert np.array_equal(got, g[key], equal_nan=True), key
+        assert np.array_equal(od.nesz_flattening(g["noise"], g["inc2d"]), g["noise_flat"], equal_nan=True)
+        flat = od.nesz_flattening(np.full((3, 16), np.nan), g["inc2d"][:3, :16])
+        assert np.isnan(flat).all() and np.isnan(g["noise_allnan_flat"]).all()
+    with pytest.raises(ValueError):
+        od.get_dsig("other", 1.0, 1.0, 1.0)

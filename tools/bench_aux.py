@@ -72,6 +72,23 @@ best, mean = timeit(lambda: D.detrend(s32, prof), warm=10, reps=7, inner=20)
 out["detrend_f32_10000x10400"] = dict(ms=best, ms_mean=mean, GBps=8 * H * W / best / 1e6, frac_of_measured_hbm=8 * H * W / best / 1e6 / HBM_GBS)
 del s0, s32
 
+# ---- dsig_cr pre-processors (row F1; HBM-bound FP64 element-wise / per-line fit) on the same EW-sized raster ----
+inc2 = torch.linspace(19, 47, W, dtype=torch.float64, device="cuda").expand(H, W).contiguous()
+scr = 10 ** (torch.rand(H, W, dtype=torch.float64, device="cuda") * 2.5 - 3.7)
+nesz = 10 ** (-3.2 + 0.05 * torch.randn(H, W, dtype=torch.float64, device="cuda"))
+for name, did, bpp in (("gmf_s1_v2", 0, 32), ("gmf_rs2_v2", 1, 24), ("nc_lut_cmodms1ahw", 2, 24)):
+    best, mean = timeit(lambda: D.dsig(did, inc2 if did == 0 else None, scr, nesz), warm=5, reps=7, inner=10)
+    out[f"get_dsig_{name}_10000x10400"] = dict(ms=best, ms_mean=mean, algorithmic_B_per_px=bpp, GBps=bpp * H * W / best / 1e6,
+                                               frac_of_measured_hbm=bpp * H * W / best / 1e6 / HBM_GBS)
+best, mean = timeit(lambda: D.dsig_wspd(1, scr * 1e3, nesz * 1e4), warm=5, reps=7, inner=10)
+out["get_dsig_wspd_s1_ew_rec_v3_10000x10400"] = dict(ms=best, ms_mean=mean, algorithmic_B_per_px=24, GBps=24 * H * W / best / 1e6,
+                                                      frac_of_measured_hbm=24 * H * W / best / 1e6 / HBM_GBS)
+best, mean = timeit(lambda: D.nesz_flatten(nesz, inc2), warm=5, reps=7, inner=5)
+# column means read noise + incidence (16 B/px), the fit reads the noise again and writes the result (16 B/px)
+out["nesz_flattening_10000x10400"] = dict(ms=best, ms_mean=mean, algorithmic_B_per_px=32, GBps=32 * H * W / best / 1e6,
+                                          frac_of_measured_hbm=32 * H * W / best / 1e6 / HBM_GBS)
+del inc2, scr, nesz
+
 # ---- inversion: cross-pol only (config 4, 10000 x 10000) and co-pol only (config 1, 1000 x 1000) ----
 plan_x = D.InversionPlan(cr=(cr, gi, gwc))
 inc, s_co, s_cr, anc = bench.synth_scene_device(10000, 10000, 3)

@@ -102,6 +102,54 @@ def detrend(sigma0, gmf_line):
     return out
 
 
+def _same_real_dtype(*ts):
+    """Common raster dtype code of device tensors: float32 only if all are float32, else everything is made float64."""
+    torch = _t()
+    if all(t.dtype == torch.float32 for t in ts):
+        return nat.XS_F32, [t.contiguous() for t in ts]
+    return nat.XS_F64, [t.to(torch.float64).contiguous() for t in ts]
+
+
+def dsig(dsig_id: int, inc, sigma0_cr, nesz_cr):
+    """dsig_cr raster on device (reference get_dsig, windspeed/utils.py:47-91); inputs already broadcast, float64 out."""
+    torch = _t()
+    ts = [sigma0_cr, nesz_cr] + ([inc] if inc is not None else [])
+    assert all(t.shape == sigma0_cr.shape for t in ts)
+    dt, ts = _same_real_dtype(*ts)
+    out = torch.empty(sigma0_cr.shape, dtype=torch.float64, device="cuda")
+    nat.check(nat.load().xs_dsig(dsig_id, dt, nat.dptr(ts[2]) if inc is not None else None, nat.dptr(ts[0]),
+                                 nat.dptr(ts[1]), nat.dptr(out), out.numel(), nat.stream_ptr()), "xs_dsig")
+    return out
+
+
+def dsig_wspd(dsig_wspd_id: int, u_crosspol, snr_cr):
+    """Co/cross blending weight on device (reference get_dsig_wspd, windspeed/utils.py:18-44)."""
+    torch = _t()
+    assert u_crosspol.shape == snr_cr.shape
+    dt, (u, s) = _same_real_dtype(u_crosspol, snr_cr)
+    out = torch.empty(u.shape, dtype=torch.float64, device="cuda")
+    nat.check(nat.load().xs_dsig_wspd(dsig_wspd_id, dt, nat.dptr(u), nat.dptr(s), nat.dptr(out), out.numel(),
+                                      nat.stream_ptr()), "xs_dsig_wspd")
+    return out
+
+
+def nesz_flatten(noise, inc):
+    """Per-line order-1 flattening of the noise in dB (reference nesz_flattening, windspeed/utils.py:94-163)."""
+    torch = _t()
+    L = nat.load()
+    assert noise.dim() == 2 and inc.shape == noise.shape
+    dt, (noise, inc) = _same_real_dtype(noise, inc)
+    h, w = noise.shape
+    out = torch.empty((h, w), dtype=torch.float64, device="cuda")
+    if h == 0 or w == 0:
+        return out
+    need = int(L.xs_nesz_flatten_workspace_bytes(h, w))
+    ws = torch.empty(need, dtype=torch.uint8, device="cuda")
+    nat.check(L.xs_nesz_flatten(nat.dptr(noise), nat.dptr(inc), h, w, dt, nat.dptr(out), nat.dptr(ws), need,
+                                nat.stream_ptr()), "xs_nesz_flatten")
+    return out
+
+
 class InversionPlan:
     """Owns an xs_plan: the device LUTs of one (co-pol, cross-pol) model pair plus the scan image.
 

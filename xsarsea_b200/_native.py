@@ -41,7 +41,11 @@ EXPORTS = [
     "xs_abi_version", "xs_last_error", "xs_launch_count", "xs_gmf_eval", "xs_lut_build", "xs_lut_interp_axis",
     "xs_lut_to_db", "xs_lut_to_linear", "xs_plan_create", "xs_plan_destroy", "xs_invert_workspace_bytes",
     "xs_invert", "xs_plan_last_stats", "xs_plan_last_scan_ms", "xs_plan_debug_counters", "xs_detrend",
+    "xs_dsig", "xs_dsig_wspd", "xs_nesz_flatten_workspace_bytes", "xs_nesz_flatten",
 ]
+
+DSIG_IDS = {"gmf_s1_v2": 0, "gmf_rs2_v2": 1, "sarwing_lut_cmodms1ahw": 2, "nc_lut_cmodms1ahw": 2}
+DSIG_WSPD_IDS = {"dsig_wspd_rs2_v3": 0, "dsig_wspd_s1_ew_rec_v3": 1, "dsig_wspd_rcm_v3": 2}
 
 
 class NativeError(RuntimeError):
@@ -151,6 +155,14 @@ def load():
         L.xs_plan_debug_counters.argtypes = [vp, ctypes.POINTER(ctypes.c_uint64)]
         L.xs_detrend.restype = i32
         L.xs_detrend.argtypes = [vp, vp, i64, i64, i32, vp, vp]
+        L.xs_dsig.restype = i32
+        L.xs_dsig.argtypes = [i32, i32, vp, vp, vp, vp, i64, vp]
+        L.xs_dsig_wspd.restype = i32
+        L.xs_dsig_wspd.argtypes = [i32, i32, vp, vp, vp, i64, vp]
+        L.xs_nesz_flatten_workspace_bytes.restype = sz
+        L.xs_nesz_flatten_workspace_bytes.argtypes = [i64, i64]
+        L.xs_nesz_flatten.restype = i32
+        L.xs_nesz_flatten.argtypes = [vp, vp, i64, i64, i32, vp, vp, sz, vp]
         if L.xs_abi_version() != 1:
             raise NativeError("libxsarsea_b200.so ABI version mismatch")
         _lib = L
