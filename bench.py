@@ -108,11 +108,13 @@ def write_ms1ahw_standin(dirname):
     """nc_lut_cmodms1ahw.nc in the reference's schema (models.py:232-262, 368-379), NetCDF-3 via scipy."""
     from scipy.io import netcdf_file
 
-    import oracle
+    from xsarsea_b200 import _device as D
+    from xsarsea_b200 import _native as nat
 
     inc = np.linspace(17.0, 50.0, 331)
     wspd = np.linspace(3.0, 80.0, 771)
-    lut_db = 10 * np.log10(oracle.lut_build("gmf_s1_v2", inc, wspd) + 1e-15)
+    # 10*log10(gmf_s1_v2 + 1e-15), evaluated with the package's own device GMF (the oracle stays out of this arm)
+    lut_db = D.lut_to_db(D.lut_build(nat.GMF_IDS["gmf_s1_v2"], inc, wspd, None)).cpu().numpy()
     path = os.path.join(dirname, "nc_lut_cmodms1ahw.nc")
     with netcdf_file(path, "w") as nc:
         nc.units, nc.pol, nc.model, nc.resolution = "dB", "VH", "cmodms1ahw", "high"

@@ -88,6 +88,28 @@ def test_dual_pol_numpy(ws):
     wind_close(dual, merged)
 
 
+def test_device_resident_tensors_in_tensors_out(ws):
+    """torch CUDA tensors in -> torch CUDA tensors out, identical to the host-array call (no copies in between)."""
+    import torch
+
+    inc, s_co, s_cr, anc = synth(6000, shape=(60, 100))
+    model = ("gmf_cmod5n", "gmf_s1_v2")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        co, dual = ws.invert_from_model(inc, s_co, s_cr, ancillary_wind=anc, dsig_cr=0.1, model=model, **KW)
+        t = lambda a: torch.from_numpy(a).cuda()
+        tco, tdual = ws.invert_from_model(t(inc), t(s_co), t(s_cr), ancillary_wind=t(anc), dsig_cr=0.1, model=model, **KW)
+        assert tco.is_cuda and tdual.is_cuda and tco.dtype == torch.complex128 and tuple(tco.shape) == inc.shape
+        assert np.array_equal(tco.cpu().numpy(), co, equal_nan=True)
+        assert np.array_equal(tdual.cpu().numpy(), dual, equal_nan=True)
+        # mono cross-pol: float64 wind speed; dsig_cr as a device raster produced by get_dsig
+        dsig = ws.get_dsig("gmf_s1_v2", t(inc), t(s_cr), 10 ** -3.2)
+        x_dev = ws.invert_from_model(t(inc), t(s_cr), dsig_cr=dsig, model="gmf_s1_v2", **KW)
+        x_host = ws.invert_from_model(inc, s_cr, dsig_cr=dsig.cpu().numpy(), model="gmf_s1_v2", **KW)
+        assert x_dev.is_cuda and x_dev.dtype == torch.float64
+        assert np.array_equal(x_dev.cpu().numpy(), x_host, equal_nan=True)
+
+
 def test_index_exact_with_the_models_own_lut(ws):
     """Feeding the oracle the device-built LUT removes the libm difference: answers must then agree exactly
     (up to the fused log10 prologue's ulp, i.e. measure-zero near-ties)."""

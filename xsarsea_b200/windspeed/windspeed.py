@@ -60,11 +60,39 @@ def clear_plan_cache():
         _PLAN_CACHE.popitem()[1].close()
 
 
+def _is_tensor(x):
+    return type(x).__module__.split(".")[0] == "torch"
+
+
+def _isnan(x):
+    return x.isnan() if _is_tensor(x) else np.isnan(x)
+
+
 def _values(x):
-    """numpy view of a numpy / labelled input (None stays None)."""
-    if x is None:
-        return None
+    """numpy view of a numpy / labelled input (None stays None; torch tensors pass through)."""
+    if x is None or _is_tensor(x):
+        return x
     return np.asarray(x.data if _xr.is_labelled(x) else x)
+
+
+def _run_resident(plan, inc, s_co, s_cr, dsig_cr, anc, *, merge_dual, cr_abs):
+    """Device-resident variant of `_run_device`: torch CUDA tensors in, torch CUDA tensors out, one `xs_invert` on the
+    current stream, no host copies (an extension of the reference's container rule "output mirrors input",
+    windspeed.py:333-388, to device arrays)."""
+    torch = nat.torch_cuda()
+    f32 = inc.dtype == torch.float32
+    rdt, cdt = (torch.float32, torch.complex64) if f32 else (torch.float64, torch.complex128)
+
+    def prep(x, dt):
+        if x is None:
+            return None
+        x = x if _is_tensor(x) else torch.as_tensor(np.asarray(x))
+        return x.to(device=inc.device, dtype=dt).expand(inc.shape).contiguous()
+
+    dsig = dsig_cr if np.isscalar(dsig_cr) else prep(dsig_cr, rdt)
+    oc, ox, _, _ = plan.invert(inc.contiguous(), prep(s_co, rdt), prep(s_cr, rdt), dsig, prep(anc, cdt), sigma0_db=False,
+                               merge_dual=merge_dual, cr_abs=cr_abs)
+    return oc, ox
 
 
 def _run_device(plan, inc, s_co, s_cr, dsig_cr, anc, *, sigma0_db, merge_dual, cr_abs, mode=nat.MODE_FAST,
@@ -193,10 +221,10 @@ def invert_from_model(inc, sigma0, sigma0_dual=None, /, ancillary_wind=None, dsi
         if models[0].iscopol:
             sigma0_co, sigma0_cr = sigma0, None
             # copol needs valid ancillary wind
-            assert anc_given and np.any(~np.isnan(_values(ancillary_wind)))
+            assert anc_given and bool((~_isnan(_values(ancillary_wind))).any())
         elif models[0].iscrosspol:
             sigma0_co, sigma0_cr = None, sigma0
-            if anc_given and not np.all(np.isnan(_values(ancillary_wind))):
+            if anc_given and not bool(_isnan(_values(ancillary_wind)).all()):
                 warnings.warn("crosspol inversion is best without ancillary wind, but using it as requested.")
             models = (None, models[0])
     else:
@@ -215,6 +243,10 @@ def invert_from_model(inc, sigma0, sigma0_dual=None, /, ancillary_wind=None, dsi
             import xarray as xr
 
             ws_cr_or_dual = xr.where((abs(ws_co) < 5) | (abs(ws_cr_or_dual) < 5), ws_co, ws_cr_or_dual)
+    elif _is_tensor(inc):
+        plan = _get_plan(models[0], models[1] if sigma0_cr is not None else None, dsig_co, kwargs)
+        ws_co, ws_cr_or_dual = _run_resident(plan, inc, sigma0_co, sigma0_cr, dsig_cr, ancillary_wind if anc_given else None,
+                                             merge_dual=dual, cr_abs=cross_only)
     else:
         plan = _get_plan(models[0], models[1] if sigma0_cr is not None else None, dsig_co, kwargs)
         dsig_in = dsig_cr if np.isscalar(dsig_cr) else _values(dsig_cr)
