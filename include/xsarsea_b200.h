@@ -124,6 +124,8 @@ void xs_plan_destroy(xs_plan *plan);
                                    otherwise the kernel applies windspeed.py:126-128 itself */
 #define XS_FLAG_MERGE_DUAL 2u   /* out_cr receives where(|co|<5 or |dual|<5, co, dual) (windspeed.py:426-428) */
 #define XS_FLAG_CR_ABS 4u       /* out_cr is float64 |wind| instead of complex128 (windspeed.py:422-423) */
+#define XS_FLAG_CR_FULL_SCAN 8u /* verification: scan every cross-pol candidate (FP32 filter + FP64 refinement) even where
+                                   the exact interval search applies (LUT row non-decreasing in wspd); same results */
 
 /* scan modes */
 #define XS_MODE_FAST 0  /* FP32 FFMA2 scan + FP64 refinement of every candidate block within the error band */

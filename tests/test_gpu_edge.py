@@ -181,13 +181,22 @@ def test_fast_equals_fp64_adversarial_sweep(dev):
     assert st["scan_pixels"] + st["exhaustive_pixels"] == n
 
 
-def test_cross_pol_filter_adversarial(dev, golden):
-    """The FP32 filter of the cross-pol scan against the oracle on inputs chosen to break a sloppy error bound: dsig_cr
-    from 1e-8 (SNR 100 in (1.25/SNR)**4) to 1e4, sigma0 exactly on LUT nodes (J_sig = 0), |wind_co| exactly on wspd
-    nodes, exact midpoints between nodes (ties -> first index), zero / negative / infinite dsig."""
+@pytest.mark.parametrize("full_scan", [False, True])
+@pytest.mark.parametrize("lut_kind", ["gmf", "plateau", "bumpy"])
+def test_cross_pol_filter_adversarial(dev, golden, lut_kind, full_scan):
+    """Both cross-pol argmin paths of k_cross -- the exact interval search (LUT rows non-decreasing in wspd) and the
+    cooperative scan with its FP32 filter (`cr_full_scan`, and every non-monotone row) -- against the oracle on inputs
+    chosen to break a sloppy bound: dsig_cr from 1e-8 (SNR 100 in (1.25/SNR)**4) to 1e4, sigma0 exactly on LUT nodes
+    (J_sig = 0), |wind_co| exactly on wspd nodes, exact midpoints between nodes (ties -> first index), zero / negative
+    / infinite dsig.  LUTs: the GMF itself (strictly increasing), the GMF rounded to 0.5 dB (plateaus: runs of equal
+    costs, first index must win), and the GMF plus a ripple (non-monotone rows: interval search not applicable)."""
     torch, D, nat = dev
     d = golden("inv_slabs")
     gi, gwc, cr = d["inc_grid"], d["wspd_cr_grid"], d["cr_lut_db"]
+    if lut_kind == "plateau":
+        cr = np.round(cr * 2) / 2
+    elif lut_kind == "bumpy":
+        cr = cr + 0.4 * np.sin(np.arange(cr.shape[1]) * 0.9)[None, :]
     rng = np.random.default_rng(21)
     n = 200_000
     b = rng.integers(0, gi.size, n)
@@ -203,7 +212,8 @@ def test_cross_pol_filter_adversarial(dev, golden):
     dsig[1::997] = -0.3
     dsig[2::997] = np.inf
     plan = D.InversionPlan(cr=(D.to_device(cr), gi, gwc))
-    _, ox, _, ix = plan.invert(D.to_device(inc), None, D.to_device(s), D.to_device(dsig), None, sigma0_db=True, want_idx=True)
+    _, ox, _, ix = plan.invert(D.to_device(inc), None, D.to_device(s), D.to_device(dsig), None, sigma0_db=True, want_idx=True,
+                               cr_full_scan=full_scan)
     with np.errstate(all="ignore"):
         _, o_du, _, o_ix = oracle.invert(inc, np.nan, s, dsig, np.nan + 0j, cr_lut=cr, inc_cr_grid=gi, wspd_cr_grid=gwc)
     assert np.array_equal(ix.cpu().numpy(), o_ix), np.flatnonzero(ix.cpu().numpy() != o_ix)[:10]
@@ -214,9 +224,10 @@ def test_cross_pol_filter_adversarial(dev, golden):
     sl = slice(0, m)
     s_co = rng.uniform(-25, -5, m)
     anc = rng.uniform(3, 30, m) * np.exp(1j * rng.uniform(-np.pi, np.pi, m))
+    anc[::7] = gwc[rng.integers(0, gwc.size, anc[::7].size)]                     # |ancillary| on a cross-pol wspd node
     plan2 = D.InversionPlan(co=(D.to_device(co_lut), gi, gw, gp), cr=(D.to_device(cr), gi, gwc))
     oc, ox, ic, ix = plan2.invert(D.to_device(inc[sl]), D.to_device(s_co), D.to_device(s[sl]), D.to_device(dsig[sl]),
-                                  D.to_device(anc), sigma0_db=True, want_idx=True)
+                                  D.to_device(anc), sigma0_db=True, want_idx=True, cr_full_scan=full_scan)
     with np.errstate(all="ignore"):
         o_co, o_du, o_ic, o_ix = oracle.invert(inc[sl], s_co, s[sl], dsig[sl], anc, co_lut=co_lut, inc_grid=gi, wspd_grid=gw,
                                                phi_grid=gp, cr_lut=cr, inc_cr_grid=gi, wspd_cr_grid=gwc)

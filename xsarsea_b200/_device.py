@@ -212,7 +212,7 @@ class InversionPlan:
 
     def invert(self, inc, sigma0_co=None, sigma0_cr=None, dsig_cr=0.1, ancillary=None, *, sigma0_db=False,
                merge_dual=False, cr_abs=False, mode=nat.MODE_FAST, want_idx=False, out_co=None, out_cr=None,
-               need_co=False):
+               need_co=False, cr_full_scan=False):
         """Run K1 on device tensors (all the same shape; float64/complex128 or float32/complex64).
 
         Returns (wind_co complex128 | None, wind_cr complex128 (float64 if cr_abs) | None, idx_co, idx_cr).
@@ -244,7 +244,7 @@ class InversionPlan:
             a.dsig_cr_scalar = float(dsig_cr)
         a.dtype = nat.XS_F32 if f32 else nat.XS_F64
         a.flags = (nat.FLAG_SIGMA0_DB if sigma0_db else 0) | (nat.FLAG_MERGE_DUAL if merge_dual else 0) | (
-            nat.FLAG_CR_ABS if cr_abs else 0)
+            nat.FLAG_CR_ABS if cr_abs else 0) | (nat.FLAG_CR_FULL_SCAN if cr_full_scan else 0)
         a.mode = mode
         a.n_px = n
         has_co = self.co_grids is not None and s_co is not None

@@ -18,7 +18,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libxsarsea_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 XS_F64, XS_F32 = 0, 1
-FLAG_SIGMA0_DB, FLAG_MERGE_DUAL, FLAG_CR_ABS = 1, 2, 4
+FLAG_SIGMA0_DB, FLAG_MERGE_DUAL, FLAG_CR_ABS, FLAG_CR_FULL_SCAN = 1, 2, 4, 8
 MODE_FAST, MODE_FP64 = 0, 1
 
 GMF_IDS = {

@@ -173,15 +173,18 @@ __global__ void k_build_cr_tables(xs_plan pl) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < pl.n_wspd_cr) pl.wspd_cr_half[i] = (float)(0.5 * pl.wspd_cr_grid[i]);
     if (i < pl.n_inc_cr) {
-        int ok = 1;
+        int ok = 1, mono = 1;
         float amax = 0.f;
+        double prev = -CUDART_INF;
         for (int w = 0; w < pl.n_wspd_cr; ++w) {
             const double v = pl.cr_lut[(int64_t)i * pl.n_wspd_cr + w];
             ok &= isfinite(v) ? 1 : 0;
+            mono &= (v >= prev) ? 1 : 0;
+            prev = v;
             pl.cr_scan[(int64_t)i * pl.n_wspd_cr + w] = (float)v;
             if (isfinite(v)) amax = fmaxf(amax, (float)fabs(v) * 1.0000002f);
         }
-        pl.cr_finite[i] = ok;
+        pl.cr_finite[i] = ok | ((ok & mono) << 1);
         pl.cr_absmax[i] = amax;
     }
 }
@@ -794,6 +797,101 @@ __device__ __forceinline__ double exact_cost_cr(double L, double s, double dsig,
     return J;
 }
 
+// Exact cross-pol argmin of one pixel by interval search, for an incidence row that is finite and non-decreasing in
+// wspd (true of every built-in cross-pol model) with dsig > 0 and a strictly ascending wspd grid.  The reference cost
+// is J(w) = fl(a(w) + b(w)), a = fl(ts*ts), ts = fl(fl(L[w]-s)/dsig), b = fl(tw*tw), tw = fl(fl(w-mag)*0.5)
+// (windspeed.py:257-264; b absent without a co-pol solution).  IEEE rounding is monotone, so ts and tw are
+// non-decreasing in w, a and b are "valley" shaped, and J >= max(a, b).  With m0 = J of any candidate, every candidate
+// that can be the argmin (J <= m0, ties included) has a <= m0 and b <= m0, and each of these sets is an index interval
+// whose ends are found by bisection.  The interval is then scanned in index order with the reference's operations
+// (first minimum wins, like np.argmin).  Returns -1 when no finite bound exists (caller falls back to the full scan).
+__device__ __forceinline__ int cross_interval_search(const double *__restrict__ col, const double *__restrict__ wg, int n,
+                                                     double s, double dsig, double mag, bool hc) {
+    auto ts_at = [=](int w) { return __ddiv_rn(__dsub_rn(col[w], s), dsig); };
+    auto tw_at = [=](int w) { return __dmul_rn(__dsub_rn(wg[w], mag), 0.5); };
+    auto cost = [=](int w) { return exact_cost_cr(col[w], s, dsig, wg[w], mag, hc); };
+    int lo = 0, hi = n;  // k = first w with ts(w) >= 0
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (ts_at(mid) < 0.0)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    const int k = lo;
+    double m0 = CUDART_INF;
+    if (k < n) m0 = cost(k);
+    if (k > 0) m0 = fmin(m0, cost(k - 1));
+    int j = 0;
+    if (hc) {
+        lo = 0, hi = n;  // j = first w with tw(w) >= 0
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (tw_at(mid) < 0.0)
+                lo = mid + 1;
+            else
+                hi = mid;
+        }
+        j = lo;
+        if (j < n) m0 = fmin(m0, cost(j));
+        if (j > 0) m0 = fmin(m0, cost(j - 1));
+    }
+    if (!(m0 < CUDART_INF)) return -1;
+    // [first, last): candidates with a(w) <= m0
+    lo = 0, hi = k;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        const double t = ts_at(mid);
+        if (__dmul_rn(t, t) > m0)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    int first = lo;
+    lo = k, hi = n;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        const double t = ts_at(mid);
+        if (__dmul_rn(t, t) <= m0)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    int last = lo;
+    if (hc) {  // intersect with the candidates with b(w) <= m0
+        lo = 0, hi = j;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            const double t = tw_at(mid);
+            if (__dmul_rn(t, t) > m0)
+                lo = mid + 1;
+            else
+                hi = mid;
+        }
+        first = max(first, lo);
+        lo = j, hi = n;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            const double t = tw_at(mid);
+            if (__dmul_rn(t, t) <= m0)
+                lo = mid + 1;
+            else
+                hi = mid;
+        }
+        last = min(last, lo);
+    }
+    double best = CUDART_INF;
+    int res = -1;
+    for (int w = first; w < last; ++w) {
+        const double J = cost(w);
+        if (J < best) {
+            best = J;
+            res = w;
+        }
+    }
+    return res;
+}
+
 // ---- cross-pol / dual-pol pass + NaN classes + merge --------------------------------------------------------
 // windspeed.py:198-207 (NaN classes), :250 (no co-pol), :252-279 (cross-pol argmin), :422-428 (abs / merge).
 // A warp takes 32 consecutive pixels: every lane does the per-pixel scalar work of its own pixel (dB prologue,
@@ -830,7 +928,20 @@ __global__ void __launch_bounds__(256) k_cross(xs_plan pl, RasterArgs a, int64_t
                             pl.cr_finite[bin];
             }
         }
-        unsigned todo = __ballot_sync(full, scan);
+        // Pixels of monotone LUT rows are settled lane by lane by the exact interval search (some tens of FP64 cost
+        // evaluations instead of n_wspd_cr); the cooperative scan below remains for the other rows and for degenerate
+        // inputs.  XS_FLAG_CR_FULL_SCAN forces the cooperative scan (tests).
+        bool settled_own = false;
+        if (scan && filter_ok && p.dsig_cr > 0.0 && (pl.cr_finite[bin] & 2) && pl.wspd_cr_sorted &&
+            !(a.flags & XS_FLAG_CR_FULL_SCAN)) {
+            const int r = cross_interval_search(pl.cr_lut + (int64_t)bin * pl.n_wspd_cr, pl.wspd_cr_grid, pl.n_wspd_cr, p.s_cr,
+                                                p.dsig_cr, mag, has_co);
+            if (r >= 0) {
+                ix = r;
+                settled_own = true;
+            }
+        }
+        unsigned todo = __ballot_sync(full, scan && !settled_own);
         while (todo) {
             const int src = __ffs(todo) - 1;
             todo &= todo - 1;
@@ -1123,6 +1234,7 @@ extern "C" int xs_plan_create(const xs_plan_desc *d, void *stream, xs_plan **out
         pl->n_wspd_cr = d->n_wspd_cr;
         pl->cr_lut = d->cr_lut_db_dev;
         pl->inc_cr_sorted = strictly_ascending(d->inc_cr_grid_host, d->n_inc_cr);
+        pl->wspd_cr_sorted = strictly_ascending(d->wspd_cr_grid_host, d->n_wspd_cr);
         if ((rc = upload(&pl->inc_cr_grid, d->inc_cr_grid_host, d->n_inc_cr, st)) != XS_OK) return fail(rc);
         if ((rc = upload(&pl->wspd_cr_grid, d->wspd_cr_grid_host, d->n_wspd_cr, st)) != XS_OK) return fail(rc);
         if ((rc = xs::check(cudaMalloc(&pl->wspd_cr_half, sizeof(float) * (size_t)d->n_wspd_cr), "cudaMalloc")) != XS_OK) return fail(rc);

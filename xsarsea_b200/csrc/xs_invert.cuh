@@ -29,8 +29,10 @@ struct xs_plan {
     float *cr_scan;        // [n_inc_cr][n_wspd_cr] (float) LUT dB
     float *cr_absmax;      // [n_inc_cr] max |LUT dB| of the incidence row
     double w_cr_absmax;    // max |wspd_cr grid|
-    int *cr_finite;        // [n_inc_cr] 1 if every LUT value of the incidence row is finite
+    int *cr_finite;        // [n_inc_cr] bit 0: every LUT value of the incidence row is finite; bit 1: and the row is
+                           // non-decreasing in wspd (the exact interval search of k_cross applies)
     int inc_cr_sorted;
+    int wspd_cr_sorted;    // wspd_cr_grid strictly ascending
     // ---- counters of the last xs_invert (device) ----
     unsigned long long *stats;  // [8]
     int device;
