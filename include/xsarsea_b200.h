@@ -218,6 +218,19 @@ size_t xs_nesz_flatten_workspace_bytes(int64_t n_lines, int64_t n_samples);
 int xs_nesz_flatten(const void *noise_dev, const void *inc_dev, int64_t n_lines, int64_t n_samples, int dtype,
                     double *out_dev, void *workspace, size_t workspace_bytes, void *stream);
 
+/* ---- local gradients ---------------------------------------------- */
+
+/* Replaces local_gradients(image), gradients.py:588-634 (with R2, :676-722): Scharr gradient (cv2.Scharr, 3x3,
+ * BORDER_REFLECT_101) as a complex number, squared, reduced by 2 (5x5 binomial pre-smoothing with scipy's 'symm'
+ * boundary, NaN-skipping 2x2 mean with an odd trailing line/sample trimmed, 3x3 binomial post-smoothing).
+ * image [n_lines][n_samples] of `dtype`; outputs are [n_lines/2][n_samples/2]:
+ *   g2_dev complex128 = sqrt(R2(grad**2)), g3_dev float64 = R2(|grad**2|),
+ *   c_dev float64 = |R2(grad**2)| / (g3 + 1e-5) with values > 1 or NaN replaced by 0.
+ * workspace >= xs_local_gradients_workspace_bytes() (three half-size float64 planes). */
+size_t xs_local_gradients_workspace_bytes(int64_t n_lines, int64_t n_samples);
+int xs_local_gradients(const void *image_dev, int64_t n_lines, int64_t n_samples, int dtype, void *g2_dev,
+                       double *g3_dev, double *c_dev, void *workspace, size_t workspace_bytes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,7 +1,7 @@
 """Generate golden vectors from the REAL reference arithmetic (dev-time; needs /root/reference + numba).
 
 Run:  python tests/golden/make_golden.py
-Writes tests/golden/gmf_points.npz, inv_small.npz, inv_slabs.npz, inv_ifr2.npz, dsig_utils.npz.
+Writes tests/golden/gmf_points.npz, inv_small.npz, inv_slabs.npz, inv_ifr2.npz, dsig_utils.npz, gradients.npz.
 
 Everything numerical in these files comes out of the reference's own code, executed through
 tests/golden/_refload.py: the numba-compiled scalar GMFs (gmfs.py:206-230 over gmfs_impl.py) and the
@@ -268,12 +268,37 @@ def dsig_utils():
     print("dsig_utils.npz")
 
 
+def gradients():
+    """local_gradients of gradients.py:588-634 evaluated with the libraries the reference delegates to (cv2.Scharr,
+    scipy.signal.convolve2d) through oracle/gradients.py -- the reference function itself needs xarray (not installable
+    here), so this file pins the third-party arithmetic, not an output of the reference function."""
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from oracle import gradients as og
+
+    rng = np.random.default_rng(11)
+    out = {}
+    for tag, (h, w) in (("odd", (101, 203)), ("even", (64, 96)), ("tiny", (2, 2)), ("thin", (3, 40))):
+        yy, xx = np.mgrid[0:h, 0:w]
+        img = 0.05 + 0.02 * np.sin(0.21 * xx + 0.13 * yy) + 0.01 * rng.standard_normal((h, w))   # streaky sigma0
+        if tag == "odd":
+            img[40:44, 50:60] = np.nan       # a masked patch: NaN spreads through the stencils, partial 2x2 blocks
+            img[0, 0] = np.nan               # corner: exercises both border rules
+        g2, g3, c = og.local_gradients(img)
+        out.update({f"{tag}/image": img, f"{tag}/G2": g2, f"{tag}/G3": g3, f"{tag}/c": c})
+    np.savez_compressed(os.path.join(HERE, "gradients.npz"), **out)
+    print("gradients.npz")
+
+
 if __name__ == "__main__":
     if sys.argv[1:] == ["dsig_utils"]:
         dsig_utils()
+        sys.exit(0)
+    if sys.argv[1:] == ["gradients"]:
+        gradients()
         sys.exit(0)
     gmf_points()
     inv_small()
     inv_slabs()
     inv_ifr2()
     dsig_utils()
+    gradients()

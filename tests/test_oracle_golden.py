@@ -155,3 +155,41 @@ def test_dsig_oracle_bit_exact_against_reference_outputs(golden):
         assert np.isnan(flat).all() and np.isnan(g["noise_allnan_flat"]).all()
     with pytest.raises(ValueError):
         od.get_dsig("other", 1.0, 1.0, 1.0)
+
+
+def test_gradients_oracle_against_golden_and_an_independent_restatement(golden):
+    """oracle/gradients.py reproduces tests/golden/gradients.npz bit for bit (same cv2 / scipy calls), and agrees with
+    a restatement that uses neither library (explicit Scharr stencil with reflect-101 borders, separable binomial
+    filters with symmetric borders) to rounding -- which pins the border rules and the filter taps independently."""
+    from oracle import gradients as og
+
+    g = golden("gradients")
+    for tag in ("odd", "even", "tiny", "thin"):
+        img = g[tag + "/image"]
+        g2, g3, c = og.local_gradients(img)
+        assert same(g2, g[tag + "/G2"]) and same(g3, g[tag + "/G3"]) and same(c, g[tag + "/c"]), tag
+
+    img = g["even/image"]
+    p = np.pad(img, 1, mode="reflect")                       # cv2 BORDER_REFLECT_101
+    dx, dy = p[:, 2:] - p[:, :-2], p[2:, :] - p[:-2, :]
+    gr = 10 * dx[1:-1] + 3 * (dx[:-2] + dx[2:])
+    gi = 10 * dy[:, 1:-1] + 3 * (dy[:, :-2] + dy[:, 2:])
+    z = (gr + 1j * gi) ** 2
+
+    def binom(a, taps):
+        r = len(taps) // 2
+        for ax in (0, 1):
+            q = np.pad(a, [(r, r) if k == ax else (0, 0) for k in (0, 1)], mode="symmetric")   # scipy 'symm'
+            a = sum(t * np.take(q, np.arange(i, i + a.shape[ax]), axis=ax) for i, t in enumerate(taps))
+        return a
+
+    def r2(a):
+        a = binom(a, np.array([1, 4, 6, 4, 1]) / 16)
+        a = a[:a.shape[0] // 2 * 2, :a.shape[1] // 2 * 2].reshape(a.shape[0] // 2, 2, a.shape[1] // 2, 2).mean(axis=(1, 3))
+        return binom(a, np.array([1, 2, 1]) / 4)
+
+    grad2, grad3 = r2(z), r2(np.abs(z))
+    np.testing.assert_allclose(np.sqrt(grad2), g["even/G2"], rtol=0, atol=1e-12 * np.abs(g["even/G2"]).max())
+    np.testing.assert_allclose(grad3, g["even/G3"], rtol=1e-12)
+    cq = np.abs(grad2) / (grad3 + 1e-5)
+    np.testing.assert_allclose(np.where(cq <= 1, cq, 0), g["even/c"], rtol=0, atol=1e-12)

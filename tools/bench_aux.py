@@ -89,6 +89,13 @@ out["nesz_flattening_10000x10400"] = dict(ms=best, ms_mean=mean, algorithmic_B_p
                                           frac_of_measured_hbm=32 * H * W / best / 1e6 / HBM_GBS)
 del inc2, scr, nesz
 
+# ---- local_gradients (row F4): image read once (8 B/px), three half-size outputs (32 B per 4 px) ----
+img = 0.1 + 0.02 * torch.rand(H, W, dtype=torch.float64, device="cuda")
+best, mean = timeit(lambda: D.local_gradients(img), warm=5, reps=7, inner=5)
+out["local_gradients_10000x10400"] = dict(ms=best, ms_mean=mean, algorithmic_B_per_px=16, GBps=16 * H * W / best / 1e6,
+                                          frac_of_measured_hbm=16 * H * W / best / 1e6 / HBM_GBS, Gpx_per_s=H * W / best / 1e6)
+del img
+
 # ---- inversion: cross-pol only (config 4, 10000 x 10000) and co-pol only (config 1, 1000 x 1000) ----
 plan_x = D.InversionPlan(cr=(cr, gi, gwc))
 inc, s_co, s_cr, anc = bench.synth_scene_device(10000, 10000, 3)

@@ -5,7 +5,7 @@ done by hand-written CUDA kernels reached through a C-ABI shared library (includ
 """
 __version__ = "0.1.0"
 
-from . import windspeed  # noqa: E402,F401
+from . import gradients, windspeed  # noqa: E402,F401
 from .detrend import (  # noqa: E402,F401
     dir_meteo_to_oceano,
     dir_meteo_to_sample,
@@ -18,5 +18,5 @@ from .detrend import (  # noqa: E402,F401
 
 # names of xsarsea/__init__.py:1-11 that belong to the hot path or are one-line helpers around it; get_test_file (HTTP
 # download of test data) and read_sarwing_owi (NetCDF-4 reader) are out of scope
-__all__ = ["windspeed", "sigma0_detrend", "dir_meteo_to_sample", "dir_sample_to_meteo", "dir_meteo_to_oceano",
+__all__ = ["windspeed", "gradients", "sigma0_detrend", "dir_meteo_to_sample", "dir_sample_to_meteo", "dir_meteo_to_oceano",
            "dir_oceano_to_meteo", "dir_to_180", "dir_to_360", "__version__"]

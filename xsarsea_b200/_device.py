@@ -150,6 +150,27 @@ def nesz_flatten(noise, inc):
     return out
 
 
+def local_gradients(image):
+    """(G2 complex128, G3 float64, c float64), each [H//2, W//2], of a 2-D device image (reference local_gradients,
+    gradients.py:588-634)."""
+    torch = _t()
+    L = nat.load()
+    assert image.dim() == 2
+    dt, (image,) = _same_real_dtype(image)
+    h, w = image.shape
+    h2, w2 = h // 2, w // 2
+    g2 = torch.empty((h2, w2), dtype=torch.complex128, device="cuda")
+    g3 = torch.empty((h2, w2), dtype=torch.float64, device="cuda")
+    c = torch.empty((h2, w2), dtype=torch.float64, device="cuda")
+    if h2 == 0 or w2 == 0:
+        return g2, g3, c
+    need = int(L.xs_local_gradients_workspace_bytes(h, w))
+    ws = torch.empty(need, dtype=torch.uint8, device="cuda")
+    nat.check(L.xs_local_gradients(nat.dptr(image), h, w, dt, nat.dptr(g2), nat.dptr(g3), nat.dptr(c), nat.dptr(ws), need,
+                                   nat.stream_ptr()), "xs_local_gradients")
+    return g2, g3, c
+
+
 class InversionPlan:
     """Owns an xs_plan: the device LUTs of one (co-pol, cross-pol) model pair plus the scan image.
 

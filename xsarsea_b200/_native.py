@@ -42,6 +42,7 @@ EXPORTS = [
     "xs_lut_to_db", "xs_lut_to_linear", "xs_plan_create", "xs_plan_destroy", "xs_invert_workspace_bytes",
     "xs_invert", "xs_plan_last_stats", "xs_plan_last_scan_ms", "xs_plan_debug_counters", "xs_detrend",
     "xs_dsig", "xs_dsig_wspd", "xs_nesz_flatten_workspace_bytes", "xs_nesz_flatten",
+    "xs_local_gradients_workspace_bytes", "xs_local_gradients",
 ]
 
 DSIG_IDS = {"gmf_s1_v2": 0, "gmf_rs2_v2": 1, "sarwing_lut_cmodms1ahw": 2, "nc_lut_cmodms1ahw": 2}
@@ -163,6 +164,10 @@ def load():
         L.xs_nesz_flatten_workspace_bytes.argtypes = [i64, i64]
         L.xs_nesz_flatten.restype = i32
         L.xs_nesz_flatten.argtypes = [vp, vp, i64, i64, i32, vp, vp, sz, vp]
+        L.xs_local_gradients_workspace_bytes.restype = sz
+        L.xs_local_gradients_workspace_bytes.argtypes = [i64, i64]
+        L.xs_local_gradients.restype = i32
+        L.xs_local_gradients.argtypes = [vp, i64, i64, i32, vp, vp, vp, vp, sz, vp]
         if L.xs_abi_version() != 1:
             raise NativeError("libxsarsea_b200.so ABI version mismatch")
         _lib = L

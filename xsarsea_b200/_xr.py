@@ -115,6 +115,27 @@ class DataArrayLite:
                              self.attrs, self.name)
 
 
+class DatasetLite(dict):
+    """Minimal stand-in for xarray.Dataset: a dict of variables with attribute access (`ds.G2`, `ds["G2"]`)."""
+
+    def __getattr__(self, item):
+        try:
+            return self[item]
+        except KeyError:
+            raise AttributeError(item) from None
+
+    @property
+    def data_vars(self):
+        return self
+
+
+def make_dataset(variables):
+    """xarray.Dataset of named DataArrays when xarray is installed, DatasetLite otherwise."""
+    if HAVE_XARRAY:
+        return _xarray.merge([v.rename(k) if getattr(v, "name", None) != k else v for k, v in variables.items()])
+    return DatasetLite(variables)
+
+
 def is_labelled(x) -> bool:
     """True for xarray.DataArray and DataArrayLite (duck typed)."""
     return hasattr(x, "dims") and hasattr(x, "data") and hasattr(x, "attrs")
