@@ -24,6 +24,7 @@ constexpr int kGP_H = 2 * kGT_H, kGP_W = 2 * kGT_W;  // pre-smoothed full-size p
 constexpr int kGG_H = kGP_H + 4, kGG_W = kGP_W + 4;  // grad12 with the 5x5 halo
 constexpr int kGI_H = kGG_H + 2, kGI_W = kGG_W + 2;  // image with the Scharr halo
 
+static_assert(kGG_H % 2 == 0 && kGG_W % 2 == 0 && kGI_W % 2 == 0, "16-byte shared-memory accesses need even extents");
 struct GradSmem {
     double g[3][kGG_H][kGG_W];                 // re, im, |.| of grad12
     union {
@@ -58,28 +59,40 @@ __global__ void __launch_bounds__(256) k_grad_reduce(const T *__restrict__ image
         sm.img[i][j] = (double)__ldg(image + (int64_t)y * w + x);
     }
     __syncthreads();
-    // ---- grad12 at the in-range positions of the tile ----
-    for (int e = threadIdx.x; e < kGG_H * kGG_W; e += blockDim.x) {
-        const int i = e / kGG_W, j = e - i * kGG_W;
-        const int y = gy0 + i, x = gx0 + j;
-        if (y < 0 || y >= h || x < 0 || x >= w) continue;
-        // separable Scharr as cv2 evaluates it: difference along one axis, then 10*centre + 3*(sum of neighbours)
-        const double (*I)[kGI_W] = sm.img;
-        const int a = i + 1, b = j + 1;  // position in the image tile
-        const double dx0 = I[a - 1][b + 1] - I[a - 1][b - 1], dx1 = I[a][b + 1] - I[a][b - 1], dx2 = I[a + 1][b + 1] - I[a + 1][b - 1];
-        const double dy0 = I[a + 1][b - 1] - I[a - 1][b - 1], dy1 = I[a + 1][b] - I[a - 1][b], dy2 = I[a + 1][b + 1] - I[a - 1][b + 1];
-        const double gr = __dadd_rn(__dmul_rn(10.0, dx1), __dmul_rn(3.0, __dadd_rn(dx0, dx2)));
-        const double gi = __dadd_rn(__dmul_rn(10.0, dy1), __dmul_rn(3.0, __dadd_rn(dy0, dy2)));
-        // numpy complex product (a+ib)(a+ib): re = a*a - b*b, im = a*b + b*a (keeps the sign of a zero imaginary part)
-        const double re = __dsub_rn(__dmul_rn(gr, gr), __dmul_rn(gi, gi));
-        const double im = __dadd_rn(__dmul_rn(gr, gi), __dmul_rn(gi, gr));
-        sm.g[0][i][j] = re;
-        sm.g[1][i][j] = im;
-        sm.g[2][i][j] = fma(gr, gr, gi * gi);  // |grad**2| = |grad|**2 (np.abs(grad12) to rounding, without a hypot)
+    // ---- grad12 at the in-range positions of the tile: a 2x2 block per thread from a 4x4 image patch (16-byte loads,
+    //      consecutive lanes 16 bytes apart: no bank conflicts, 32 B of shared-memory reads per value) ----
+    for (int e = threadIdx.x; e < (kGG_H / 2) * (kGG_W / 2); e += blockDim.x) {
+        const int bi = e / (kGG_W / 2), bj = e - bi * (kGG_W / 2);
+        const int i = 2 * bi, j = 2 * bj;
+        double I[4][4];  // image tile rows i..i+3, columns j..j+3 (tile position = g position + 1 on both axes)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const double2 lo = *reinterpret_cast<const double2 *>(&sm.img[i + r][j]);
+            const double2 hi = *reinterpret_cast<const double2 *>(&sm.img[i + r][j + 2]);
+            I[r][0] = lo.x, I[r][1] = lo.y, I[r][2] = hi.x, I[r][3] = hi.y;
+        }
+#pragma unroll
+        for (int di = 0; di < 2; ++di)
+#pragma unroll
+            for (int dj = 0; dj < 2; ++dj) {
+                const int y = gy0 + i + di, x = gx0 + j + dj;
+                if (y < 0 || y >= h || x < 0 || x >= w) continue;
+                // separable Scharr as cv2 evaluates it: difference along one axis, then 10*centre + 3*(sum of neighbours)
+                const int a = di + 1, b = dj + 1;
+                const double dx0 = I[a - 1][b + 1] - I[a - 1][b - 1], dx1 = I[a][b + 1] - I[a][b - 1], dx2 = I[a + 1][b + 1] - I[a + 1][b - 1];
+                const double dy0 = I[a + 1][b - 1] - I[a - 1][b - 1], dy1 = I[a + 1][b] - I[a - 1][b], dy2 = I[a + 1][b + 1] - I[a - 1][b + 1];
+                const double gr = __dadd_rn(__dmul_rn(10.0, dx1), __dmul_rn(3.0, __dadd_rn(dx0, dx2)));
+                const double gi = __dadd_rn(__dmul_rn(10.0, dy1), __dmul_rn(3.0, __dadd_rn(dy0, dy2)));
+                // numpy complex product (a+ib)(a+ib): re = a*a - b*b, im = a*b + b*a (keeps the sign of a zero imaginary part)
+                sm.g[0][i + di][j + dj] = __dsub_rn(__dmul_rn(gr, gr), __dmul_rn(gi, gi));
+                sm.g[1][i + di][j + dj] = __dadd_rn(__dmul_rn(gr, gi), __dmul_rn(gi, gr));
+                sm.g[2][i + di][j + dj] = fma(gr, gr, gi * gi);  // |grad**2| = |grad|**2 (np.abs(grad12) to rounding, no hypot)
+            }
     }
     __syncthreads();
     // ---- out-of-range halo = 'symm' reflection of the in-range values (the reflected positions are in the tile) ----
-    for (int e = threadIdx.x; e < kGG_H * kGG_W; e += blockDim.x) {
+    const bool interior = gy0 >= 0 && gx0 >= 0 && gy0 + kGG_H <= h && gx0 + kGG_W <= w;  // CTA-uniform: no halo to mirror
+    for (int e = threadIdx.x; !interior && e < kGG_H * kGG_W; e += blockDim.x) {
         const int i = e / kGG_W, j = e - i * kGG_W;
         const int y = gy0 + i, x = gx0 + j;
         if (y >= 0 && y < h && x >= 0 && x < w) continue;
@@ -88,21 +101,17 @@ __global__ void __launch_bounds__(256) k_grad_reduce(const T *__restrict__ image
 #pragma unroll
         for (int k = 0; k < 3; ++k) sm.g[k][i][j] = ok ? sm.g[k][si][sj] : 0.0;
     }
-    __syncthreads();
+    if (!interior) __syncthreads();
     // ---- 5-tap binomial along the sample axis (img is dead: hs aliases it) ----
-    // four consecutive outputs per thread from eight loaded values (shared-memory bandwidth bounds this kernel)
-    for (int e = threadIdx.x; e < 3 * kGG_H * (kGP_W / 4); e += blockDim.x) {
-        const int k = e / (kGG_H * (kGP_W / 4)), r = e - k * (kGG_H * (kGP_W / 4));
-        const int i = r / (kGP_W / 4), j = 4 * (r - i * (kGP_W / 4));
+    // two outputs per thread from three 16-byte loads, consecutive lanes 16 bytes apart (no bank conflicts)
+    for (int e = threadIdx.x; e < 3 * kGG_H * (kGP_W / 2); e += blockDim.x) {
+        const int k = e / (kGG_H * (kGP_W / 2)), r = e - k * (kGG_H * (kGP_W / 2));
+        const int i = r / (kGP_W / 2), j = 2 * (r - i * (kGP_W / 2));
         const double2 *row = reinterpret_cast<const double2 *>(&sm.g[k][i][j]);  // 16-byte aligned: j and kGG_W are even
-        const double2 v0 = row[0], v1 = row[1], v2 = row[2], v3 = row[3];
-        const double v[8] = {v0.x, v0.y, v1.x, v1.y, v2.x, v2.y, v3.x, v3.y};
-        double o[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) o[q] = (v[q] + v[q + 4]) * 0.0625 + (v[q + 1] + v[q + 3]) * 0.25 + v[q + 2] * 0.375;
-        double2 *dst = reinterpret_cast<double2 *>(&sm.hs[k][i][j]);
-        dst[0] = make_double2(o[0], o[1]);
-        dst[1] = make_double2(o[2], o[3]);
+        const double2 v0 = row[0], v1 = row[1], v2 = row[2];
+        const double o0 = (v0.x + v2.x) * 0.0625 + (v0.y + v1.y) * 0.25 + v1.x * 0.375;
+        const double o1 = (v0.y + v2.y) * 0.0625 + (v1.x + v2.x) * 0.25 + v1.y * 0.375;
+        *reinterpret_cast<double2 *>(&sm.hs[k][i][j]) = make_double2(o0, o1);
     }
     __syncthreads();
     // ---- 5-tap binomial along the line axis + NaN-skipping 2x2 mean ----
