@@ -807,13 +807,13 @@ __device__ __forceinline__ double exact_cost_cr(double L, double s, double dsig,
 // (first minimum wins, like np.argmin).  Returns -1 when no finite bound exists (caller falls back to the full scan).
 __device__ __forceinline__ int cross_interval_search(const double *__restrict__ col, const double *__restrict__ wg, int n,
                                                      double s, double dsig, double mag, bool hc) {
-    auto ts_at = [=](int w) { return __ddiv_rn(__dsub_rn(col[w], s), dsig); };
+    auto num_at = [=](int w) { return __dsub_rn(col[w], s); };  // ts = num/dsig has the sign of num (dsig > 0)
     auto tw_at = [=](int w) { return __dmul_rn(__dsub_rn(wg[w], mag), 0.5); };
     auto cost = [=](int w) { return exact_cost_cr(col[w], s, dsig, wg[w], mag, hc); };
-    int lo = 0, hi = n;  // k = first w with ts(w) >= 0
+    int lo = 0, hi = n;  // k = first w with num(w) >= 0
     while (lo < hi) {
         const int mid = (lo + hi) >> 1;
-        if (ts_at(mid) < 0.0)
+        if (num_at(mid) < 0.0)
             lo = mid + 1;
         else
             hi = mid;
@@ -837,12 +837,25 @@ __device__ __forceinline__ int cross_interval_search(const double *__restrict__ 
         if (j > 0) m0 = fmin(m0, cost(j - 1));
     }
     if (!(m0 < CUDART_INF)) return -1;
-    // [first, last): candidates with a(w) <= m0
+    // a(w) > m0 ?  a = fl(fl(num/dsig)^2) = (num/dsig)^2 (1+d1)^2 (1+d2), |d| <= 2^-53, and q = fl(fl(sqrt(m0))*dsig) =
+    // dsig*sqrt(m0)(1+d3)(1+d4): |num| outside q(1 -+ 1e-14) decides the comparison without the division (the software
+    // FP64 division dominated this kernel); inside that sliver, or where the magnitudes leave the normal range so that
+    // the relative-error model does not hold, the reference's own operations are evaluated.
+    const double q = sqrt(m0) * dsig;
+    const bool cheap = m0 >= 1e-290 && m0 <= 1e290 && q >= 1e-290 && q <= 1e290;
+    const double q_hi = q * (1.0 + 1e-14), q_lo = q * (1.0 - 1e-14);
+    auto a_gt_m0 = [=](int w) {
+        const double num = num_at(w), an = fabs(num);
+        if (cheap && an > q_hi) return true;
+        if (cheap && an < q_lo) return false;
+        const double t = __ddiv_rn(num, dsig);
+        return __dmul_rn(t, t) > m0;
+    };
+    // [first, last): candidates with a(w) <= m0 (a is non-increasing left of k, non-decreasing from k on)
     lo = 0, hi = k;
     while (lo < hi) {
         const int mid = (lo + hi) >> 1;
-        const double t = ts_at(mid);
-        if (__dmul_rn(t, t) > m0)
+        if (a_gt_m0(mid))
             lo = mid + 1;
         else
             hi = mid;
@@ -851,8 +864,7 @@ __device__ __forceinline__ int cross_interval_search(const double *__restrict__ 
     lo = k, hi = n;
     while (lo < hi) {
         const int mid = (lo + hi) >> 1;
-        const double t = ts_at(mid);
-        if (__dmul_rn(t, t) <= m0)
+        if (!a_gt_m0(mid))
             lo = mid + 1;
         else
             hi = mid;
