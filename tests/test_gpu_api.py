@@ -402,3 +402,55 @@ def test_config5_ew_scene_dual_pol_with_dsig_raster_and_detrend(ws):
     out = D.detrend(s_co, prof)
     ratio = prof / prof.mean()
     assert torch.allclose(out * ratio, s_co, rtol=1e-14, atol=0)
+
+
+def test_device_resident_chain_noise_flattening_to_gradients(ws):
+    """The whole chain a dual-pol user runs (docs/examples/windspeed_retrieval_L1.ipynb cells 26-33 + the streaks
+    notebook), device-resident from end to end: nesz_flattening -> get_dsig -> invert_from_model (dual-pol, dsig_cr
+    raster) and sigma0_detrend -> local_gradients, against the same chain computed by the oracles on the host."""
+    import torch
+
+    import xsarsea_b200
+    from oracle import dsig as od
+    from oracle import gradients as og
+    from xsarsea_b200 import _xr
+
+    h, w = 120, 260
+    rng = np.random.default_rng(17)
+    inc = np.broadcast_to(np.linspace(20.0, 45.0, w), (h, w)).copy()
+    wspd, phi = rng.uniform(3, 22, (h, w)), rng.uniform(0, 360, (h, w))
+    s_co = oracle.gmf_eval("gmf_cmod5n", inc, wspd, phi) * np.exp(rng.normal(0, 0.05, (h, w)))
+    s_cr = oracle.gmf_eval("gmf_s1_v2", inc, wspd) * np.exp(rng.normal(0, 0.05, (h, w)))
+    anc = (wspd + rng.normal(0, 2, (h, w))) * np.exp(1j * np.deg2rad(phi + rng.normal(0, 20, (h, w))))
+    nesz = 10 ** ((-33.0 + 0.1 * (inc - 20) + rng.normal(0, 0.2, (h, w))) / 10)
+    nesz[rng.random((h, w)) < 0.01] = np.nan
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    model = ("gmf_cmod5n", "gmf_s1_v2")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        # device chain
+        flat_d = ws.nesz_flattening(t(nesz), t(inc))
+        dsig_d = ws.get_dsig("gmf_s1_v2", t(inc), t(s_cr), flat_d)
+        co_d, dual_d = ws.invert_from_model(t(inc), t(s_co), t(s_cr), ancillary_wind=t(anc), dsig_cr=dsig_d, model=model, **KW)
+        assert all(x.is_cuda for x in (flat_d, dsig_d, co_d, dual_d))
+        # host chain through the oracles
+        flat_o = od.nesz_flattening(nesz, inc)
+        dsig_o = od.get_dsig("gmf_s1_v2", inc, s_cr, flat_o)
+        o_co, o_du, _, _ = oracle_dual(inc, s_co, s_cr, anc, dsig_cr=dsig_o)
+        with np.errstate(invalid="ignore"):
+            merged = np.where((np.abs(o_co) < 5) | (np.abs(o_du) < 5), o_co, o_du)
+    np.testing.assert_allclose(flat_d.cpu().numpy(), flat_o, rtol=1e-10)
+    np.testing.assert_allclose(dsig_d.cpu().numpy(), dsig_o, rtol=1e-9)
+    wind_close(co_d.cpu().numpy(), o_co)
+    wind_close(dual_d.cpu().numpy(), merged)
+    # detrend (labelled inputs: the reference's sigma0_detrend needs .isel) -> local_gradients
+    lab = lambda a: _xr.make_dataarray(a, dims=("line", "sample"), coords={"line": np.arange(h), "sample": np.arange(w)})
+    det = xsarsea_b200.sigma0_detrend(lab(s_co), lab(inc), model="gmf_cmod5n")
+    prof = oracle.gmf_eval("gmf_cmod5n", inc[0], np.full(w, 10.0), np.full(w, 45.0))
+    det_o = s_co / (prof / np.nanmean(prof))
+    np.testing.assert_allclose(np.asarray(det.data), det_o, rtol=1e-12)
+    ds = xsarsea_b200.gradients.local_gradients(det)
+    g2, g3, c = og.local_gradients(det_o)
+    for got, want in ((ds.G2, g2), (ds.G3, g3), (ds.c, c)):
+        got = np.asarray(got.data)
+        assert np.abs(got - want).max() <= 1e-9 * np.abs(want).max()
