@@ -449,6 +449,8 @@ def test_device_resident_chain_noise_flattening_to_gradients(ws):
     prof = oracle.gmf_eval("gmf_cmod5n", inc[0], np.full(w, 10.0), np.full(w, 45.0))
     det_o = s_co / (prof / np.nanmean(prof))
     np.testing.assert_allclose(np.asarray(det.data), det_o, rtol=1e-12)
+    det_t = xsarsea_b200.sigma0_detrend(t(s_co), t(inc), model="gmf_cmod5n")      # CUDA tensors in -> CUDA tensor out
+    assert det_t.is_cuda and np.array_equal(det_t.cpu().numpy(), np.asarray(det.data), equal_nan=True)
     ds = xsarsea_b200.gradients.local_gradients(det)
     g2, g3, c = og.local_gradients(det_o)
     for got, want in ((ds.G2, g2), (ds.G3, g3), (ds.c, c)):

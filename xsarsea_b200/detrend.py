@@ -32,10 +32,16 @@ def sigma0_detrend(sigma0, inc_angle, wind_speed_gmf=np.array([10.0]), wind_dir_
     for var in [wind_speed_gmf, wind_dir_gmf]:
         if var.ndim == 1 and var.size > 1:
             raise ValueError("wind_speed_gmf and wind_dir_gmf size must be 1 or 0")
-    inc_line = np.asarray(inc_angle.isel(line=0).data, dtype=np.float64).reshape(-1)  # needs a labelled array, like the reference
+    torch = nat.torch_cuda()
+    resident = type(sigma0).__module__.split(".")[0] == "torch"
+    if resident:
+        # device-resident extension: CUDA tensors in ([..., line, sample] sigma0, [line, sample] incidence), CUDA tensor out
+        inc_t = inc_angle if type(inc_angle).__module__.split(".")[0] == "torch" else torch.as_tensor(np.asarray(inc_angle))
+        inc_line = inc_t.reshape(-1, inc_t.shape[-1])[0].detach().cpu().numpy().astype(np.float64)
+    else:
+        inc_line = np.asarray(inc_angle.isel(line=0).data, dtype=np.float64).reshape(-1)  # needs a labelled array, like the reference
     wspd = float(np.asarray(wind_speed_gmf).reshape(-1)[0])
     phi = float(np.asarray(wind_dir_gmf).reshape(-1)[0])
-    torch = nat.torch_cuda()
 
     t_inc = dev.to_device(inc_line)
     if getattr(model, "_device_id", None) is not None:
@@ -50,8 +56,15 @@ def sigma0_detrend(sigma0, inc_angle, wind_speed_gmf=np.array([10.0]), wind_dir_
             vals = model(inc_line, np.array([wspd]))
         profile = dev.to_device(np.asarray(vals, dtype=np.float64).reshape(-1))
 
-    s0 = np.asarray(sigma0.data if _xr.is_labelled(sigma0) else sigma0)
     w = inc_line.size
+    if resident:
+        if sigma0.shape[-1] != w:
+            raise ValueError(f"sigma0 sample axis ({sigma0.shape[-1]}) does not match inc_angle ({w})")
+        t_s0 = sigma0.cuda()
+        if t_s0.dtype not in (torch.float32, torch.float64):
+            t_s0 = t_s0.to(torch.float64)
+        return dev.detrend(t_s0.reshape(-1, w), profile).reshape(sigma0.shape)
+    s0 = np.asarray(sigma0.data if _xr.is_labelled(sigma0) else sigma0)
     if s0.shape[-1] != w:
         raise ValueError(f"sigma0 sample axis ({s0.shape[-1]}) does not match inc_angle ({w})")
     f32 = s0.dtype == np.float32
