@@ -254,6 +254,12 @@ def main():
         run_reference(args, rank, world)
         return
 
+    # stdout carries exactly one JSON line: anything a library prints on fd 1 meanwhile (NCCL's version banner, for one)
+    # goes to stderr instead
+    sys.stdout.flush()
+    stdout_fd = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
 
@@ -377,6 +383,8 @@ def main():
                "sample": f"{sample[0].shape[0]}x{sample[0].shape[1]} px crop across the swath of the same scene, numba "
                          f"gufunc with the reference's decorator arguments (oracle/numba_port.py), JIT excluded"}
 
+    sys.stdout.flush()
+    os.dup2(stdout_fd, 1)
     if rank == 0:
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": "px/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -399,6 +407,8 @@ def main():
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
             "stats": stats,
         }))
+    sys.stdout.flush()
+    os.dup2(2, 1)
     if world > 1:
         dist.destroy_process_group()
 
