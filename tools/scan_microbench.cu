@@ -17,6 +17,7 @@ constexpr int KP = 3, ROWS = 32;
 // 10: centred expansion: per pair Lc = L - c and M = Lc^2 + w2q are shared by the P pixels; per pixel two FFMA2
 //     (a = k_p*Lc + M, J = nwh*g + a) and FMNMX3.
 // 11: w^2/4 folded out of the per-candidate work: t' = nwh*g (FMUL2), J = d*d + t', row minimum r, then m = min(m, r + w2q).
+// 12-15: the running minimum taken by integer min/max instructions on the float bit patterns (timing only).
 // 5: as 0 without the min (sum into m with FADD: all FMA pipe). 6: only the loads + FMNMX3 (no FMA-pipe work)
 template <int MODE, int P>
 __global__ void __launch_bounds__(256, 2) k(const float *__restrict__ src, const float2 *__restrict__ rowtab, float *out, int reps) {
@@ -114,7 +115,12 @@ __global__ void __launch_bounds__(256, 2) k(const float *__restrict__ src, const
                         const u64 J = ffma2(d, d, t);
                         float j0, j1;
                         unpack2(J, j0, j1);
-                        if (MODE == 1) m[p] = fminf(fminf(m[p], j0), j1);
+                        if (MODE == 12) m[p] = __int_as_float(__vimin3_s32(__float_as_int(m[p]), __float_as_int(j0), __float_as_int(j1)));
+                        else if (MODE == 13) m[p] = __int_as_float(min(min(__float_as_int(m[p]), __float_as_int(j0)), __float_as_int(j1)));
+                        else if (MODE == 14) m[p] = __uint_as_float(__vimin3_u32(__float_as_uint(m[p]), __float_as_uint(j0), __float_as_uint(j1)));
+                        else if (MODE == 15) m[p] = __int_as_float(__vimax3_s32(__float_as_int(m[p]), __float_as_int(j0), __float_as_int(j1)));
+                        else if (MODE == 16) { if (j & 1) m[p] = fmin3(m[p], j0, j1); else m[p] = fminf(m[p], j0 + j1); }
+                        else if (MODE == 1) m[p] = fminf(fminf(m[p], j0), j1);
                         else if (MODE == 5) m[p] = m[p] + j0 + j1;
                         else m[p] = fmin3(m[p], j0, j1);
                     }
@@ -236,6 +242,10 @@ int main() {
         run<9, 8>("hybrid B: scalar t and d, packed J", src, rt, out);
         run<10, 8>("centred expansion: 2 FFMA2 + FMNMX3 per pixel pair", src, rt, out);
         run<11, 8>("w2q folded out: FADD2 + FMUL2 + FFMA2 + row min", src, rt, out);
+        run<12, 8>("min as VIMNMX3.S32 on the float bits", src, rt, out);
+        run<13, 8>("min as 2 x IMNMX.S32", src, rt, out);
+        run<14, 8>("min as VIMNMX3.U32", src, rt, out);
+        run<15, 8>("max as VIMNMX3.S32", src, rt, out);
         run<0, 4>("as k_scan_co, P=4", src, rt, out);
         run<3, 4>("scalar, P=4", src, rt, out);
     }
