@@ -280,6 +280,80 @@ __global__ void __launch_bounds__(kBinThreads) k_bin_scatter(xs_plan pl, RasterA
     }
 }
 
+// ---- local sort of the pixel list by sigma0 (centred scan flavour only) ----------------------------------------
+// The centred flavour of k_scan_co shares (L - c)^2 between the 8 pixels of a warp, which keeps its error band tight only
+// if those pixels have similar sigma0.  Every run of 8 consecutive tiles (<= 256 list entries, possibly across a bin
+// boundary) is therefore sorted by (incidence bin, sigma0) in shared memory: bins stay contiguous and in order, and a
+// warp's 8 pixels span 1/32 of the run's sigma0 range.
+constexpr int kSortRun = 256;
+__global__ void __launch_bounds__(kSortRun) k_list_localsort(xs_plan pl, RasterArgs a, Workspace ws, int tile_px) {
+    __shared__ unsigned long long key[kSortRun];
+    __shared__ unsigned val[kSortRun];
+    __shared__ unsigned range[2];
+    const unsigned n_tiles = (unsigned)ws.counters[0];
+    const unsigned tiles_per_run = kSortRun / tile_px;
+    const unsigned t0 = blockIdx.x * tiles_per_run;
+    if (t0 >= n_tiles) return;
+    if (threadIdx.x < 2) {
+        const unsigned t = threadIdx.x == 0 ? t0 : min(t0 + tiles_per_run, n_tiles);
+        unsigned pos;
+        if (t >= n_tiles)
+            pos = ws.bin_start[pl.n_inc];
+        else {
+            int lo = 0, hi = pl.n_inc;
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (ws.tile_start[mid] <= t)
+                    lo = mid;
+                else
+                    hi = mid;
+            }
+            pos = ws.bin_start[lo] + (t - ws.tile_start[lo]) * tile_px;
+        }
+        range[threadIdx.x] = pos;
+    }
+    __syncthreads();
+    const unsigned first = range[0], count = range[1] - range[0];  // count <= kSortRun
+    unsigned long long k = ~0ull;
+    unsigned v = 0;
+    if (threadIdx.x < count) {
+        const unsigned e = first + threadIdx.x;
+        v = ws.list[e];
+        int lo = 0, hi = pl.n_inc;  // bin of list position e: last b with bin_start[b] <= e
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (ws.bin_start[mid] <= e)
+                lo = mid;
+            else
+                hi = mid;
+        }
+        const float sf = (float)load_real(a.s_co, v, a.dtype);  // linear or dB: monotone either way
+        unsigned b = __float_as_uint(sf);
+        b = (b & 0x80000000u) ? ~b : (b | 0x80000000u);  // order-preserving map of the float bits
+        k = ((unsigned long long)lo << 32) | b;
+    }
+    key[threadIdx.x] = k;
+    val[threadIdx.x] = v;
+    __syncthreads();
+    for (int size = 2; size <= kSortRun; size <<= 1)
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            const int i = threadIdx.x, j = i ^ stride;
+            if (j > i) {
+                const bool up = (i & size) == 0;
+                const unsigned long long ki = key[i], kj = key[j];
+                if ((ki > kj) == up) {
+                    key[i] = kj;
+                    key[j] = ki;
+                    const unsigned t = val[i];
+                    val[i] = val[j];
+                    val[j] = t;
+                }
+            }
+            __syncthreads();
+        }
+    if (threadIdx.x < count) ws.list[first + threadIdx.x] = val[threadIdx.x];
+}
+
 // ---- co-pol result of one pixel ----------------------------------------------------------------------------
 // windspeed.py:231-247.  The reference picks +phi or -phi by comparing |angle(anc/sol)| and |angle(anc/sol2)|
 // (ties keep +phi); for phi in [0,180] that is Im(anc) >= 0 ("direction sign").
@@ -480,10 +554,32 @@ k_scan_co(xs_plan pl, RasterArgs a, Workspace ws, double2 *out_co, int *idx_co) 
                     g[p][j] = pack2(g0, g1);
                 }
             }
+            // kMath == 5 (centred flavour): cs = centre of the warp's sigma0/dsig values; nqs[p] then holds k_p = -2 (s_p/dsig
+            // - cs) and scabs[p] an upper bound of |s_p/dsig - cs|
+            float cs = 0.f, scabs[P];
+            if (kMath == 5) {
+                double smin = CUDART_INF, smax = -CUDART_INF;
+#pragma unroll
+                for (int p = 0; p < P; ++p) {
+                    const PixelSlot &sl = sm.px[warp * P + p];
+                    if (sl.state == 1) {
+                        const double v = sl.s / pl.dsig_co;
+                        smin = fmin(smin, v);
+                        smax = fmax(smax, v);
+                    }
+                }
+                cs = smin <= smax ? (float)(0.5 * (smin + smax)) : 0.f;
+            }
 #pragma unroll
             for (int p = 0; p < P; ++p) {
                 const PixelSlot &sl = sm.px[warp * P + p];
-                nqs[p] = sl.state == 1 ? (float)(-(sl.s / pl.dsig_co)) : 0.f;
+                scabs[p] = 0.f;
+                if (kMath == 5) {
+                    const double sc = sl.state == 1 ? sl.s / pl.dsig_co - (double)cs : 0.0;
+                    nqs[p] = (float)(-2.0 * sc);
+                    scabs[p] = (float)fabs(sc) * 1.0000002f;
+                } else
+                    nqs[p] = sl.state == 1 ? (float)(-(sl.s / pl.dsig_co)) : 0.f;
             }
 
             float m[P];
@@ -543,13 +639,26 @@ k_scan_co(xs_plan pl, RasterArgs a, Workspace ws, double2 *out_co, int *idx_co) 
                     u64 L[KP];
 #pragma unroll
                     for (int j = 0; j < KP; ++j) L[j] = rows[r * (32 * KP) + lane + 32 * j];
+                    u64 M[KP];
+                    if (kMath == 5) {  // shared by the warp's pixels: Lc = L - cs, M = Lc^2 + w^2/4
+                        const u64 ncs2 = pack2(-cs, -cs);
+#pragma unroll
+                        for (int j = 0; j < KP; ++j) {
+                            L[j] = fadd2(L[j], ncs2);
+                            M[j] = ffma2(L[j], L[j], w2q);
+                        }
+                    }
 #pragma unroll
                     for (int p = 0; p < P; ++p) {
                         const u64 q2 = pack2(nqs[p], nqs[p]);
 #pragma unroll
                         for (int j = 0; j < KP; ++j) {
                             float j0, j1;
-                            if (kMath == 1) {  // experiment: scalar FADD/FFMA instead of the packed f32x2 forms
+                            if (kMath == 5) {  // J'' = k_p Lc + M + (-w/2) g: two FFMA2 per candidate pair
+                                const u64 aa = ffma2(q2, L[j], M[j]);
+                                const u64 J = ffma2(nwh, g[p][j], aa);
+                                unpack2(J, j0, j1);
+                            } else if (kMath == 1) {  // experiment: scalar FADD/FFMA instead of the packed f32x2 forms
                                 float l0, l1, g0, g1;
                                 unpack2(L[j], l0, l1);
                                 unpack2(g[p][j], g0, g1);
@@ -628,6 +737,12 @@ k_scan_co(xs_plan pl, RasterArgs a, Workspace ws, double2 *out_co, int *idx_co) 
                 flat = iw * pl.n_phi + ip;
                 if (k >= n_cand || iw >= pl.n_wspd || ip >= pl.n_phi) return false;
                 const float2 rt = rowtab_s[iw];
+                if (kMath == 5) {
+                    const float lc = __fadd_rn(slab32[(int64_t)iw * pl.nph_pad + ip], -cs);
+                    const float mm = __fmaf_rn(lc, lc, rt.y);
+                    const float aa = __fmaf_rn(nq, lc, mm);
+                    return __fmaf_rn(rt.x, g32(sl.qa, sl.qb, pl.cos_phi[ip], pl.sin_phi[ip]), aa) <= thr;
+                }
                 const float d = __fadd_rn(slab32[(int64_t)iw * pl.nph_pad + ip], nq);
                 const float t = __fmaf_rn(rt.x, g32(sl.qa, sl.qb, pl.cos_phi[ip], pl.sin_phi[ip]), rt.y);
                 return __fmaf_rn(d, d, t) <= thr;
@@ -659,9 +774,22 @@ k_scan_co(xs_plan pl, RasterArgs a, Workspace ws, double2 *out_co, int *idx_co) 
                 const float A = sl.amag;
                 const float W = (float)pl.w_absmax * 1.0000002f;
                 const float T = W * A + 0.25f * W * W;
-                const float D = sqrtf(fmaxf(m32, 0.f) + 0.25f * A * A + 1.0f);
-                const float Q = fabsf(nqs[p]);
-                const float E = 5.9604645e-8f * 1.5f * (3.f * T + 2.f * D * (lmax + Q + D) + (fabsf(m32) + 0.25f * A * A + T));
+                float D, E;
+                if (kMath == 5) {
+                    // J'' = J' - sc^2 (sc = s/dsig - cs): candidates that can still win have |L/dsig - s/dsig| <= D and
+                    // |L/dsig - cs| <= Lam = D + |sc|.  Error terms (u = 2^-24): image value and Lc roundings 2 Lam (lmax + Lam)
+                    // through Lc^2 and 2 |sc| (lmax + 2 Lam) through k_p Lc; M, a and J roundings Lam^2 + W^2/4,
+                    // Lam^2 + W^2/4 + 2 |sc| Lam and D^2 + sc^2 + T; row-table and g roundings W^2/4 + W A; the W terms
+                    // add up to W^2 + 2 W A <= 4 T (derivation in DESIGN.md 4.1).
+                    const float SC = scabs[p];
+                    D = sqrtf(fmaxf(m32 + SC * SC * 1.0000002f, 0.f) + 0.25f * A * A + 1.0f);
+                    const float Lam = D + SC;
+                    E = 5.9604645e-8f * 1.5f * (2.f * Lam * lmax + 2.f * SC * lmax + 4.f * Lam * Lam + 6.f * SC * Lam + SC * SC + D * D + 4.f * T);
+                } else {
+                    D = sqrtf(fmaxf(m32, 0.f) + 0.25f * A * A + 1.0f);
+                    const float Q = fabsf(nqs[p]);
+                    E = 5.9604645e-8f * 1.5f * (3.f * T + 2.f * D * (lmax + Q + D) + (fabsf(m32) + 0.25f * A * A + T));
+                }
                 thr[p] = m32 + 2.f * E;
                 const bool sane = (E < 0.25f) && (m32 < CUDART_INF_F);
                 if (!sane) {  // warp-uniform: magnitudes outside the range the error bound was derived for
@@ -1081,7 +1209,8 @@ static int launch_scan(const xs_plan *pl, const RasterArgs &ra, const Workspace 
 // Scan configuration: pixels per warp P, warps per CTA NW, CTAs per SM MB (register budget = 64K/(NW*32*MB)), math
 // flavour (0 packed f32x2, 1 scalar, 2 scalar t + packed d/J, 3 packed without refinement = measurement only) and
 // where the per-lane argmin bookkeeping lives.  XS_SCAN_VARIANT (environment) selects one of the experimental
-// configurations for KP == 3 that DESIGN.md section 4.1 reports on; 0 (default) is the shipped one.
+// configurations for KP == 3 that DESIGN.md section 4.1 reports on; 0 (default) is the shipped one (centred flavour,
+// math 5), 99 the direct three-operation form that was the default before.
 struct ScanConfig {
     int p, nw;
 };
@@ -1093,6 +1222,14 @@ static int scan_variant() {
     }
     return v;
 }
+// does dispatch_scan pick a centred (kMath == 5) instantiation?  (then the pixel list is sorted locally by sigma0)
+static bool scan_is_centred(int kp) {
+    if (kp != 3) return false;
+    switch (scan_variant()) {
+        case 1: case 3: case 8: case 11: case 20: case 30: case 40: case 41: case 51: case 52: case 60: case 99: return false;
+        default: return true;
+    }
+}
 static ScanConfig scan_config(int kp) {
     if (kp >= 4) return {4, 8};
     if (kp == 3) {
@@ -1101,6 +1238,9 @@ static ScanConfig scan_config(int kp) {
             case 3: return {8, 12};
             case 8: case 11: case 20: case 30: case 40: case 60: return {8, 8};
             case 52: return {8, 2};
+            case 72: return {8, 6};
+            case 75: return {16, 2};
+            case 77: return {12, 4};
             default: return {8, 4};
         }
     }
@@ -1124,7 +1264,14 @@ static int dispatch_scan(const xs_plan *pl, const RasterArgs &ra, const Workspac
                 case 51: return launch_scan<3, 8, 4, 4, 0, false, 4>(pl, ra, ws, out_co, idx_co, stream);
                 case 52: return launch_scan<3, 8, 2, 8, 0, false, 3>(pl, ra, ws, out_co, idx_co, stream);  // 8 CTAs x 2 warps
                 case 60: return launch_scan<3, 8, 8, 2>(pl, ra, ws, out_co, idx_co, stream);          // 2 CTAs x 8 warps, 4 stages
-                default: return launch_scan<3, 8, 4, 4, 0, false, 3>(pl, ra, ws, out_co, idx_co, stream);  // shipped
+                case 70: return launch_scan<3, 8, 4, 4, 5, false, 3>(pl, ra, ws, out_co, idx_co, stream);  // centred flavour, shipped shape
+                case 71: return launch_scan<3, 8, 4, 3, 5, false, 3>(pl, ra, ws, out_co, idx_co, stream);  // centred, 3 CTAs (168 regs)
+                case 72: return launch_scan<3, 8, 6, 2, 5, false, 3>(pl, ra, ws, out_co, idx_co, stream);  // centred, 2 CTAs x 6 warps
+                case 75: return launch_scan<3, 16, 2, 4, 5, false, 3>(pl, ra, ws, out_co, idx_co, stream); // centred, P = 16, 4 CTAs x 2 warps
+                case 76: return launch_scan<3, 8, 4, 3, 5, false, 4>(pl, ra, ws, out_co, idx_co, stream);  // centred, 3 CTAs, 4 stages
+                case 77: return launch_scan<3, 12, 4, 2, 5, false, 3>(pl, ra, ws, out_co, idx_co, stream); // centred, P = 12, 2 CTAs x 4 warps
+                case 99: return launch_scan<3, 8, 4, 4, 0, false, 3>(pl, ra, ws, out_co, idx_co, stream);  // direct form (the former default)
+                default: return launch_scan<3, 8, 4, 3, 5, false, 3>(pl, ra, ws, out_co, idx_co, stream);  // shipped: centred, 3 CTAs x 4 warps
             }
         case 4: return launch_scan<4, 4, 8, 1>(pl, ra, ws, out_co, idx_co, stream);
         default: return launch_scan<6, 4, 8, 1>(pl, ra, ws, out_co, idx_co, stream);
@@ -1346,6 +1493,10 @@ extern "C" int xs_invert(const xs_plan *pl, const xs_invert_args *ar, void *stre
             XS_LAUNCH(k_bin_count, bin_grid, kBinThreads, sizeof(unsigned) * pl->n_inc, st, *pl, ra, n, ws);
             XS_LAUNCH(k_bin_offsets, 1, 1024, 0, st, pl->n_inc, tile_px, ws);
             XS_LAUNCH(k_bin_scatter, bin_grid, kBinThreads, 2 * sizeof(unsigned) * pl->n_inc, st, *pl, ra, n, ws);
+            if (scan_is_centred(pl->kp)) {  // centred flavour: the pixels of a warp need similar sigma0
+                const int64_t max_tiles = ceil_div(n, tile_px) + pl->n_inc;
+                XS_LAUNCH(k_list_localsort, (unsigned)ceil_div(max_tiles, kSortRun / tile_px), kSortRun, 0, st, *pl, ra, ws, tile_px);
+            }
             xs_plan *mpl = const_cast<xs_plan *>(pl);  // timing events are bookkeeping, not plan state
             XS_CUDA(cudaEventRecord(mpl->ev_scan0, st));
             const int rc = dispatch_scan(pl, ra, ws, out_co, ar->idx_co, stream);
