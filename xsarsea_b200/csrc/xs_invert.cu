@@ -434,7 +434,7 @@ struct ScanSmem {
     alignas(16) uint64_t full[NS];
     alignas(16) uint64_t empty[NS];
     PixelSlot px[NW * P];
-    unsigned next_tile;
+    unsigned next_tile[2];
     BookSmem<P, NW * 32, BK> book;
 };
 
@@ -458,6 +458,8 @@ k_scan_co(xs_plan pl, RasterArgs a, Workspace ws, double2 *out_co, int *idx_co) 
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr int TP = NW * P;  // pixels per tile
+    constexpr bool kCentred = kMath == 5 || kMath == 6;  // two-FFMA2 centred cost (see the settle section)
+    constexpr bool kWarpOwn = kMath == 6;  // every warp loads and writes its own P pixels: one CTA barrier per tile
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NS; ++s) {
@@ -478,12 +480,25 @@ k_scan_co(xs_plan pl, RasterArgs a, Workspace ws, double2 *out_co, int *idx_co) 
     long long t_last = clock64();
     // Tiles are handed out dynamically (one atomic per tile): CTAs do not all progress at the same speed, and a static
     // round-robin left ~13 % of the SM time idle at the end of the kernel.
-    for (;;) {
-        __syncthreads();  // previous tile's slots and sm.next_tile are no longer read
-        if (threadIdx.x == 0) sm.next_tile = (unsigned)atomicAdd(&ws.counters[8], 1ull);
+    if (kWarpOwn) {
+        if (threadIdx.x == 0) sm.next_tile[0] = (unsigned)atomicAdd(&ws.counters[8], 1ull);
         __syncthreads();
-        const unsigned tile = sm.next_tile;
-        if (tile >= n_tiles) break;
+    }
+    for (unsigned tile_it = 0;; ++tile_it) {
+        unsigned tile;
+        if (kWarpOwn) {
+            // the tile index was fetched during the previous tile (double-buffered), the slots are per warp: the single
+            // barrier at the end of the loop body is the only CTA-wide synchronisation of a tile
+            tile = sm.next_tile[tile_it & 1];
+            if (tile >= n_tiles) break;
+            if (threadIdx.x == 0) sm.next_tile[(tile_it + 1) & 1] = (unsigned)atomicAdd(&ws.counters[8], 1ull);
+        } else {
+            __syncthreads();  // previous tile's slots and sm.next_tile are no longer read
+            if (threadIdx.x == 0) sm.next_tile[0] = (unsigned)atomicAdd(&ws.counters[8], 1ull);
+            __syncthreads();
+            tile = sm.next_tile[0];
+            if (tile >= n_tiles) break;
+        }
         // tile -> (bin, pixel range): last bin with tile_start[bin] <= tile
         int lo = 0, hi = pl.n_inc;
         while (hi - lo > 1) {
@@ -498,15 +513,16 @@ k_scan_co(xs_plan pl, RasterArgs a, Workspace ws, double2 *out_co, int *idx_co) 
         const unsigned last = min(first + TP, ws.bin_start[bin + 1]);
         const int nan_idx = pl.first_nan[bin];
 
-        // ---- load the tile's pixels (one thread per pixel) ----
-        if (threadIdx.x < TP) {
+        // ---- load the tile's pixels (one thread per pixel; with kWarpOwn lanes 0..P-1 of every warp load its own) ----
+        const int my_slot = kWarpOwn ? warp * P + lane : (int)threadIdx.x;
+        if (kWarpOwn ? lane < P : threadIdx.x < TP) {
             PixelSlot sl;
             sl.state = 0;
             sl.px = 0;
             sl.idx = -1;
             sl.qa = sl.qb = sl.s = sl.anc_im = 0.0;
             sl.amag = 0.f;
-            const unsigned e = first + threadIdx.x;
+            const unsigned e = first + my_slot;
             if (e < last) {
                 const unsigned px = ws.list[e];
                 const Pixel p = load_pixel(pl, a, px);
@@ -525,9 +541,12 @@ k_scan_co(xs_plan pl, RasterArgs a, Workspace ws, double2 *out_co, int *idx_co) 
                 } else
                     sl.state = 1;
             }
-            sm.px[threadIdx.x] = sl;
+            sm.px[my_slot] = sl;
         }
-        __syncthreads();
+        if (kWarpOwn)
+            __syncwarp();
+        else
+            __syncthreads();
 
         if (nan_idx < 0) {
             // ---- per-lane per-pixel query constants ----
@@ -554,10 +573,10 @@ k_scan_co(xs_plan pl, RasterArgs a, Workspace ws, double2 *out_co, int *idx_co) 
                     g[p][j] = pack2(g0, g1);
                 }
             }
-            // kMath == 5 (centred flavour): cs = centre of the warp's sigma0/dsig values; nqs[p] then holds k_p = -2 (s_p/dsig
+            // kCentred (centred flavour): cs = centre of the warp's sigma0/dsig values; nqs[p] then holds k_p = -2 (s_p/dsig
             // - cs) and scabs[p] an upper bound of |s_p/dsig - cs|
             float cs = 0.f, scabs[P];
-            if (kMath == 5) {
+            if (kCentred) {
                 double smin = CUDART_INF, smax = -CUDART_INF;
 #pragma unroll
                 for (int p = 0; p < P; ++p) {
@@ -574,7 +593,7 @@ k_scan_co(xs_plan pl, RasterArgs a, Workspace ws, double2 *out_co, int *idx_co) 
             for (int p = 0; p < P; ++p) {
                 const PixelSlot &sl = sm.px[warp * P + p];
                 scabs[p] = 0.f;
-                if (kMath == 5) {
+                if (kCentred) {
                     const double sc = sl.state == 1 ? sl.s / pl.dsig_co - (double)cs : 0.0;
                     nqs[p] = (float)(-2.0 * sc);
                     scabs[p] = (float)fabs(sc) * 1.0000002f;
@@ -640,7 +659,7 @@ k_scan_co(xs_plan pl, RasterArgs a, Workspace ws, double2 *out_co, int *idx_co) 
 #pragma unroll
                     for (int j = 0; j < KP; ++j) L[j] = rows[r * (32 * KP) + lane + 32 * j];
                     u64 M[KP];
-                    if (kMath == 5) {  // shared by the warp's pixels: Lc = L - cs, M = Lc^2 + w^2/4
+                    if (kCentred) {  // shared by the warp's pixels: Lc = L - cs, M = Lc^2 + w^2/4
                         const u64 ncs2 = pack2(-cs, -cs);
 #pragma unroll
                         for (int j = 0; j < KP; ++j) {
@@ -654,7 +673,7 @@ k_scan_co(xs_plan pl, RasterArgs a, Workspace ws, double2 *out_co, int *idx_co) 
 #pragma unroll
                         for (int j = 0; j < KP; ++j) {
                             float j0, j1;
-                            if (kMath == 5) {  // J'' = k_p Lc + M + (-w/2) g: two FFMA2 per candidate pair
+                            if (kCentred) {  // J'' = k_p Lc + M + (-w/2) g: two FFMA2 per candidate pair
                                 const u64 aa = ffma2(q2, L[j], M[j]);
                                 const u64 J = ffma2(nwh, g[p][j], aa);
                                 unpack2(J, j0, j1);
@@ -737,7 +756,7 @@ k_scan_co(xs_plan pl, RasterArgs a, Workspace ws, double2 *out_co, int *idx_co) 
                 flat = iw * pl.n_phi + ip;
                 if (k >= n_cand || iw >= pl.n_wspd || ip >= pl.n_phi) return false;
                 const float2 rt = rowtab_s[iw];
-                if (kMath == 5) {
+                if (kCentred) {
                     const float lc = __fadd_rn(slab32[(int64_t)iw * pl.nph_pad + ip], -cs);
                     const float mm = __fmaf_rn(lc, lc, rt.y);
                     const float aa = __fmaf_rn(nq, lc, mm);
@@ -775,7 +794,7 @@ k_scan_co(xs_plan pl, RasterArgs a, Workspace ws, double2 *out_co, int *idx_co) 
                 const float W = (float)pl.w_absmax * 1.0000002f;
                 const float T = W * A + 0.25f * W * W;
                 float D, E;
-                if (kMath == 5) {
+                if (kCentred) {
                     // J'' = J' - sc^2 (sc = s/dsig - cs): candidates that can still win have |L/dsig - s/dsig| <= D and
                     // |L/dsig - cs| <= Lam = D + |sc|.  Error terms (u = 2^-24): image value and Lc roundings 2 Lam (lmax + Lam)
                     // through Lc^2 and 2 |sc| (lmax + 2 Lam) through k_p Lc; M, a and J roundings Lam^2 + W^2/4,
@@ -891,16 +910,20 @@ k_scan_co(xs_plan pl, RasterArgs a, Workspace ws, double2 *out_co, int *idx_co) 
             }
         }
         XS_TICK(2);
-        __syncthreads();
+        if (kWarpOwn)
+            __syncwarp();
+        else
+            __syncthreads();
         // ---- write results / queue leftovers ----
-        if (threadIdx.x < TP) {
-            const PixelSlot &sl = sm.px[threadIdx.x];
+        if (kWarpOwn ? lane < P : threadIdx.x < TP) {
+            const PixelSlot &sl = sm.px[my_slot];
             if (sl.state == 2)
                 write_co(pl, sl.idx, make_double2(sl.qa, sl.anc_im), sl.px, out_co, idx_co);
             else if (sl.state == 3)
                 ws.fallback[atomicAdd(&ws.counters[1], 1ull)] = sl.px;
         }
         XS_TICK(3);
+        if (kWarpOwn) __syncthreads();  // next tile index visible; every warp is done with this tile's ring traffic
     }
     if (lane == 0) {
         if (n_scanned) atomicAdd(&ws.counters[2], n_scanned);
@@ -1222,7 +1245,7 @@ static int scan_variant() {
     }
     return v;
 }
-// does dispatch_scan pick a centred (kMath == 5) instantiation?  (then the pixel list is sorted locally by sigma0)
+// does dispatch_scan pick a centred (kCentred) instantiation?  (then the pixel list is sorted locally by sigma0)
 static bool scan_is_centred(int kp) {
     if (kp != 3) return false;
     switch (scan_variant()) {
@@ -1241,6 +1264,8 @@ static ScanConfig scan_config(int kp) {
             case 72: return {8, 6};
             case 75: return {16, 2};
             case 77: return {12, 4};
+            case 78: return {10, 4};
+            case 79: return {9, 4};
             default: return {8, 4};
         }
     }
@@ -1270,6 +1295,10 @@ static int dispatch_scan(const xs_plan *pl, const RasterArgs &ra, const Workspac
                 case 75: return launch_scan<3, 16, 2, 4, 5, false, 3>(pl, ra, ws, out_co, idx_co, stream); // centred, P = 16, 4 CTAs x 2 warps
                 case 76: return launch_scan<3, 8, 4, 3, 5, false, 4>(pl, ra, ws, out_co, idx_co, stream);  // centred, 3 CTAs, 4 stages
                 case 77: return launch_scan<3, 12, 4, 2, 5, false, 3>(pl, ra, ws, out_co, idx_co, stream); // centred, P = 12, 2 CTAs x 4 warps
+                case 80: return launch_scan<3, 8, 4, 3, 6, false, 3>(pl, ra, ws, out_co, idx_co, stream);  // centred, per-warp slots, 1 barrier/tile
+                case 81: return launch_scan<3, 8, 4, 4, 6, false, 3>(pl, ra, ws, out_co, idx_co, stream);  // same, 4 CTAs (128 regs)
+                case 78: return launch_scan<3, 10, 4, 3, 5, false, 3>(pl, ra, ws, out_co, idx_co, stream); // centred, P = 10, 3 CTAs x 4 warps
+                case 79: return launch_scan<3, 9, 4, 3, 5, false, 3>(pl, ra, ws, out_co, idx_co, stream);  // centred, P = 9
                 case 99: return launch_scan<3, 8, 4, 4, 0, false, 3>(pl, ra, ws, out_co, idx_co, stream);  // direct form (the former default)
                 default: return launch_scan<3, 8, 4, 3, 5, false, 3>(pl, ra, ws, out_co, idx_co, stream);  // shipped: centred, 3 CTAs x 4 warps
             }
