@@ -1247,6 +1247,7 @@ static int scan_variant() {
 }
 // does dispatch_scan pick a centred (kCentred) instantiation?  (then the pixel list is sorted locally by sigma0)
 static bool scan_is_centred(int kp) {
+    if (kp == 1 || kp == 2) return scan_variant() != 99;
     if (kp != 3) return false;
     switch (scan_variant()) {
         case 1: case 3: case 8: case 11: case 20: case 30: case 40: case 41: case 51: case 52: case 60: case 99: return false;
@@ -1274,8 +1275,12 @@ static ScanConfig scan_config(int kp) {
 static int dispatch_scan(const xs_plan *pl, const RasterArgs &ra, const Workspace &ws, double2 *out_co, int *idx_co,
                          void *stream) {
     switch (pl->kp) {
-        case 1: return launch_scan<1, 8, 4, 4, 0, false, 3>(pl, ra, ws, out_co, idx_co, stream);
-        case 2: return launch_scan<2, 8, 4, 4, 0, false, 3>(pl, ra, ws, out_co, idx_co, stream);
+        case 1:
+            if (scan_variant() == 99) return launch_scan<1, 8, 4, 4, 0, false, 3>(pl, ra, ws, out_co, idx_co, stream);
+            return launch_scan<1, 8, 4, 3, 5, false, 3>(pl, ra, ws, out_co, idx_co, stream);
+        case 2:
+            if (scan_variant() == 99) return launch_scan<2, 8, 4, 4, 0, false, 3>(pl, ra, ws, out_co, idx_co, stream);
+            return launch_scan<2, 8, 4, 3, 5, false, 3>(pl, ra, ws, out_co, idx_co, stream);
         case 3:
             switch (scan_variant()) {
                 case 1: return launch_scan<3, 4, 8, 2>(pl, ra, ws, out_co, idx_co, stream);           // P = 4
