@@ -458,8 +458,9 @@ k_scan_co(xs_plan pl, RasterArgs a, Workspace ws, double2 *out_co, int *idx_co) 
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr int TP = NW * P;  // pixels per tile
-    constexpr bool kCentred = kMath == 5 || kMath == 6;  // two-FFMA2 centred cost (see the settle section)
-    constexpr bool kWarpOwn = kMath == 6;  // every warp loads and writes its own P pixels: one CTA barrier per tile
+    constexpr bool kCentred = kMath == 5 || kMath == 6 || kMath == 7;  // two-FFMA2 centred cost (see the settle section)
+    constexpr bool kWarpOwn = kMath == 6;
+    constexpr bool kJOuter = kMath == 7;  // experiment: phi-pair loop outside the pixel loop (shorter live ranges of lambda, M)  // every warp loads and writes its own P pixels: one CTA barrier per tile
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NS; ++s) {
@@ -658,6 +659,23 @@ k_scan_co(xs_plan pl, RasterArgs a, Workspace ws, double2 *out_co, int *idx_co) 
                     u64 L[KP];
 #pragma unroll
                     for (int j = 0; j < KP; ++j) L[j] = rows[r * (32 * KP) + lane + 32 * j];
+                    if (kJOuter) {
+                        const u64 ncs2 = pack2(-cs, -cs);
+#pragma unroll
+                        for (int j = 0; j < KP; ++j) {
+                            const u64 lc = fadd2(L[j], ncs2);
+                            const u64 mj = ffma2(lc, lc, w2q);
+#pragma unroll
+                            for (int p = 0; p < P; ++p) {
+                                const u64 aa = ffma2(pack2(nqs[p], nqs[p]), lc, mj);
+                                const u64 J = ffma2(nwh, g[p][j], aa);
+                                float j0, j1;
+                                unpack2(J, j0, j1);
+                                m[p] = fmin3(m[p], j0, j1);
+                            }
+                        }
+                        continue;
+                    }
                     u64 M[KP];
                     if (kCentred) {  // shared by the warp's pixels: Lc = L - cs, M = Lc^2 + w^2/4
                         const u64 ncs2 = pack2(-cs, -cs);
@@ -1233,7 +1251,9 @@ static int launch_scan(const xs_plan *pl, const RasterArgs &ra, const Workspace 
 // flavour (0 packed f32x2, 1 scalar, 2 scalar t + packed d/J, 3 packed without refinement = measurement only) and
 // where the per-lane argmin bookkeeping lives.  XS_SCAN_VARIANT (environment) selects one of the experimental
 // configurations for KP == 3 that DESIGN.md section 4.1 reports on; 0 (default) is the shipped one (centred flavour,
-// math 5), 99 the direct three-operation form that was the default before.
+// math 5), 99 the direct three-operation form that was the default before.  The other shapes DESIGN.md lists as
+// measured (P = 4..16, 2-12 warps per CTA, scalar / hybrid math, shared-memory bookkeeping, ring depths) were removed
+// from the dispatch after measurement to keep the build short; their code paths (kMath 1, 2, 7, kBookSmem) remain.
 struct ScanConfig {
     int p, nw;
 };
@@ -1249,27 +1269,12 @@ static int scan_variant() {
 static bool scan_is_centred(int kp) {
     if (kp == 1 || kp == 2) return scan_variant() != 99;
     if (kp != 3) return false;
-    switch (scan_variant()) {
-        case 1: case 3: case 8: case 11: case 20: case 30: case 40: case 41: case 51: case 52: case 60: case 99: return false;
-        default: return true;
-    }
+    const int v = scan_variant();
+    return !(v == 30 || v == 41 || v == 99);
 }
 static ScanConfig scan_config(int kp) {
     if (kp >= 4) return {4, 8};
-    if (kp == 3) {
-        switch (scan_variant()) {
-            case 1: return {4, 8};
-            case 3: return {8, 12};
-            case 8: case 11: case 20: case 30: case 40: case 60: return {8, 8};
-            case 52: return {8, 2};
-            case 72: return {8, 6};
-            case 75: return {16, 2};
-            case 77: return {12, 4};
-            case 78: return {10, 4};
-            case 79: return {9, 4};
-            default: return {8, 4};
-        }
-    }
+    if (kp == 3 && scan_variant() == 30) return {8, 8};
     return {8, 4};
 }
 static int dispatch_scan(const xs_plan *pl, const RasterArgs &ra, const Workspace &ws, double2 *out_co, int *idx_co,
@@ -1283,27 +1288,10 @@ static int dispatch_scan(const xs_plan *pl, const RasterArgs &ra, const Workspac
             return launch_scan<2, 8, 4, 3, 5, false, 3>(pl, ra, ws, out_co, idx_co, stream);
         case 3:
             switch (scan_variant()) {
-                case 1: return launch_scan<3, 4, 8, 2>(pl, ra, ws, out_co, idx_co, stream);           // P = 4
-                case 3: return launch_scan<3, 8, 12, 1>(pl, ra, ws, out_co, idx_co, stream);          // 12 warps, 168 regs
-                case 8: return launch_scan<3, 8, 8, 2, 1>(pl, ra, ws, out_co, idx_co, stream);        // scalar math
-                case 11: return launch_scan<3, 8, 8, 2, 2>(pl, ra, ws, out_co, idx_co, stream);       // hybrid math
-                case 20: return launch_scan<3, 8, 8, 2, 0, true>(pl, ra, ws, out_co, idx_co, stream); // smem bookkeeping
-                case 30: return launch_scan<3, 8, 8, 2, 3>(pl, ra, ws, out_co, idx_co, stream);       // NOT exact: no refinement
-                case 40: return launch_scan<3, 8, 8, 2, 4>(pl, ra, ws, out_co, idx_co, stream);       // phase timers
-                case 41: return launch_scan<3, 8, 4, 4, 4, false, 3>(pl, ra, ws, out_co, idx_co, stream);  // phase timers, shipped shape
-                case 51: return launch_scan<3, 8, 4, 4, 0, false, 4>(pl, ra, ws, out_co, idx_co, stream);
-                case 52: return launch_scan<3, 8, 2, 8, 0, false, 3>(pl, ra, ws, out_co, idx_co, stream);  // 8 CTAs x 2 warps
-                case 60: return launch_scan<3, 8, 8, 2>(pl, ra, ws, out_co, idx_co, stream);          // 2 CTAs x 8 warps, 4 stages
-                case 70: return launch_scan<3, 8, 4, 4, 5, false, 3>(pl, ra, ws, out_co, idx_co, stream);  // centred flavour, shipped shape
-                case 71: return launch_scan<3, 8, 4, 3, 5, false, 3>(pl, ra, ws, out_co, idx_co, stream);  // centred, 3 CTAs (168 regs)
-                case 72: return launch_scan<3, 8, 6, 2, 5, false, 3>(pl, ra, ws, out_co, idx_co, stream);  // centred, 2 CTAs x 6 warps
-                case 75: return launch_scan<3, 16, 2, 4, 5, false, 3>(pl, ra, ws, out_co, idx_co, stream); // centred, P = 16, 4 CTAs x 2 warps
-                case 76: return launch_scan<3, 8, 4, 3, 5, false, 4>(pl, ra, ws, out_co, idx_co, stream);  // centred, 3 CTAs, 4 stages
-                case 77: return launch_scan<3, 12, 4, 2, 5, false, 3>(pl, ra, ws, out_co, idx_co, stream); // centred, P = 12, 2 CTAs x 4 warps
+                case 30: return launch_scan<3, 8, 8, 2, 3>(pl, ra, ws, out_co, idx_co, stream);            // NOT exact: no refinement (measurement)
+                case 41: return launch_scan<3, 8, 4, 4, 4, false, 3>(pl, ra, ws, out_co, idx_co, stream);  // direct form with phase timers
+                case 70: return launch_scan<3, 8, 4, 4, 5, false, 3>(pl, ra, ws, out_co, idx_co, stream);  // centred, 4 CTAs (128 regs, spills)
                 case 80: return launch_scan<3, 8, 4, 3, 6, false, 3>(pl, ra, ws, out_co, idx_co, stream);  // centred, per-warp slots, 1 barrier/tile
-                case 81: return launch_scan<3, 8, 4, 4, 6, false, 3>(pl, ra, ws, out_co, idx_co, stream);  // same, 4 CTAs (128 regs)
-                case 78: return launch_scan<3, 10, 4, 3, 5, false, 3>(pl, ra, ws, out_co, idx_co, stream); // centred, P = 10, 3 CTAs x 4 warps
-                case 79: return launch_scan<3, 9, 4, 3, 5, false, 3>(pl, ra, ws, out_co, idx_co, stream);  // centred, P = 9
                 case 99: return launch_scan<3, 8, 4, 4, 0, false, 3>(pl, ra, ws, out_co, idx_co, stream);  // direct form (the former default)
                 default: return launch_scan<3, 8, 4, 3, 5, false, 3>(pl, ra, ws, out_co, idx_co, stream);  // shipped: centred, 3 CTAs x 4 warps
             }
