@@ -231,12 +231,11 @@ extern "C" int xs_local_gradients(const void *image, int64_t n_lines, int64_t n_
         return XS_E_UNSUPPORTED;
     }
     const size_t smem = sizeof(GradSmem);
-    static bool configured = false;
-    if (!configured) {
+    // per launch, not once per process: the attribute belongs to the current device's context
+    if (dtype == XS_F64)
         XS_CUDA(cudaFuncSetAttribute(k_grad_reduce<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else
         XS_CUDA(cudaFuncSetAttribute(k_grad_reduce<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
     if (dtype == XS_F64)
         XS_LAUNCH(k_grad_reduce<double>, grid, 256, smem, stream, (const double *)image, h, w, h2, w2, c_re, c_im, c_abs);
     else

@@ -1229,11 +1229,8 @@ template <int KP, int P, int NW, int MB, int SC = 0, bool BK = false, int NS = k
 static int launch_scan(const xs_plan *pl, const RasterArgs &ra, const Workspace &ws, double2 *out_co, int *idx_co,
                        void *stream) {
     const size_t smem = sizeof(ScanSmem<KP, P, NW, NS, BK>) + sizeof(float2) * (size_t)pl->n_wspd_pad;
-    static bool configured = false;  // per instantiation
-    if (!configured) {
-        XS_CUDA(cudaFuncSetAttribute(k_scan_co<KP, P, NW, MB, SC, BK, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        configured = true;
-    }
+    // per launch, not once per process: the attribute belongs to the current device's context
+    XS_CUDA(cudaFuncSetAttribute(k_scan_co<KP, P, NW, MB, SC, BK, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     if (smem > 200 * 1024) {
         set_error("xs_invert: wspd grid too long for the shared-memory row table");
         return XS_E_UNSUPPORTED;
