@@ -526,12 +526,14 @@ k_scan_co(xs_plan pl, RasterArgs a, Workspace ws, double2 *out_co, int *idx_co) 
             const unsigned e = first + my_slot;
             if (e < last) {
                 const unsigned px = ws.list[e];
-                const Pixel p = load_pixel(pl, a, px);
+                // only what the co-pol scan needs (load_pixel would also convert the cross-pol sigma0 to dB)
+                const double2 anc = load_cplx(a.anc, px, a.dtype);
+                const double s_raw = load_real(a.s_co, px, a.dtype);
                 sl.px = px;
-                sl.qa = p.anc.x;
-                sl.anc_im = p.anc.y;
-                sl.qb = pl.phi_180 ? fabs(p.anc.y) : p.anc.y;
-                sl.s = p.s_co;
+                sl.qa = anc.x;
+                sl.anc_im = anc.y;
+                sl.qb = pl.phi_180 ? fabs(anc.y) : anc.y;
+                sl.s = (a.flags & XS_FLAG_SIGMA0_DB) ? s_raw : to_db(s_raw);
                 sl.amag = (float)hypot(sl.qa, sl.qb) * 1.0000002f;
                 const bool finite_q = isfinite(sl.qa) && isfinite(sl.qb) && isfinite(sl.s);
                 if (!finite_q)
