@@ -35,6 +35,12 @@ FLOP_PER_PX = 8 * 499 * 181 + 6 * 771  # 8 flop per co-pol candida
 METRIC = "inverted pixels/sec (dual-pol cmod5n+ms1ahw)"
 
 
+def workload_text(args):
+    """The workload both arms of the bench report (config.workload)."""
+    return (f"dual-pol invert: gmf_cmod5n (default LUT 501x499x181) + nc_lut_cmodms1ahw (synthetic stand-in 331x771), "
+            f"S1 IW {args.lines}x{args.samples} px per GPU, inc {INC_NEAR}-{INC_FAR} deg, 1% NaN, dsig_cr=0.1, ancillary wind")
+
+
 def peaks():
     p = {}
     try:
@@ -225,8 +231,7 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": v, "unit": "px/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(secs)), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"dual-pol gmf_cmod5n + nc_lut_cmodms1ahw (synthetic stand-in), S1 IW {args.lines}x{args.samples}",
-                   "sample": sample_txt},
+        "config": {"workload": workload_text(args), "sample": sample_txt},
         "cpu_baseline": {"value": v, "unit": "px/s", "cores": threads, "kind": "port", "sample": sample_txt},
         "e2e": {"value": v, "unit": "px/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -390,9 +395,7 @@ def main():
             "metric": METRIC, "value": value, "unit": "px/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 scan + f64 refinement (f64/c128 rasters)", "data": f"synthetic (SURVEY D2 recipe, torch CUDA generator, seed {args.seed}+rank)",
-            "config": {"workload": f"dual-pol invert: gmf_cmod5n (default LUT 501x499x181) + nc_lut_cmodms1ahw (synthetic stand-in "
-                                   f"331x771), S1 IW {args.lines}x{args.samples} px per GPU, inc {INC_NEAR}-{INC_FAR} deg, "
-                                   f"1% NaN, dsig_cr=0.1, ancillary wind",
+            "config": {"workload": workload_text(args),
                        "l2": "inputs (40 B/px x %.1f Mpx = %.1f GB) exceed L2 (126 MB)" % (n_px / 1e6, 40 * n_px / 1e9),
                        "sharding": "one scene per GPU, no data-path collective", "lut_build_s": lut_s},
             "roofline": {"bound": "fp32 cuda-core (FMA pipe)", "kernel": "k_scan_co", "achieved": achieved,

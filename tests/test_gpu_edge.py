@@ -276,3 +276,33 @@ def test_plan_lifecycle_and_api_latency(dev):
     assert out.shape == (H, W) and np.isfinite(out).mean() > 0.99
     assert dt < 0.25, f"cached-plan call on 1 Mpx took {dt:.3f} s"   # kernel ~12 ms + 72 MB of PCIe traffic
     print(f"invert_from_model 1000x1000 from host: {1e3 * dt:.1f} ms")
+
+
+def test_pixel_order_invariance_and_equal_sigma0_runs(dev):
+    """The centred scan sorts runs of the pixel list by sigma0 and centres every warp on its own pixels: the result of a
+    pixel must not depend on its neighbours.  Property: a random permutation of the pixels permutes the outputs, bit for
+    bit; long runs of pixels with exactly equal sigma0 (a flat field: sort ties, zero spread around the centre) and runs
+    with a huge spread inside one warp (sigma0 from -150 dB to +20 dB in the same incidence bin) still agree with the
+    exhaustive FP64 kernel."""
+    torch, D, nat = dev
+    gi, gw, gp = np.linspace(16, 66, 501), np.linspace(0.2, 50, 499), np.linspace(0, 180, 181)
+    lut = D.lut_to_db(D.lut_build(nat.GMF_IDS["gmf_cmod5n"], gi, gw, gp))
+    plan = D.InversionPlan(co=(lut, gi, gw, gp))
+    g = torch.Generator(device="cuda").manual_seed(5)
+    n = 300_000
+    f64 = dict(device="cuda", dtype=torch.float64)
+    inc = 30 + 0.35 * torch.rand(n, generator=g, **f64)          # four incidence bins only: long lists per bin
+    s = -25 + 20 * torch.rand(n, generator=g, **f64)
+    s[: n // 3] = -14.25                                         # flat field: exactly equal sigma0
+    wild = torch.arange(n // 3, n // 3 + 4096, device="cuda")
+    s[wild] = torch.where(torch.rand(4096, generator=g, device="cuda") < 0.5, -150.0, 20.0).to(torch.float64)
+    anc = torch.polar(1 + 24 * torch.rand(n, generator=g, **f64), 2 * np.pi * torch.rand(n, generator=g, **f64) - np.pi)
+    a, _, ia, _ = plan.invert(inc, s, None, 0.1, anc, sigma0_db=True, want_idx=True)
+    b, _, ib, _ = plan.invert(inc, s, None, 0.1, anc, sigma0_db=True, want_idx=True, mode=nat.MODE_FP64)
+    assert torch.equal(ia, ib)
+    perm = torch.randperm(n, generator=g, device="cuda")
+    c, _, ic, _ = plan.invert(inc[perm].contiguous(), s[perm].contiguous(), None, 0.1, anc[perm].contiguous(), sigma0_db=True,
+                              want_idx=True)
+    assert torch.equal(ic, ia[perm])
+    assert torch.equal(torch.view_as_real(c), torch.view_as_real(a[perm]))
+    plan.close()
