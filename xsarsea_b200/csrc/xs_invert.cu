@@ -441,7 +441,7 @@ struct ScanSmem {
 // kMath == 4: instrumented build (clock64 per phase, summed over warps into ws.counters[4..7]); math as flavour 0
 #define XS_TICK(slot)                                              \
     do {                                                           \
-        if (kMath == 4) {                                          \
+        if (kMath == 4 || kMath == 8) {                            \
             const long long _now = clock64();                      \
             if (lane == 0) t_acc[slot] += (u64)(_now - t_last);    \
             t_last = _now;                                         \
@@ -458,7 +458,7 @@ k_scan_co(xs_plan pl, RasterArgs a, Workspace ws, double2 *out_co, int *idx_co) 
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr int TP = NW * P;  // pixels per tile
-    constexpr bool kCentred = kMath == 5 || kMath == 6 || kMath == 7;  // two-FFMA2 centred cost (see the settle section)
+    constexpr bool kCentred = kMath == 5 || kMath == 6 || kMath == 7 || kMath == 8;  // 8: centred + phase timers  // two-FFMA2 centred cost (see the settle section)
     constexpr bool kWarpOwn = kMath == 6;
     constexpr bool kJOuter = kMath == 7;  // experiment: phi-pair loop outside the pixel loop (shorter live ranges of lambda, M)  // every warp loads and writes its own P pixels: one CTA barrier per tile
 
@@ -948,7 +948,7 @@ k_scan_co(xs_plan pl, RasterArgs a, Workspace ws, double2 *out_co, int *idx_co) 
     if (lane == 0) {
         if (n_scanned) atomicAdd(&ws.counters[2], n_scanned);
         if (n_refined) atomicAdd(&ws.counters[3], n_refined);
-        if (kMath == 4)
+        if (kMath == 4 || kMath == 8)
         {
             for (int k = 0; k < 4; ++k) atomicAdd(&ws.counters[4 + k], t_acc[k]);
             atomicAdd(&ws.counters[9], t_acc[4]);
@@ -1289,6 +1289,7 @@ static int dispatch_scan(const xs_plan *pl, const RasterArgs &ra, const Workspac
             switch (scan_variant()) {
                 case 30: return launch_scan<3, 8, 8, 2, 3>(pl, ra, ws, out_co, idx_co, stream);            // NOT exact: no refinement (measurement)
                 case 41: return launch_scan<3, 8, 4, 4, 4, false, 3>(pl, ra, ws, out_co, idx_co, stream);  // direct form with phase timers
+                case 42: return launch_scan<3, 8, 4, 3, 8, false, 3>(pl, ra, ws, out_co, idx_co, stream);  // shipped form with phase timers
                 case 70: return launch_scan<3, 8, 4, 4, 5, false, 3>(pl, ra, ws, out_co, idx_co, stream);  // centred, 4 CTAs (128 regs, spills)
                 case 80: return launch_scan<3, 8, 4, 3, 6, false, 3>(pl, ra, ws, out_co, idx_co, stream);  // centred, per-warp slots, 1 barrier/tile
                 case 99: return launch_scan<3, 8, 4, 4, 0, false, 3>(pl, ra, ws, out_co, idx_co, stream);  // direct form (the former default)
