@@ -231,3 +231,24 @@ def test_direction_helpers():
     assert abs(x.dir_meteo_to_sample(100.0, 10.0) - 0.0) < 1e-15           # pi/2 - deg2rad(meteo - heading)
     back = x.dir_sample_to_meteo(np.rad2deg(x.dir_meteo_to_sample(a, 12.0)), 12.0)
     np.testing.assert_allclose(back, a)
+
+
+def test_gradients_host_side():
+    """Argument errors of local_gradients are raised on the host; without a GPU the call refuses to run (no CPU
+    fallback); the dataset stand-in gives attribute and item access like xarray.Dataset."""
+    import torch
+
+    from xsarsea_b200 import _xr, gradients
+    from xsarsea_b200._native import NativeError
+
+    with pytest.raises(ValueError, match="2D image"):
+        gradients.local_gradients(np.zeros((2, 3, 4)))
+    with pytest.raises(ValueError, match="2D image"):
+        gradients.local_gradients(torch.zeros(5))
+    if not torch.cuda.is_available():
+        with pytest.raises(NativeError):
+            gradients.local_gradients(np.zeros((8, 8)))
+    ds = _xr.DatasetLite(G2=np.ones(2), c=np.zeros(2))
+    assert ds.G2 is ds["G2"] and set(ds.data_vars) == {"G2", "c"}
+    with pytest.raises(AttributeError):
+        ds.G3

@@ -35,13 +35,16 @@ def local_gradients(image):
     (an xarray.Dataset when xarray is installed and the input is labelled, otherwise a dict-like with attribute access;
     CUDA tensors in -> CUDA tensors out.)
     """
-    torch = nat.torch_cuda()
     if _is_tensor(image):
+        if image.dim() != 2:
+            raise ValueError("local_gradients needs a 2D image with dims ['line', 'sample']")
+        nat.torch_cuda()
         g2, g3, c = dev.local_gradients(image.cuda())
         return _xr.DatasetLite(G2=g2, G3=g3, c=c)
     vals = np.asarray(image.data if _xr.is_labelled(image) else image)
     if vals.ndim != 2:
         raise ValueError("local_gradients needs a 2D image with dims ['line', 'sample']")
+    torch = nat.torch_cuda()
     dt = np.float32 if vals.dtype == np.float32 else np.float64
     g2, g3, c = (t.cpu().numpy() for t in dev.local_gradients(torch.from_numpy(np.ascontiguousarray(vals, dtype=dt)).cuda()))
     if not _xr.is_labelled(image):
