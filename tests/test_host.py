@@ -252,3 +252,26 @@ def test_gradients_host_side():
     assert ds.G2 is ds["G2"] and set(ds.data_vars) == {"G2", "c"}
     with pytest.raises(AttributeError):
         ds.G3
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the reference's CPU path; runs without a GPU) prints exactly one JSON line with the
+    keys the driver reads, on the same metric / unit / workload as the CUDA arm."""
+    import json
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+                        "--cpu-lines", "16"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    import bench
+
+    assert d["impl"] == "reference" and d["metric"] == bench.METRIC and d["unit"] == "px/s" and d["higher_is_better"] is True
+    assert d["value"] > 0 and d["steps"] == 1 and d["warmup"] == 1 and d["n_gpus"] == 1
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "px/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "gmf_cmod5n" in d["config"]["workload"] and "sample" in d["config"]
