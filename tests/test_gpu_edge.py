@@ -274,7 +274,7 @@ def test_plan_lifecycle_and_api_latency(dev):
         out = ws.invert_from_model(inc, s0, ancillary_wind=anc, model="gmf_cmod5n")
         dt = time.perf_counter() - t0
     assert out.shape == (H, W) and np.isfinite(out).mean() > 0.99
-    assert dt < 0.25, f"cached-plan call on 1 Mpx took {dt:.3f} s"   # kernel ~12 ms + 72 MB of PCIe traffic
+    assert dt < 0.5, f"cached-plan call on 1 Mpx took {dt:.3f} s"   # kernel ~11 ms + 72 MB of PCIe traffic (typically 30-40 ms)
     print(f"invert_from_model 1000x1000 from host: {1e3 * dt:.1f} ms")
 
 
