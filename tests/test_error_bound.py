@@ -1,0 +1,139 @@
+"""CPU check of the error bound of the centred FP32 scan (`k_scan_co` with kMath 5).
+
+The kernel's exactness rests on `E >= |J''_fp32 - J''_exact|` for every candidate that can still win.  This test
+re-creates the kernel's FP32 operation sequence in numpy (every FP32 operation is evaluated exactly in float64 -- a
+product of two floats and one addend fit -- and rounded once to float32), evaluates the exact shifted cost in extended
+precision, mirrors the kernel's formula for E, and checks on seeded adversarial pixels (sigma0 on LUT nodes, ancillary
+wind on candidates, strong winds, wide spreads of sigma0 inside a warp) that
+  * every candidate with |L/dsig - s/dsig| <= D has an FP32 cost within E of the exact one,
+  * the exact argmin is inside the band {J_fp32 <= m32 + 2E}, i.e. the FP64 refinement sees it.
+No GPU and nothing of the product is involved: this pins the mathematics the kernel's comments and DESIGN.md state."""
+import numpy as np
+import pytest
+
+import oracle
+
+U = 2.0 ** -24
+F32 = np.float32
+
+
+def f32(x):
+    return np.asarray(x, dtype=np.float64).astype(F32).astype(np.float64)   # one rounding to float32, held as float64
+
+
+def fma32(a, b, c):
+    """fl32(a*b + c) for float32-valued a, b, c (a*b is exact in float64; the sum is rounded to float64 first, which can
+    differ from a true fused rounding by a double-rounding ulp of float32 in ~1e-9 of the cases -- irrelevant for a
+    magnitude check)."""
+    return f32(a * b + c)
+
+
+@pytest.fixture(scope="module")
+def slabs():
+    gi = np.array([20.0, 30.0, 37.5, 45.0, 60.0])
+    gw, gp = np.linspace(0.2, 50, 499), np.linspace(0, 180, 181)
+    lut_db = 10 * np.log10(oracle.lut_build("gmf_cmod5n", gi, gw, gp) + 1e-15)
+    return lut_db, gw, gp
+
+
+def kernel_E(m32, sc_abs, amag, lmax, wmax):
+    """Mirror of the kMath == 5 branch of the settle section of k_scan_co (float arithmetic there, float64 here)."""
+    A, W = amag, wmax * 1.0000002
+    T = W * A + 0.25 * W * W
+    SC = sc_abs
+    D = np.sqrt(np.maximum(m32 + SC * SC * 1.0000002, 0.0) + 0.25 * A * A + 1.0)
+    Lam = D + SC
+    E = 5.9604645e-8 * 1.5 * (2 * Lam * lmax + 2 * SC * lmax + 4 * Lam * Lam + 6 * SC * Lam + SC * SC + D * D + 4 * T)
+    return E, D
+
+
+@pytest.mark.parametrize("spread_db", [0.0, 0.3, 3.0, 15.0])
+def test_centred_scan_error_bound(slabs, spread_db):
+    lut_db, gw, gp = slabs
+    dsig = 0.1
+    rng = np.random.default_rng(int(spread_db * 10) + 1)
+    cphi, sphi = np.cos(np.radians(gp)), np.sin(np.radians(gp))
+    nwh32, w2q32 = f32(-0.5 * gw), f32(0.25 * gw * gw)
+    worst = 0.0
+    for b in range(lut_db.shape[0]):
+        Ls = lut_db[b] / dsig                       # [n_wspd, n_phi] float64 (the kernel: (float)(L/dsig))
+        L32 = f32(Ls)
+        lmax = np.abs(L32).max() * 1.0000002
+        for trial in range(24):
+            kind = trial % 6
+            iw, ip = rng.integers(0, gw.size), rng.integers(0, gp.size)
+            s = lut_db[b, iw, ip] if kind in (0, 1) else rng.uniform(-35.0, 5.0)      # on a node / anywhere
+            if kind == 4:
+                s = rng.uniform(-60.0, 20.0)                                          # outside the LUT range
+            a_w = gw[iw] if kind in (0, 2) else rng.uniform(0.0, 60.0)
+            a_p = np.radians(gp[ip]) if kind in (0, 2) else rng.uniform(0.0, np.pi)
+            qa, qb = a_w * np.cos(a_p), a_w * np.sin(a_p)                             # qb = |Im| (mirrored phi grid)
+            if kind == 5:
+                qa = qb = 0.0
+            # warp centre: somewhere within +- spread of the pixel's own sigma0 (the kernel: middle of the warp's 8 pixels)
+            cs = float(F32((s + rng.uniform(-spread_db, spread_db)) / dsig))
+            sc = s / dsig - cs
+            k32 = float(F32(-2.0 * sc))
+            g64 = qa * cphi + qb * sphi
+            g32 = f32(g64)
+            # the kernel's operation sequence
+            Lc = f32(L32 - cs)
+            M = fma32(Lc, Lc, w2q32[:, None])
+            aa = fma32(k32, Lc, M)
+            J32 = fma32(nwh32[:, None], g32[None, :], aa)
+            # exact shifted cost J'' = J' - sc^2 in extended precision
+            lam = Ls.astype(np.longdouble) - np.longdouble(cs)
+            Jx = lam * lam - 2 * np.longdouble(sc) * lam + (np.longdouble(0.25) * gw * gw)[:, None] - (
+                np.longdouble(0.5) * gw)[:, None] * g64.astype(np.longdouble)[None, :]
+            err = np.abs(J32 - Jx.astype(np.float64))
+            m32 = J32.min()
+            amag = float(F32(np.hypot(qa, qb))) * 1.0000002
+            E, D = kernel_E(m32, abs(sc) * 1.0000002, amag, lmax, gw.max())
+            if not (E < 0.25):          # the kernel sends such pixels to the exhaustive FP64 kernel
+                continue
+            d = np.abs(Ls - s / dsig)
+            can_win = d <= D
+            assert can_win.any()
+            assert err[can_win].max() <= E, (b, trial, kind, err[can_win].max(), E)
+            worst = max(worst, err[can_win].max() / E)
+            # the exact argmin (first minimum) is inside the band the refinement examines, and candidates outside the
+            # |d| <= D cone are outside the band
+            ix = np.unravel_index(np.argmin(Jx), Jx.shape)
+            assert J32[ix] <= m32 + 2 * E
+            assert (J32[~can_win] > m32 + 2 * E).all()
+    assert 0 < worst <= 1.0
+
+
+def test_direct_form_error_bound(slabs):
+    """Same check for the direct form (XS_SCAN_VARIANT=99): d = L32 - s32, t = fma(-w/2, g, w^2/4), J' = fma(d, d, t) with
+    E = 1.5 u [3T + 2D(Lmax + |q| + D) + |m32| + A^2/4 + T]."""
+    lut_db, gw, gp = slabs
+    dsig = 0.1
+    rng = np.random.default_rng(3)
+    cphi, sphi = np.cos(np.radians(gp)), np.sin(np.radians(gp))
+    nwh32, w2q32 = f32(-0.5 * gw), f32(0.25 * gw * gw)
+    for b in range(lut_db.shape[0]):
+        Ls = lut_db[b] / dsig
+        L32 = f32(Ls)
+        lmax = np.abs(L32).max() * 1.0000002
+        for trial in range(12):
+            s = rng.uniform(-35.0, 5.0)
+            a_w, a_p = rng.uniform(0.0, 60.0), rng.uniform(0.0, np.pi)
+            qa, qb = a_w * np.cos(a_p), a_w * np.sin(a_p)
+            nq32 = float(F32(-(s / dsig)))
+            g64 = qa * cphi + qb * sphi
+            d32 = f32(L32 + nq32)
+            t32 = fma32(nwh32[:, None], f32(g64)[None, :], w2q32[:, None])
+            J32 = fma32(d32, d32, t32)
+            dx = Ls.astype(np.longdouble) - np.longdouble(s / dsig)
+            Jx = dx * dx + (np.longdouble(0.25) * gw * gw)[:, None] - (np.longdouble(0.5) * gw)[:, None] * g64.astype(
+                np.longdouble)[None, :]
+            m32 = J32.min()
+            A, W = float(F32(np.hypot(qa, qb))) * 1.0000002, gw.max() * 1.0000002
+            T = W * A + 0.25 * W * W
+            D = np.sqrt(max(m32, 0.0) + 0.25 * A * A + 1.0)
+            E = 5.9604645e-8 * 1.5 * (3 * T + 2 * D * (lmax + abs(nq32) + D) + (abs(m32) + 0.25 * A * A + T))
+            assert E < 0.25
+            can_win = np.abs(Ls - s / dsig) <= D
+            assert np.abs(J32 - Jx.astype(np.float64))[can_win].max() <= E
+            assert J32[np.unravel_index(np.argmin(Jx), Jx.shape)] <= m32 + 2 * E
