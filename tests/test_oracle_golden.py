@@ -193,3 +193,39 @@ def test_gradients_oracle_against_golden_and_an_independent_restatement(golden):
     np.testing.assert_allclose(grad3, g["even/G3"], rtol=1e-12)
     cq = np.abs(grad2) / (grad3 + 1e-5)
     np.testing.assert_allclose(np.where(cq <= 1, cq, 0), g["even/c"], rtol=0, atol=1e-12)
+
+
+def test_nesz_line_fit_algorithm_matches_polyfit():
+    """The per-line fit of xs_nesz_flatten (one pass, sums shifted by the line's first finite point, centred normal
+    equations; equal abscissae -> the minimum-norm solution a = ybar/(2x), b = ybar/2 that np.polyfit's scaled lstsq
+    returns) transcribed to numpy, against np.polyfit itself -- pins the algorithm the kernel's comments state."""
+    import warnings
+
+    rng = np.random.default_rng(9)
+
+    def device_fit(x, y):
+        x0, y0 = x[0], y[0]
+        dx, dy = x - x0, y - y0
+        n, sx, sy, sxx, sxy = x.size, dx.sum(), dy.sum(), (dx * dx).sum(), (dx * dy).sum()
+        mx, my = sx / n, sy / n
+        cxx, cxy = sxx - sx * mx, sxy - sx * my
+        if cxx > 0 and np.isfinite(cxx):
+            a = cxy / cxx
+            return a, (y0 + my) - a * (x0 + mx)
+        xb, yb = x0 + mx, y0 + my
+        return yb / (2 * xb), yb / 2
+
+    for n in (2, 3, 50, 5000):
+        x = np.sort(rng.uniform(19, 47, n))
+        y = -30 + 0.15 * x + rng.normal(0, 0.3, n)
+        a, b = device_fit(x, y)
+        pa, pb = np.polyfit(x, y, 1)
+        np.testing.assert_allclose([a, b], [pa, pb], rtol=1e-9)
+        np.testing.assert_allclose(a * x + b, pa * x + pb, rtol=0, atol=1e-10)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")          # RankWarning: that is the point
+        for n in (1, 4):
+            x, y = np.full(n, 33.25), rng.uniform(-40, -20, n)
+            a, b = device_fit(x, y)
+            pa, pb = np.polyfit(x, y, 1)
+            np.testing.assert_allclose([a, b], [pa, pb], rtol=1e-12)
