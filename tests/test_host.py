@@ -275,3 +275,57 @@ def test_bench_reference_arm_contract():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "px/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "gmf_cmod5n" in d["config"]["workload"] and "sample" in d["config"]
+
+
+def test_nc_lut_files_host_side(tmp_path):
+    """Row A6 on the host: LUT files in the reference's schema (models.py:232-262, 368-379) are parsed into models --
+    name = file stem with the `nc_lut_` prefix (:446), alias = the `model` attribute, low-resolution files move their
+    steps into `*_lr` (:392-395), files without the prefix are ignored, the raw table comes back as written."""
+    from scipy.io import netcdf_file
+
+    from xsarsea_b200 import windspeed as ws
+    from xsarsea_b200.windspeed.models import Model, NcLutModel
+
+    def write(path, resolution, inc, wspd, phi=None, units="dB", pol="VH", model="testlut"):
+        with netcdf_file(str(path), "w") as nc:
+            nc.units, nc.pol, nc.model, nc.resolution = units, pol, model, resolution
+            nc.inc_range, nc.wspd_range = np.array([inc[0], inc[-1]]), np.array([wspd[0], wspd[-1]])
+            nc.inc_step, nc.wspd_step = float(inc[1] - inc[0]), float(wspd[1] - wspd[0])
+            nc.createDimension("incidence", inc.size)
+            nc.createDimension("wspd", wspd.size)
+            nc.createVariable("incidence", "d", ("incidence",))[:] = inc
+            nc.createVariable("wspd", "d", ("wspd",))[:] = wspd
+            dims = ("incidence", "wspd")
+            shape = (inc.size, wspd.size)
+            if phi is not None:
+                nc.phi_range, nc.phi_step = np.array([phi[0], phi[-1]]), float(phi[1] - phi[0])
+                nc.createDimension("phi", phi.size)
+                nc.createVariable("phi", "d", ("phi",))[:] = phi
+                dims, shape = dims + ("phi",), shape + (phi.size,)
+            table = -30.0 + np.arange(np.prod(shape), dtype=np.float64).reshape(shape) * 1e-3
+            nc.createVariable("sigma0_model", "d", dims)[:] = table
+        return table
+
+    inc, wspd, phi = np.linspace(17, 50, 34), np.linspace(3, 80, 78), np.linspace(0, 180, 37)
+    t_hi = write(tmp_path / "nc_lut_testlut.nc", "high", inc, wspd)
+    write(tmp_path / "nc_lut_testlow.nc", "low", inc[::2], wspd[::2], phi, pol="VV", model="testlow")
+    write(tmp_path / "other_testlut.nc", "high", inc, wspd)          # no nc_lut_ prefix: not registered
+    try:
+        ws.register_nc_luts(str(tmp_path))
+        df = ws.available_models()
+        assert "nc_lut_testlut" in df.index and "nc_lut_testlow" in df.index and "other_testlut" not in df.index
+        hi = ws.get_model("nc_lut_testlut")
+        assert isinstance(hi, NcLutModel) and ws.get_model("testlut") is hi and hi.iscrosspol and hi.pol == "VH"
+        assert hi.units == "dB" and hi.resolution == "high" and hi.inc_range == [17.0, 50.0] and hi.wspd_range == [3.0, 80.0]
+        assert hi.phi_range is None and abs(hi.inc_step - 1.0) < 1e-12 and abs(hi.wspd_step - 1.0) < 1e-12
+        lo = ws.get_model("testlow")
+        assert lo.iscopol and lo.resolution == "low" and lo.phi_range == [0.0, 180.0]
+        assert abs(lo.inc_step_lr - 2.0) < 1e-12 and abs(lo.wspd_step_lr - 2.0) < 1e-12 and abs(lo.phi_step_lr - 5.0) < 1e-12
+        assert lo.inc_step == 0.1 and lo.wspd_step == 0.1 and lo.phi_step == 1           # defaults of models.py:46-48
+        vals, g_inc, g_wspd, g_phi, units, res = hi._raw_lut_host()
+        assert np.array_equal(vals, t_hi) and np.array_equal(g_inc, inc) and np.array_equal(g_wspd, wspd) and g_phi is None
+        assert units == "dB" and res == "high"
+        assert ws.register_nc_luts(str(tmp_path), gmf_names=["nothing"]) is None   # filter by name: nothing added
+    finally:
+        for n in ("nc_lut_testlut", "nc_lut_testlow"):
+            Model._available_models.pop(n, None)
