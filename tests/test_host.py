@@ -329,3 +329,39 @@ def test_nc_lut_files_host_side(tmp_path):
     finally:
         for n in ("nc_lut_testlut", "nc_lut_testlow"):
             Model._available_models.pop(n, None)
+
+
+def test_cmod7_table_reader_host_side(tmp_path):
+    """Row A7 on the host: the KNMI table layout (cmod7.py:19-75) -- little-endian float32, one leading and one trailing
+    record marker dropped, (wspd, phi, inc) in Fortran order, linear units, low resolution -- and the registration
+    (name gmf_cmod7, priority 1 so that it owns the `cmod7` alias)."""
+    from xsarsea_b200 import windspeed as ws
+    from xsarsea_b200.windspeed.models import Model
+
+    n_w, n_p, n_i = 250, 73, 51
+    rng = np.random.default_rng(1)
+    table = rng.uniform(1e-4, 1.0, (n_i, n_w, n_p)).astype(np.float32)              # [inc][wspd][phi]
+    fortran = np.transpose(table, (1, 2, 0))                                         # (wspd, phi, inc)
+    rec = np.concatenate([[123.0], fortran.reshape(-1, order="F"), [456.0]]).astype("<f4")
+    d = tmp_path / "cmod7"
+    d.mkdir()
+    rec.tofile(str(d / "gmf_cmod7_vv.dat_little_endian"))
+    try:
+        ws.register_cmod7(str(d))
+        m = ws.get_model("gmf_cmod7")
+        assert ws.get_model("cmod7") is m and m.pol == "VV" and m._priority == 1 and m.iscopol
+        vals, inc, wspd, phi, units, res = m._raw_lut_host()
+        assert vals.shape == (n_i, n_w, n_p) and vals.dtype == np.float64 and units == "linear" and res == "low"
+        assert np.array_equal(vals, table.astype(np.float64))
+        assert inc[0] == 16 and inc[-1] == 66 and inc.size == n_i and phi[0] == 0 and phi[-1] == 180 and phi.size == n_p
+        assert abs(wspd[0] - 0.2) < 1e-12 and abs(wspd[-1] - 50.0) < 1e-9 and wspd.size == n_w
+    finally:
+        Model._available_models.pop("gmf_cmod7", None)
+    import pytest as _pytest
+
+    try:
+        ws.register_cmod7(str(tmp_path / "missing"))
+        with _pytest.raises(FileNotFoundError):
+            ws.get_model("gmf_cmod7")._raw_lut_host()
+    finally:
+        Model._available_models.pop("gmf_cmod7", None)
