@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define XS_ABI_VERSION 1
+#define XS_ABI_VERSION 2
 
 /* error codes */
 #define XS_OK 0
@@ -64,6 +64,15 @@ int xs_abi_version(void);
 const char *xs_last_error(void);
 /* Number of kernel launches issued by this library in this process so far (bench.py's gpu_launches). */
 int64_t xs_launch_count(void);
+
+/* A pair of CUDA events owned by the library, handed to xs_invert through xs_invert_args.scan_timer to time the co-pol
+ * scan on the launching stream (bench.py's roofline of the dominant kernel).  One timer per in-flight call: timers, like
+ * workspaces, belong to the call and not to the plan, so concurrent calls on one plan do not share any mutable state. */
+typedef struct xs_timer xs_timer;
+int xs_timer_create(xs_timer **timer_out);
+void xs_timer_destroy(xs_timer *timer);
+/* Waits for the second event; XS_E_INVALID if the timer has not been recorded by an xs_invert yet. */
+int xs_timer_elapsed_ms(xs_timer *timer, float *ms);
 
 /* ---- GMF evaluation ------------------------------------------------------------------------- */
 
@@ -126,9 +135,18 @@ void xs_plan_destroy(xs_plan *plan);
 #define XS_FLAG_CR_ABS 4u       /* out_cr is float64 |wind| instead of complex128 (windspeed.py:422-423) */
 #define XS_FLAG_CR_FULL_SCAN 8u /* verification: scan every cross-pol candidate (FP32 filter + FP64 refinement) even where
                                    the exact interval search applies (LUT row non-decreasing in wspd); same results */
+#define XS_FLAG_OUT_SPEED_DIR 16u /* row F2 epilogue: out_co / out_cr are two planes [speed m/s | direction deg], n_px
+                                   elements each (float64, or float32 with XS_FLAG_OUT_F32), instead of complex128:
+                                   np.abs(wind) and np.angle(wind, deg=True), the post-processing every caller of the
+                                   reference applies (docs/examples/windspeed_retrieval_L1.ipynb cell 33).  Halves (f64)
+                                   or quarters (f32) the device->host copy.  With XS_FLAG_CR_ABS out_cr stays the single
+                                   float64 speed plane. */
+#define XS_FLAG_DIR_METEO 32u   /* with OUT_SPEED_DIR: direction = (90 - angle + ground_heading) % 360, i.e.
+                                   dir_sample_to_meteo (detrend.py:114-130) wrapped to [0, 360) */
+#define XS_FLAG_OUT_F32 64u     /* with OUT_SPEED_DIR: float32 planes */
 
 /* scan modes */
-#define XS_MODE_FAST 0  /* FP32 FFMA2 scan + FP64 refinement of every candidate block within the error band */
+#define XS_MODE_FAST 0  /* FP32 FFMA2 scan (k_scan_co) + exact refinement of every candidate inside the error band (k_refine_co) */
 #define XS_MODE_FP64 1  /* exhaustive FP64 evaluation of every candidate (verification / fallback) */
 
 typedef struct xs_invert_args {
@@ -152,29 +170,30 @@ typedef struct xs_invert_args {
     /* scratch */
     void *workspace;
     size_t workspace_bytes;   /* >= xs_invert_workspace_bytes(plan, n_px) */
+    /* per-call bookkeeping (ABI 2; all optional): nothing mutable lives on the plan, so one plan may serve any number
+     * of concurrent xs_invert calls (different host threads and streams), each with its own workspace */
+    uint64_t *counters_dev;   /* device, XS_N_COUNTERS words: the call's counters, copied on the stream at the end */
+    xs_timer *scan_timer;     /* recorded around the co-pol scan (k_scan_co + k_refine_co) of this call */
+    /* F2 epilogue (XS_FLAG_OUT_SPEED_DIR): planes instead of complex128 */
+    const void *ground_heading; /* device, n_px of `dtype`, degrees; NULL = directions stay in the antenna convention */
+    double ground_heading_scalar; /* used when ground_heading is NULL and XS_FLAG_DIR_METEO is set */
 } xs_invert_args;
 
-size_t xs_invert_workspace_bytes(const xs_plan *plan, int64_t n_px);
+#define XS_N_COUNTERS 16
+
+/* Workspace an xs_invert call with these flags needs (256-byte aligned device memory, owned by the call). */
+size_t xs_invert_workspace_bytes(const xs_plan *plan, int64_t n_px, uint32_t flags);
 
 /* K1: replaces _invert_from_model_numpy / __invert_from_model_1d, windspeed/windspeed.py:132-331
  * (gufunc "(n),(n),(n),(n),(n)->(n),(n)"), with the dB prologue (:126-128) and the dual-pol merge
  * epilogue (:426-428) optionally fused. */
 int xs_invert(const xs_plan *plan, const xs_invert_args *args, void *stream);
 
-/* Statistics of the last xs_invert on this plan (device counters, read synchronously):
- * stats[0] = co-pol pixels settled by the FP32 scan, [1] = (lane, chunk) cells re-examined by the refinement,
- * [2] = pixels sent to the exhaustive FP64 scan, [3] = co-pol tiles. */
-int xs_plan_last_stats(const xs_plan *plan, int64_t stats[4]);
-
-/* Raw device counters of the last xs_invert on this plan (development aid): [0] tiles, [1] pixels queued for the
- * exhaustive kernel, [2] pixels settled by the scan, [3] chunks re-evaluated in FP64, [4..7] clock64 sums per phase
- * (prologue, main loop, refinement, write-out) when the instrumented scan variant is selected, else 0. */
-int xs_plan_debug_counters(const xs_plan *plan, unsigned long long out[16]);
-
-/* Device time in ms of the co-pol scan kernel (k_scan_co) of the last xs_invert on this plan, from CUDA events
- * recorded around that launch on the caller's stream (waits for the kernel to finish).  Used by bench.py for the
- * roofline of the dominant kernel.  XS_E_INVALID if no scan has been launched on the plan yet. */
-int xs_plan_last_scan_ms(const xs_plan *plan, float *ms);
+/* Layout of the counters an xs_invert call leaves in args.counters_dev (read them with any device->host copy after
+ * the stream has reached the end of the call): [0] co-pol tiles, [1] pixels sent to the exhaustive FP64 scan,
+ * [2] co-pol pixels settled by the FP32 scan (+ refinement), [3] (lane, chunk) cells re-examined by the refinement,
+ * [4..7], [9], [10] clock64 sums per phase when an instrumented scan variant is selected (development aid), else 0,
+ * [8] tile hand-out cursor, [11] pixels the refinement settled in FP64 (more than one candidate inside the band). */
 
 /* ---- detrend -------------------------------------------------------------------------------- */
 

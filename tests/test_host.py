@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_native.EXPORTS), declared ^ set(_native.EXPORTS)
     for sym in declared:
         assert hasattr(lib, sym), sym
-    assert lib.xs_abi_version() == 1
+    assert lib.xs_abi_version() == 2
     assert lib.xs_launch_count() == 0    # loading the library launches nothing
 
 

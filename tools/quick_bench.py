@@ -39,11 +39,13 @@ for dual in (False, True):
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        oc, ox, _, _ = plan.invert(inc, s_co, s_cr if dual else None, 0.1, anc, merge_dual=dual, mode=mode)
+        oc, ox, _, _ = plan.invert(inc, s_co, s_cr if dual else None, 0.1, anc, merge_dual=dual, mode=mode, timed=(mode == 0))
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
         st = plan.last_stats()
+        if mode == 0:
+            st['scan_ms'], st['refine_ms'] = plan.last_scan_ms()
         print(json.dumps(dict(dual=dual, H=H, W=W, ms=ms, Mpx_s=H * W / ms / 1e3, **st,
                               frac_fp32_peak=H * W * (727178 if dual else 722552) / (ms * 1e-3) / 74.4e12)), flush=True)
 print("debug counters", plan.debug_counters())

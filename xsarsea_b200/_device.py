@@ -7,6 +7,7 @@ the reference does.
 from __future__ import annotations
 
 import ctypes
+import threading
 
 import numpy as np
 
@@ -171,18 +172,48 @@ def local_gradients(image):
     return g2, g3, c
 
 
+class ScanTimer:
+    """An `xs_timer` (CUDA events recorded around the co-pol scan of one xs_invert call)."""
+
+    def __init__(self):
+        self._h = ctypes.c_void_p()
+        nat.check(nat.load().xs_timer_create(ctypes.byref(self._h)), "xs_timer_create")
+
+    def elapsed_ms(self):
+        """(k_scan_co, k_refine_co) device times in ms; waits for the kernels to finish."""
+        ms = (ctypes.c_float * 2)()
+        nat.check(nat.load().xs_timer_elapsed_ms(self._h, ms), "xs_timer_elapsed_ms")
+        return float(ms[0]), float(ms[1])
+
+    def __del__(self):
+        try:
+            if self._h:
+                nat.load().xs_timer_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+
 class InversionPlan:
     """Owns an xs_plan: the device LUTs of one (co-pol, cross-pol) model pair plus the scan image.
 
     co = (lut_db [n_inc, n_wspd, n_phi] device f64, inc_grid, wspd_grid, phi_grid) or None
-    cr = (lut_db [n_inc, n_wspd] device f64, inc_grid, wspd_grid) or None
+    cr = (lut_db [n_inc_cr, n_wspd_cr] device f64, inc_grid, wspd_grid) or None
     Mirrors the per-call setup of windspeed.py:139-181 (done once here and cached by the caller).
+
+    Re-entrant (dask's threaded scheduler calls the operator concurrently): the native plan is
+    immutable after creation; every `invert` call allocates its own workspace, counters and (optionally) timer, and the
+    "last call" bookkeeping is per host thread.  `close()` is deferred while calls are in flight.
     """
 
     def __init__(self, co=None, cr=None, dsig_co=0.1):
         torch = _t()
         L = nat.load()
         self._handle = None
+        self._lock = threading.Lock()
+        self._users = 0
+        self._close_pending = False
+        self._tls = threading.local()
         d = nat.PlanDesc()
         keep = []
         self.co_grids = self.cr_grids = None
@@ -215,12 +246,16 @@ class InversionPlan:
         h = ctypes.c_void_p()
         nat.check(L.xs_plan_create(ctypes.byref(d), nat.stream_ptr(), ctypes.byref(h)), "xs_plan_create")
         self._handle = h
-        self._workspace = None
 
     def close(self):
-        if self._handle is not None:
-            nat.load().xs_plan_destroy(self._handle)
-            self._handle = None
+        """Free the native plan -- after the calls in flight on other threads have returned."""
+        with self._lock:
+            if self._users > 0:
+                self._close_pending = True
+                return
+            h, self._handle = self._handle, None
+        if h is not None:
+            nat.load().xs_plan_destroy(h)
 
     def __del__(self):
         try:
@@ -228,15 +263,34 @@ class InversionPlan:
         except Exception:
             pass
 
-    def workspace_bytes(self, n_px: int) -> int:
-        return int(nat.load().xs_invert_workspace_bytes(self._handle, int(n_px)))
+    def _acquire(self):
+        with self._lock:
+            if self._handle is None or self._close_pending:
+                raise nat.NativeError("InversionPlan is closed")
+            self._users += 1
+            return self._handle
+
+    def _release(self):
+        with self._lock:
+            self._users -= 1
+            last = self._users == 0 and self._close_pending
+            if last:
+                self._close_pending = False
+        if last:
+            self.close()
+
+    def workspace_bytes(self, n_px: int, flags: int = 0) -> int:
+        return int(nat.load().xs_invert_workspace_bytes(self._handle, int(n_px), int(flags)))
 
     def invert(self, inc, sigma0_co=None, sigma0_cr=None, dsig_cr=0.1, ancillary=None, *, sigma0_db=False,
                merge_dual=False, cr_abs=False, mode=nat.MODE_FAST, want_idx=False, out_co=None, out_cr=None,
-               need_co=False, cr_full_scan=False):
+               need_co=False, cr_full_scan=False, speed_dir=False, ground_heading=None, out_f32=False, timed=False):
         """Run K1 on device tensors (all the same shape; float64/complex128 or float32/complex64).
 
         Returns (wind_co complex128 | None, wind_cr complex128 (float64 if cr_abs) | None, idx_co, idx_cr).
+        speed_dir=True (row F2 epilogue): the winds are [2, *shape] planes (speed m/s, direction deg; float32 with
+        out_f32) instead of complex128 -- direction = np.angle(wind, deg=True), or (90 - angle + ground_heading) % 360
+        when `ground_heading` (device raster or scalar, degrees) is given.
         """
         torch = _t()
         L = nat.load()
@@ -257,48 +311,78 @@ class InversionPlan:
         a = nat.InvertArgs()
         a.inc, a.sigma0_co, a.sigma0_cr = inc.data_ptr(), nat.dptr(s_co), nat.dptr(s_cr)
         a.ancillary = nat.dptr(anc)
-        dsig_t = None
+        dsig_t = gh_t = None
         if hasattr(dsig_cr, "shape") and getattr(dsig_cr, "ndim", 0) > 0:
             dsig_t = prep(dsig_cr, rdt)
             a.dsig_cr = dsig_t.data_ptr()
         else:
             a.dsig_cr_scalar = float(dsig_cr)
         a.dtype = nat.XS_F32 if f32 else nat.XS_F64
-        a.flags = (nat.FLAG_SIGMA0_DB if sigma0_db else 0) | (nat.FLAG_MERGE_DUAL if merge_dual else 0) | (
+        flags = (nat.FLAG_SIGMA0_DB if sigma0_db else 0) | (nat.FLAG_MERGE_DUAL if merge_dual else 0) | (
             nat.FLAG_CR_ABS if cr_abs else 0) | (nat.FLAG_CR_FULL_SCAN if cr_full_scan else 0)
+        if speed_dir:
+            flags |= nat.FLAG_OUT_SPEED_DIR | (nat.FLAG_OUT_F32 if out_f32 else 0)
+            if ground_heading is not None:
+                flags |= nat.FLAG_DIR_METEO
+                if hasattr(ground_heading, "shape") and getattr(ground_heading, "ndim", 0) > 0:
+                    gh_t = prep(ground_heading, rdt)
+                    a.ground_heading = gh_t.data_ptr()
+                else:
+                    a.ground_heading_scalar = float(ground_heading)
+        elif ground_heading is not None or out_f32:
+            raise ValueError("ground_heading / out_f32 need speed_dir=True")
+        a.flags = flags
         a.mode = mode
         a.n_px = n
         has_co = self.co_grids is not None and s_co is not None
-        has_cr = self.cr_grids is not None and s_cr is not None
+        pdt = torch.float32 if out_f32 else torch.float64
         if out_co is None and (has_co or need_co):
-            out_co = torch.empty(shape, dtype=torch.complex128, device="cuda")
+            out_co = torch.empty((2,) + tuple(shape), dtype=pdt, device="cuda") if speed_dir else torch.empty(
+                shape, dtype=torch.complex128, device="cuda")
         if out_cr is None:
-            out_cr = torch.empty(shape, dtype=torch.float64 if cr_abs else torch.complex128, device="cuda")
+            if cr_abs:
+                out_cr = torch.empty(shape, dtype=torch.float64, device="cuda")
+            elif speed_dir:
+                out_cr = torch.empty((2,) + tuple(shape), dtype=pdt, device="cuda")
+            else:
+                out_cr = torch.empty(shape, dtype=torch.complex128, device="cuda")
         a.out_co, a.out_cr = nat.dptr(out_co), nat.dptr(out_cr)
         idx_co = idx_cr = None
         if want_idx:
             idx_co = torch.empty(shape, dtype=torch.int32, device="cuda")
             idx_cr = torch.empty(shape, dtype=torch.int32, device="cuda")
             a.idx_co, a.idx_cr = idx_co.data_ptr(), idx_cr.data_ptr()
-        need = self.workspace_bytes(n)
-        if self._workspace is None or self._workspace.numel() < need:
-            self._workspace = torch.empty(need, dtype=torch.uint8, device="cuda")
-        a.workspace, a.workspace_bytes = self._workspace.data_ptr(), self._workspace.numel()
-        nat.check(L.xs_invert(self._handle, ctypes.byref(a), nat.stream_ptr()), "xs_invert")
+        handle = self._acquire()
+        try:
+            # everything mutable belongs to this call: workspace (stream-ordered allocation on the current stream),
+            # counters, timer
+            need = int(L.xs_invert_workspace_bytes(handle, n, flags))
+            workspace = torch.empty(max(need, 256), dtype=torch.uint8, device="cuda")
+            counters = torch.zeros(nat.N_COUNTERS, dtype=torch.int64, device="cuda")
+            timer = ScanTimer() if timed else None
+            a.workspace, a.workspace_bytes = workspace.data_ptr(), workspace.numel()
+            a.counters_dev = counters.data_ptr()
+            a.scan_timer = timer._h if timer is not None else None
+            nat.check(L.xs_invert(handle, ctypes.byref(a), nat.stream_ptr()), "xs_invert")
+        finally:
+            self._release()
+        self._tls.counters, self._tls.timer = counters, timer
         return out_co, out_cr, idx_co, idx_cr
 
-    def last_scan_ms(self) -> float:
-        """Device time of the last co-pol scan kernel (CUDA events on the launch stream)."""
-        ms = ctypes.c_float()
-        nat.check(nat.load().xs_plan_last_scan_ms(self._handle, ctypes.byref(ms)), "xs_plan_last_scan_ms")
-        return float(ms.value)
+    def last_scan_ms(self):
+        """Device times (k_scan_co, k_refine_co) in ms of this thread's last `invert(..., timed=True)`."""
+        timer = getattr(self._tls, "timer", None)
+        if timer is None:
+            raise nat.NativeError("no timed invert() call on this thread")
+        return timer.elapsed_ms()
 
     def debug_counters(self):
-        c = (ctypes.c_uint64 * 16)()
-        nat.check(nat.load().xs_plan_debug_counters(self._handle, c), "xs_plan_debug_counters")
-        return [int(v) for v in c]
+        """Raw device counters of this thread's last invert() (layout: include/xsarsea_b200.h)."""
+        c = getattr(self._tls, "counters", None)
+        if c is None:
+            raise nat.NativeError("no invert() call on this thread")
+        return [int(v) for v in c.cpu().tolist()]
 
     def last_stats(self):
-        s = (ctypes.c_int64 * 4)()
-        nat.check(nat.load().xs_plan_last_stats(self._handle, s), "xs_plan_last_stats")
-        return dict(scan_pixels=s[0], fp64_chunks=s[1], exhaustive_pixels=s[2], tiles=s[3])
+        c = self.debug_counters()
+        return dict(scan_pixels=c[2], fp64_chunks=c[3], exhaustive_pixels=c[1], tiles=c[0], fp64_pixels=c[11])

@@ -19,6 +19,9 @@ CSRC = os.path.join(_HERE, "csrc")
 
 XS_F64, XS_F32 = 0, 1
 FLAG_SIGMA0_DB, FLAG_MERGE_DUAL, FLAG_CR_ABS, FLAG_CR_FULL_SCAN = 1, 2, 4, 8
+FLAG_OUT_SPEED_DIR, FLAG_DIR_METEO, FLAG_OUT_F32 = 16, 32, 64
+ABI_VERSION = 2
+N_COUNTERS = 16
 MODE_FAST, MODE_FP64 = 0, 1
 
 GMF_IDS = {
@@ -40,7 +43,7 @@ GMF_IDS = {
 EXPORTS = [
     "xs_abi_version", "xs_last_error", "xs_launch_count", "xs_gmf_eval", "xs_lut_build", "xs_lut_interp_axis",
     "xs_lut_to_db", "xs_lut_to_linear", "xs_plan_create", "xs_plan_destroy", "xs_invert_workspace_bytes",
-    "xs_invert", "xs_plan_last_stats", "xs_plan_last_scan_ms", "xs_plan_debug_counters", "xs_detrend",
+    "xs_invert", "xs_timer_create", "xs_timer_destroy", "xs_timer_elapsed_ms", "xs_detrend",
     "xs_dsig", "xs_dsig_wspd", "xs_nesz_flatten_workspace_bytes", "xs_nesz_flatten",
     "xs_local_gradients_workspace_bytes", "xs_local_gradients",
 ]
@@ -92,6 +95,10 @@ class InvertArgs(ctypes.Structure):
         ("idx_cr", ctypes.c_void_p),
         ("workspace", ctypes.c_void_p),
         ("workspace_bytes", ctypes.c_size_t),
+        ("counters_dev", ctypes.c_void_p),
+        ("scan_timer", ctypes.c_void_p),
+        ("ground_heading", ctypes.c_void_p),
+        ("ground_heading_scalar", ctypes.c_double),
     ]
 
 
@@ -145,15 +152,15 @@ def load():
         L.xs_plan_destroy.restype = None
         L.xs_plan_destroy.argtypes = [vp]
         L.xs_invert_workspace_bytes.restype = sz
-        L.xs_invert_workspace_bytes.argtypes = [vp, i64]
+        L.xs_invert_workspace_bytes.argtypes = [vp, i64, ctypes.c_uint32]
         L.xs_invert.restype = i32
         L.xs_invert.argtypes = [vp, ctypes.POINTER(InvertArgs), vp]
-        L.xs_plan_last_stats.restype = i32
-        L.xs_plan_last_stats.argtypes = [vp, ctypes.POINTER(i64)]
-        L.xs_plan_last_scan_ms.restype = i32
-        L.xs_plan_last_scan_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_float)]
-        L.xs_plan_debug_counters.restype = i32
-        L.xs_plan_debug_counters.argtypes = [vp, ctypes.POINTER(ctypes.c_uint64)]
+        L.xs_timer_create.restype = i32
+        L.xs_timer_create.argtypes = [ctypes.POINTER(vp)]
+        L.xs_timer_destroy.restype = None
+        L.xs_timer_destroy.argtypes = [vp]
+        L.xs_timer_elapsed_ms.restype = i32
+        L.xs_timer_elapsed_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_float)]
         L.xs_detrend.restype = i32
         L.xs_detrend.argtypes = [vp, vp, i64, i64, i32, vp, vp]
         L.xs_dsig.restype = i32
@@ -168,7 +175,7 @@ def load():
         L.xs_local_gradients_workspace_bytes.argtypes = [i64, i64]
         L.xs_local_gradients.restype = i32
         L.xs_local_gradients.argtypes = [vp, i64, i64, i32, vp, vp, vp, vp, sz, vp]
-        if L.xs_abi_version() != 1:
+        if L.xs_abi_version() != ABI_VERSION:
             raise NativeError("libxsarsea_b200.so ABI version mismatch")
         _lib = L
         return L

@@ -4,12 +4,14 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <atomic>
+
 #include "../../include/xsarsea_b200.h"
 
 namespace xs {
 
 void set_error(const char *fmt, ...);
-extern int64_t g_launches;
+extern std::atomic<int64_t> g_launches;  // concurrent host threads launch through the same library
 
 inline int check(cudaError_t e, const char *what) {
     if (e != cudaSuccess) {

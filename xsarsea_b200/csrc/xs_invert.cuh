@@ -33,19 +33,23 @@ struct xs_plan {
                            // non-decreasing in wspd (the exact interval search of k_cross applies)
     int inc_cr_sorted;
     int wspd_cr_sorted;    // wspd_cr_grid strictly ascending
-    // ---- counters of the last xs_invert (device) ----
-    unsigned long long *stats;  // [8]
     int device;
-    cudaEvent_t ev_scan0, ev_scan1;  // around the last k_scan_co launch
-    int scan_timed;
+    // nothing mutable lives here: counters, timers and workspaces belong to the xs_invert call (ABI 2), so one plan
+    // serves concurrent calls from several host threads / streams
+};
+
+struct xs_timer {
+    cudaEvent_t ev[3];  // before k_scan_co, after k_scan_co, after k_refine_co
+    int recorded;
 };
 
 namespace xs {
 
 constexpr int kChunkRows = 16;     // wspd rows per staged chunk = granularity of the argmin bookkeeping
 constexpr int kRowPad = 8;         // the scan image pads the wspd axis to a multiple of this (+inf rows)
-constexpr int kStages = 4;         // shared-memory ring depth
-constexpr int kMaxIncBins = 8192;  // bins that fit the shared-memory histograms
+constexpr int kStages = 3;         // shared-memory ring depth of the scan
+constexpr int kTilePad = 32;       // upper bound of the pixels per scan tile (the bin segments of the pixel list are padded to tiles)
+constexpr int kMaxIncBins = 6144;  // bins whose two shared-memory histograms (k_bin_scatter) fit the default 48 KB
 
 // raster element access: XS_F64 / XS_F32, promoted to double on load
 __device__ __forceinline__ double load_real(const void *p, int64_t i, int dtype) {
@@ -195,5 +199,170 @@ struct ArgMin {
     }
     __device__ __forceinline__ int result() const { return nan_idx != 0x7fffffff ? nan_idx : idx; }
 };
+
+
+typedef unsigned long long u64;
+
+// ---- packed FP32 helpers (sm_100 FADD2 / FFMA2 / FMNMX3) -------------------------------------------------
+__device__ __forceinline__ u64 pack2(float x, float y) {
+    u64 d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(x), "f"(y));
+    return d;
+}
+__device__ __forceinline__ void unpack2(u64 v, float &x, float &y) { asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(v)); }
+__device__ __forceinline__ u64 ffma2(u64 a, u64 b, u64 c) {
+    u64 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ u64 fadd2(u64 a, u64 b) {
+    u64 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ float fmin3(float a, float b, float c) {
+    float d;
+    asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+
+// g(phi) = a cos(phi) + b sin(phi) rounded to FP32; one definition so that the scan and the refinement that re-creates
+// the scan's FP32 costs use bit-identical values
+__device__ __forceinline__ float g32(double qa, double qb, double c, double s) {
+    return (float)__fma_rn(qa, c, __dmul_rn(qb, s));
+}
+
+// ---- mbarrier / bulk-async copy (TMA) ----------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// shared-memory arrival counter with acquire/release ordering inside the CTA
+__device__ __forceinline__ unsigned atom_add_acq_rel_shared(unsigned *p, unsigned v) {
+    unsigned old;
+    asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(smem_u32(p)), "r"(v) : "memory");
+    return old;
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---- per-call workspace ------------------------------------------------------------------------------------------
+// The pixels that take the co-pol inversion are counting-sorted by incidence bin; every bin's segment of the list is
+// padded to whole scan tiles (sentinel entries), so tile t is the list positions [t*tile_px, (t+1)*tile_px) and all of a
+// tile's pixels share one LUT slab.  k_list_prepare then orders runs of the list by sigma0 and materialises one PixRec
+// per list position (what the scan streams in with one bulk copy per tile); k_scan_co leaves one RefRec per scanned
+// pixel (the error band and the contending (lane, chunk) cells) for k_refine_co.
+struct __align__(16) PixRec {  // 32 B
+    double qa, qb, s;          // m_antenna, m_azi (|.| if phi_180), sigma0 in dB
+    unsigned px;               // raster index
+    unsigned short bin;
+    unsigned char state;       // 0: padding, 1: scan, 2: the slab holds NaN (answer = first NaN), 3: exhaustive FP64 needed
+    unsigned char neg;         // Im(ancillary) < 0 (direction sign, windspeed.py:234-242)
+};
+struct __align__(16) RefRec {  // 32 B
+    float thr, cs, nq;         // band threshold m32 + 2E, warp centre, k = -2 (s/dsig - cs): what re-creates the FP32 costs
+    unsigned cont, wide;       // lanes with exactly one / with several chunks inside the band (0, 0: exhaustive FP64 needed)
+    unsigned ch_lo, ch_hi;     // best-chunk indices of the first `cap` cont lanes (8 x 8 bit when n_chunks <= 256, else 4 x 16)
+    unsigned spare;
+};
+static_assert(sizeof(PixRec) == 32 && sizeof(RefRec) == 32, "record layout");
+
+// counters (u64): see XS_N_COUNTERS in the public header
+struct Workspace {
+    u64 *counters;         // [16]
+    unsigned *hist;        // [n_inc]
+    unsigned *bin_start;   // [n_inc + 1] padded list position of the bin's first entry
+    unsigned *cursor;      // [n_inc]
+    unsigned *tile_start;  // [n_inc + 1]
+    unsigned *list;        // [n_list] pixel indices grouped by bin, 0xffffffff = padding
+    unsigned *fallback;    // [n_px] pixels for the exhaustive kernel
+    PixRec *pix;           // [n_list]
+    RefRec *rec;           // [n_list]
+    int *idx_tmp;          // [n_px] co-pol argmin when the caller gave no idx_co and the outputs are speed/direction planes
+    int64_t n_list;        // n_px + kTilePad * n_inc rounded up to a sort run
+};
+size_t ws_layout(int n_inc, int64_t n_px, unsigned flags, char *base, Workspace *w);
+
+// ---- outputs ---------------------------------------------------------------------------------------------------------
+// complex128 per pixel (the reference's return type), or -- XS_FLAG_OUT_SPEED_DIR -- two planes [speed | direction] of
+// float64 / float32 (row F2: the abs / angle / dir_sample_to_meteo post-processing every caller applies, fused).
+struct OutSpec {
+    void *co, *cr;
+    int *idx_co, *idx_cr;
+    const void *gh;      // ground heading raster or NULL
+    double gh_scalar;
+    int64_t n_px;
+    unsigned flags;
+    int dtype;           // raster dtype (of gh)
+};
+
+// windspeed.py:231-247 from the flat argmin: w * (cos phi, +- sin phi); the reference picks +phi or -phi by comparing
+// |angle(anc/sol)| and |angle(anc/sol2)| (ties keep +phi); for phi in [0,180] that is Im(anc) >= 0.
+__device__ __forceinline__ double2 co_from_idx(const xs_plan &pl, int idx, bool anc_im_neg) {
+    const int iw = idx / pl.n_phi, ip = idx - iw * pl.n_phi;
+    const double w = pl.wspd_grid[iw];
+    double re = w * pl.cos_phi[ip], im = w * pl.sin_phi[ip];
+    if (pl.phi_180 && anc_im_neg) im = -im;
+    return make_double2(re, im);
+}
+
+// np.abs / np.angle(deg=True) / (90 - angle + ground_heading) % 360 (docs/examples/windspeed_retrieval_L1.ipynb cell 33,
+// detrend.py:114-130) of one result
+__device__ __forceinline__ void store_wind(const OutSpec &o, void *base, int64_t px, double2 z) {
+    if (!(o.flags & XS_FLAG_OUT_SPEED_DIR)) {
+        reinterpret_cast<double2 *>(base)[px] = z;
+        return;
+    }
+    const double spd = hypot(z.x, z.y);
+    double dir = atan2(z.y, z.x) * (180.0 / 3.14159265358979323846);  // np.angle(z, deg=True)
+    if (o.flags & XS_FLAG_DIR_METEO) {
+        const double gh = o.gh ? load_real(o.gh, px, o.dtype) : o.gh_scalar;
+        dir = __dadd_rn(__dsub_rn(90.0, dir), gh);  // dir_sample_to_meteo
+        double r = fmod(dir, 360.0);                // np.mod: the result takes the sign of the divisor
+        if (r != 0.0 && r < 0.0) r += 360.0;
+        dir = r;
+    }
+    if (o.flags & XS_FLAG_OUT_F32) {
+        float *f = reinterpret_cast<float *>(base);
+        f[px] = (float)spd;
+        f[o.n_px + px] = (float)dir;
+    } else {
+        double *d = reinterpret_cast<double *>(base);
+        d[px] = spd;
+        d[o.n_px + px] = dir;
+    }
+}
+
+// co-pol result of one pixel: complex output (the cross-pol pass reads it back) or, with plane outputs, only the index
+__device__ __forceinline__ void write_co(const xs_plan &pl, const OutSpec &o, int idx, bool anc_im_neg, int64_t px) {
+    if (o.idx_co) o.idx_co[px] = idx;
+    if (!(o.flags & XS_FLAG_OUT_SPEED_DIR)) reinterpret_cast<double2 *>(o.co)[px] = co_from_idx(pl, idx, anc_im_neg);
+}
+
+int launch_scan_pipeline(const xs_plan *pl, const RasterArgs &ra, const Workspace &ws, const OutSpec &out, int64_t n_px,
+                         xs_timer *timer, cudaStream_t st);
+int scan_tile_px(int kp);
 
 }  // namespace xs

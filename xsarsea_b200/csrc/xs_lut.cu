@@ -3,6 +3,7 @@
 // state shared by the library (error text, launch counter).
 #include <stdarg.h>
 
+#include <atomic>
 #include <vector>
 
 #include "xs_common.cuh"
@@ -10,7 +11,7 @@
 namespace xs {
 
 static thread_local char g_err[512] = "";
-int64_t g_launches = 0;
+std::atomic<int64_t> g_launches{0};
 
 void set_error(const char *fmt, ...) {
     va_list ap;
@@ -64,7 +65,7 @@ static int grid_for(int64_t n, int block) {
 
 extern "C" int xs_abi_version(void) { return XS_ABI_VERSION; }
 extern "C" const char *xs_last_error(void) { return xs::g_err; }
-extern "C" int64_t xs_launch_count(void) { return xs::g_launches; }
+extern "C" int64_t xs_launch_count(void) { return xs::g_launches.load(); }
 
 extern "C" int xs_lut_interp_axis(const double *src, int64_t outer, int n_src, int64_t inner, const double *x_src,
                                   const double *x_dst, int n_dst, double *dst, void *stream) {

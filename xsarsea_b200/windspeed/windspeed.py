@@ -9,6 +9,8 @@ GPU in row blocks on side streams so host<->device copies overlap the scan.
 from __future__ import annotations
 
 import logging
+import queue
+import threading
 import warnings
 from collections import OrderedDict
 
@@ -23,41 +25,47 @@ logger = logging.getLogger("xsarsea.windspeed")
 
 _PLAN_CACHE: "OrderedDict[tuple, dev.InversionPlan]" = OrderedDict()
 _PLAN_CACHE_MAX = 4
-BLOCK_PIXELS = 1 << 25  # pixels per streamed block (32 Mi px: 1.3 GB of f64 inputs, 1 GB of outputs)
+_PLAN_LOCK = threading.RLock()
+BLOCK_PIXELS = 1 << 24  # pixels per streamed block (16 Mi px: 0.67 GB of f64 inputs, 0.5 GB of outputs)
 
 
 def _get_plan(model_co, model_cr, dsig_co, kwargs):
-    """Device LUTs + scan image for a model pair (what windspeed.py:139-181 sets up on every call), cached."""
-    luts = []
-    for m in (model_co, model_cr):
-        luts.append(None if m is None else m.to_lut_device(units="dB", **kwargs))
-    key = (id(luts[0]), id(luts[1]), float(dsig_co))
-    plan = _PLAN_CACHE.get(key)
-    if plan is None:
-        co = cr = None
-        if luts[0] is not None:
-            l = luts[0]
-            if l.phi is None:
-                raise ValueError(f"model {model_co.name} has no phi dimension: not a co-pol model")
-            co = (l.data, l.inc, l.wspd, l.phi)
-        if luts[1] is not None:
-            l = luts[1]
-            if l.phi is not None:
-                raise ValueError(f"model {model_cr.name} has a phi dimension: not a cross-pol model")
-            cr = (l.data, l.inc, l.wspd)
-        plan = dev.InversionPlan(co=co, cr=cr, dsig_co=dsig_co)
-        plan._luts = luts  # keep the cached DeviceLut objects (and their ids) alive with the plan
-        _PLAN_CACHE[key] = plan
-        while len(_PLAN_CACHE) > _PLAN_CACHE_MAX:
-            _PLAN_CACHE.popitem(last=False)[1].close()
-    else:
-        _PLAN_CACHE.move_to_end(key)
-    return plan
+    """Device LUTs + scan image for a model pair (what windspeed.py:139-181 sets up on every call), cached.
+
+    Thread-safe: LUT building, plan creation and cache eviction happen under one lock; an evicted plan is only dropped
+    from the cache -- it is destroyed when the last caller still holding it lets go (`InversionPlan.__del__`/`close`
+    defer while calls are in flight), so eviction can never pull a plan from under a running inversion."""
+    with _PLAN_LOCK:
+        luts = []
+        for m in (model_co, model_cr):
+            luts.append(None if m is None else m.to_lut_device(units="dB", **kwargs))
+        key = (id(luts[0]), id(luts[1]), float(dsig_co))
+        plan = _PLAN_CACHE.get(key)
+        if plan is None:
+            co = cr = None
+            if luts[0] is not None:
+                l = luts[0]
+                if l.phi is None:
+                    raise ValueError(f"model {model_co.name} has no phi dimension: not a co-pol model")
+                co = (l.data, l.inc, l.wspd, l.phi)
+            if luts[1] is not None:
+                l = luts[1]
+                if l.phi is not None:
+                    raise ValueError(f"model {model_cr.name} has a phi dimension: not a cross-pol model")
+                cr = (l.data, l.inc, l.wspd)
+            plan = dev.InversionPlan(co=co, cr=cr, dsig_co=dsig_co)  # synchronises the stream the LUTs were built on
+            plan._luts = luts  # keep the cached DeviceLut objects (and their ids) alive with the plan
+            _PLAN_CACHE[key] = plan
+            while len(_PLAN_CACHE) > _PLAN_CACHE_MAX:
+                _PLAN_CACHE.popitem(last=False)  # dropped, not closed: users still holding it keep it alive
+        else:
+            _PLAN_CACHE.move_to_end(key)
+        return plan
 
 
 def clear_plan_cache():
-    while _PLAN_CACHE:
-        _PLAN_CACHE.popitem()[1].close()
+    with _PLAN_LOCK:
+        _PLAN_CACHE.clear()
 
 
 def _is_tensor(x):
@@ -75,12 +83,16 @@ def _values(x):
     return np.asarray(x.data if _xr.is_labelled(x) else x)
 
 
-def _run_resident(plan, inc, s_co, s_cr, dsig_cr, anc, *, merge_dual, cr_abs):
+def _run_resident(plan, inc, s_co, s_cr, dsig_cr, anc, *, merge_dual, cr_abs, speed_dir=False, ground_heading=None,
+                  out_f32=False):
     """Device-resident variant of `_run_device`: torch CUDA tensors in, torch CUDA tensors out, one `xs_invert` on the
     current stream, no host copies (an extension of the reference's container rule "output mirrors input",
-    windspeed.py:333-388, to device arrays)."""
+    windspeed.py:333-388, to device arrays).  float32 arithmetic inputs are used as such only when every raster is
+    float32 / complex64; a mix is promoted to float64 / complex128 (like the host path and numpy's own promotion)."""
     torch = nat.torch_cuda()
-    f32 = inc.dtype == torch.float32
+    given = [x for x in (inc, s_co, s_cr, anc, ground_heading) + (() if np.isscalar(dsig_cr) else (dsig_cr,))
+             if x is not None and hasattr(x, "dtype")]
+    f32 = all(str(x.dtype).split(".")[-1] in ("float32", "complex64") for x in given)
     rdt, cdt = (torch.float32, torch.complex64) if f32 else (torch.float64, torch.complex128)
 
     def prep(x, dt):
@@ -90,79 +102,186 @@ def _run_resident(plan, inc, s_co, s_cr, dsig_cr, anc, *, merge_dual, cr_abs):
         return x.to(device=inc.device, dtype=dt).expand(inc.shape).contiguous()
 
     dsig = dsig_cr if np.isscalar(dsig_cr) else prep(dsig_cr, rdt)
-    oc, ox, _, _ = plan.invert(inc.contiguous(), prep(s_co, rdt), prep(s_cr, rdt), dsig, prep(anc, cdt), sigma0_db=False,
-                               merge_dual=merge_dual, cr_abs=cr_abs)
+    gh = ground_heading if (ground_heading is None or np.isscalar(ground_heading)) else prep(ground_heading, rdt)
+    oc, ox, _, _ = plan.invert(prep(inc, rdt), prep(s_co, rdt), prep(s_cr, rdt), dsig, prep(anc, cdt), sigma0_db=False,
+                               merge_dual=merge_dual, cr_abs=cr_abs, speed_dir=speed_dir, ground_heading=gh, out_f32=out_f32)
     return oc, ox
 
 
+class _PinnedPool:
+    """Block-sized pinned staging buffers, reused across calls (and handed out per call, so concurrent calls never
+    share one).  Only these are page-locked: inputs are read from, and results delivered into, ordinary pageable numpy
+    arrays, so repeated calls on differently sized scenes do not accumulate locked RAM."""
+
+    def __init__(self, keep=12):
+        self._free, self._lock, self._keep = {}, threading.Lock(), keep
+
+    def take(self, nbytes):
+        torch = nat.torch_cuda()
+        with self._lock:
+            lst = self._free.get(nbytes)
+            if lst:
+                return lst.pop()
+        return torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+
+    def give(self, buf):
+        with self._lock:
+            lst = self._free.setdefault(buf.numel(), [])
+            if sum(len(v) for v in self._free.values()) < self._keep:
+                lst.append(buf)
+
+
+_POOL = _PinnedPool()
+
+
 def _run_device(plan, inc, s_co, s_cr, dsig_cr, anc, *, sigma0_db, merge_dual, cr_abs, mode=nat.MODE_FAST,
-                need_co=False):
-    """Host arrays in, host arrays out.  Streams row blocks: H2D on one side stream, xs_invert on the current
-    stream, D2H on another side stream; two device slots so block k+1 uploads while block k is scanned."""
+                need_co=False, speed_dir=False, ground_heading=None, out_f32=False):
+    """Host arrays in, host arrays out.  Row blocks are streamed: H2D on one side stream, xs_invert on the current
+    stream, D2H on another side stream, two device slots so block k+1 uploads while block k is scanned.  Host memory that
+    is not page-locked is staged through block-sized pinned buffers (inputs by this thread, results by a helper thread
+    that copies each finished block into the pageable output while the GPU works on the next ones)."""
     torch = nat.torch_cuda()
     shape = inc.shape
-    f32 = all(a is None or a.dtype in (np.float32, np.complex64) for a in (inc, s_co, s_cr, anc)) and (
+    rasters = (inc, s_co, s_cr, anc, ground_heading if isinstance(ground_heading, np.ndarray) else None)
+    f32 = all(a is None or a.dtype in (np.float32, np.complex64) for a in rasters) and (
         not isinstance(dsig_cr, np.ndarray) or dsig_cr.dtype == np.float32)
     rdt, cdt = (np.float32, np.complex64) if f32 else (np.float64, np.complex128)
 
     def flat(a, dt):
         return None if a is None else np.ascontiguousarray(np.broadcast_to(a, shape), dtype=dt).reshape(-1)
 
-    h_inc, h_co, h_cr, h_anc = flat(inc, rdt), flat(s_co, rdt), flat(s_cr, rdt), flat(anc, cdt)
     h_dsig = flat(dsig_cr, rdt) if isinstance(dsig_cr, np.ndarray) and dsig_cr.ndim > 0 else None
+    h_gh = flat(ground_heading, rdt) if isinstance(ground_heading, np.ndarray) and ground_heading.ndim > 0 else None
+    gh_scalar = None if (ground_heading is None or h_gh is not None) else float(ground_heading)
+    h_in = [flat(inc, rdt), flat(s_co, rdt), flat(s_cr, rdt), h_dsig, flat(anc, cdt), h_gh]
     dsig_scalar = 0.1 if h_dsig is not None else float(dsig_cr)
-    n = h_inc.size
-    want_co = plan.co_grids is not None and h_co is not None
-    out_co = torch.empty(n, dtype=torch.complex128, pin_memory=True) if (want_co or need_co) else None
-    out_cr = torch.empty(n, dtype=torch.float64 if cr_abs else torch.complex128, pin_memory=True)
+    n = h_in[0].size
+    want_co = plan.co_grids is not None and h_in[1] is not None
+    pdt = np.float32 if out_f32 else np.float64
+    wind_shape, wind_dt = ((2, n), pdt) if speed_dir else ((n,), np.complex128)
+    out_co = np.empty(wind_shape, dtype=wind_dt) if (want_co or need_co) else None
+    out_cr = np.empty((n,), dtype=np.float64) if cr_abs else np.empty(wind_shape, dtype=wind_dt)
+
+    def finish(o):
+        return None if o is None else o.reshape(((2,) if o.ndim == 2 else ()) + tuple(shape))
+
     if n == 0:
-        return (None if out_co is None else out_co.numpy().reshape(shape)), out_cr.numpy().reshape(shape)
+        return finish(out_co), finish(out_cr)
 
     blk = min(n, BLOCK_PIXELS)
     nslots = 1 if n <= blk else 2
-    trdt, tcdt = (torch.float32, torch.complex64) if f32 else (torch.float64, torch.complex128)
-
-    def dbuf(h, dt):
-        return None if h is None else [torch.empty(blk, dtype=dt, device="cuda") for _ in range(nslots)]
-
-    d_inc, d_co, d_cr, d_dsig, d_anc = dbuf(h_inc, trdt), dbuf(h_co, trdt), dbuf(h_cr, trdt), dbuf(h_dsig, trdt), dbuf(h_anc, tcdt)
-    d_oco = None if out_co is None else [torch.empty(blk, dtype=torch.complex128, device="cuda") for _ in range(nslots)]
-    d_ocr = [torch.empty(blk, dtype=out_cr.dtype, device="cuda") for _ in range(nslots)]
+    t_of = {np.dtype(np.float32): torch.float32, np.dtype(np.float64): torch.float64,
+            np.dtype(np.complex64): torch.complex64, np.dtype(np.complex128): torch.complex128}
     cur = torch.cuda.current_stream()
     s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
-    ev_scan = [None] * nslots   # scan of the block that last used the slot's inputs
-    ev_d2h = [None] * nslots    # download of the block that last used the slot's outputs
-    for k, lo in enumerate(range(0, n, blk)):
-        hi = min(lo + blk, n)
-        m = hi - lo
-        slot = k % nslots
-        with torch.cuda.stream(s_in):
-            if ev_scan[slot] is not None:
-                s_in.wait_event(ev_scan[slot])
-            for d, h in ((d_inc, h_inc), (d_co, h_co), (d_cr, h_cr), (d_dsig, h_dsig), (d_anc, h_anc)):
-                if d is not None:
-                    d[slot][:m].copy_(torch.from_numpy(h[lo:hi]), non_blocking=True)
-            ev_in = torch.cuda.Event()
-            ev_in.record(s_in)
-        cur.wait_event(ev_in)
-        if ev_d2h[slot] is not None:
-            cur.wait_event(ev_d2h[slot])
-        sl = lambda d: None if d is None else d[slot][:m]
-        plan.invert(sl(d_inc), sl(d_co), sl(d_cr), sl(d_dsig) if d_dsig is not None else dsig_scalar, sl(d_anc),
-                    sigma0_db=sigma0_db, merge_dual=merge_dual, cr_abs=cr_abs, mode=mode,
-                    out_co=sl(d_oco), out_cr=sl(d_ocr))
-        ev_scan[slot] = torch.cuda.Event()
-        ev_scan[slot].record(cur)
-        with torch.cuda.stream(s_out):
-            s_out.wait_event(ev_scan[slot])
-            if out_co is not None:
-                out_co[lo:hi].copy_(d_oco[slot][:m], non_blocking=True)
-            out_cr[lo:hi].copy_(d_ocr[slot][:m], non_blocking=True)
-            ev_d2h[slot] = torch.cuda.Event()
-            ev_d2h[slot].record(s_out)
-    s_out.synchronize()
-    cur.synchronize()
-    return (None if out_co is None else out_co.numpy().reshape(shape)), out_cr.numpy().reshape(shape)
+    # the device slots come from the caching allocator of `cur`: order the side streams behind whatever `cur` still has
+    # in flight on recycled blocks (they are all idle again when this function returns: it ends with full synchronisation)
+    s_in.wait_stream(cur)
+    s_out.wait_stream(cur)
+    d_in = [None if h is None else [torch.empty(blk, dtype=t_of[h.dtype], device="cuda") for _ in range(nslots)] for h in h_in]
+    d_oco = None if out_co is None else [torch.empty(wind_shape[:-1] + (blk,), dtype=t_of[np.dtype(wind_dt)], device="cuda")
+                                         for _ in range(nslots)]
+    d_ocr = [torch.empty(((blk,) if cr_abs else wind_shape[:-1] + (blk,)), dtype=t_of[out_cr.dtype], device="cuda")
+             for _ in range(nslots)]
+    # pinned staging: inputs that are not page-locked already, and both outputs
+    taken = []
+
+    def pinned(nelem, np_dt):
+        buf = _POOL.take(int(nelem) * np.dtype(np_dt).itemsize)
+        taken.append(buf)
+        return buf.numpy().view(np_dt)
+
+    in_stage = [None if (h is None or torch.from_numpy(h).is_pinned()) else [pinned(blk, h.dtype) for _ in range(nslots)]
+                for h in h_in]
+    oco_stage = None if out_co is None else [pinned(out_co.size // n * blk, out_co.dtype).reshape(wind_shape[:-1] + (blk,))
+                                             for _ in range(nslots)]
+    ocr_stage = [pinned(out_cr.size // n * blk, out_cr.dtype).reshape(out_cr.shape[:-1] + (blk,)) for _ in range(nslots)]
+
+    def front(bufs, slot, m):
+        """Contiguous view of the first m pixels' worth of a slot buffer: [m] or -- planes -- [2][m]."""
+        if bufs is None:
+            return None
+        b = bufs[slot]
+        return b[:m] if b.ndim == 1 else b.reshape(-1)[:2 * m].reshape(2, m)
+
+    ev_h2d = [None] * nslots    # upload of the block that last used the slot's input staging
+    ev_scan = [None] * nslots   # scan of the block that last used the slot's device inputs
+    slot_free = [threading.Semaphore(1) for _ in range(nslots)]  # output staging of the slot has been drained
+    jobs: "queue.Queue" = queue.Queue()
+    errors = []
+
+    def drain():
+        while True:
+            job = jobs.get()
+            if job is None:
+                return
+            ev, slot, lo, hi = job
+            try:
+                ev.synchronize()
+                if out_co is not None:
+                    out_co[..., lo:hi] = front(oco_stage, slot, hi - lo)
+                out_cr[..., lo:hi] = front(ocr_stage, slot, hi - lo)
+            except Exception as e:  # pragma: no cover
+                errors.append(e)
+            finally:
+                slot_free[slot].release()
+
+    worker = threading.Thread(target=drain, name="xs-d2h", daemon=True)
+    worker.start()
+    try:
+        for k, lo in enumerate(range(0, n, blk)):
+            hi = min(lo + blk, n)
+            m = hi - lo
+            slot = k % nslots
+            if ev_h2d[slot] is not None:
+                ev_h2d[slot].synchronize()  # the slot's input staging is read by the previous upload until then
+            srcs = []
+            for h, st in zip(h_in, in_stage):
+                if h is None:
+                    srcs.append(None)
+                elif st is None:
+                    srcs.append(torch.from_numpy(h[lo:hi]))
+                else:
+                    np.copyto(st[slot][:m], h[lo:hi])
+                    srcs.append(torch.from_numpy(st[slot][:m]))
+            with torch.cuda.stream(s_in):
+                if ev_scan[slot] is not None:
+                    s_in.wait_event(ev_scan[slot])
+                for d, src in zip(d_in, srcs):
+                    if d is not None:
+                        d[slot][:m].copy_(src, non_blocking=True)
+                ev_in = torch.cuda.Event()
+                ev_in.record(s_in)
+            ev_h2d[slot] = ev_in
+            cur.wait_event(ev_in)
+            slot_free[slot].acquire()  # results of the block that last used the slot are on the host
+            sl = lambda d: None if d is None else d[slot][:m]
+            o_co, o_cr = front(d_oco, slot, m), front(d_ocr, slot, m)
+            plan.invert(sl(d_in[0]), sl(d_in[1]), sl(d_in[2]), sl(d_in[3]) if d_in[3] is not None else dsig_scalar,
+                        sl(d_in[4]), sigma0_db=sigma0_db, merge_dual=merge_dual, cr_abs=cr_abs, mode=mode,
+                        out_co=o_co, out_cr=o_cr, speed_dir=speed_dir, out_f32=out_f32,
+                        ground_heading=sl(d_in[5]) if d_in[5] is not None else gh_scalar)
+            ev_scan[slot] = torch.cuda.Event()
+            ev_scan[slot].record(cur)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(ev_scan[slot])
+                if out_co is not None:
+                    torch.from_numpy(front(oco_stage, slot, m)).copy_(o_co, non_blocking=True)
+                torch.from_numpy(front(ocr_stage, slot, m)).copy_(o_cr, non_blocking=True)
+                ev_out = torch.cuda.Event()
+                ev_out.record(s_out)
+            jobs.put((ev_out, slot, lo, hi))
+    finally:
+        jobs.put(None)
+        worker.join()
+        s_in.synchronize()
+        s_out.synchronize()
+        cur.synchronize()
+        for buf in taken:
+            _POOL.give(buf)
+    if errors:
+        raise errors[0]
+    return finish(out_co), finish(out_cr)
 
 
 def _invert_from_model_numpy(models, dsig_co, kwargs, np_inc, np_sigma0_co_db, np_sigma0_cr_db, np_dsig_cr,
@@ -203,6 +322,31 @@ def invert_from_model(inc, sigma0, sigma0_dual=None, /, ancillary_wind=None, dsi
     co-pol only: complex128 wind (abs = m/s, angle = direction, antenna convention); cross-pol only: float64 wind
     speed; dual-pol: tuple (wind_co, wind_dual) with wind_dual merged as in windspeed.py:426-428.
     """
+    return _invert(inc, sigma0, sigma0_dual, ancillary_wind, dsig_co, dsig_cr, model, kwargs)
+
+
+def invert_to_speed_dir(inc, sigma0, sigma0_dual=None, /, ancillary_wind=None, dsig_co=0.1, dsig_cr=0.1, model=None,
+                        ground_heading=None, dtype=np.float64, **kwargs):
+    """`invert_from_model` with the post-processing every caller applies to its result fused into the inversion
+    kernels (docs/examples/windspeed_retrieval_L1.ipynb cell 33, detrend.py:114-130):
+
+        windspeed = np.abs(wind)
+        winddir   = np.angle(wind, deg=True)                          # ground_heading is None: antenna convention
+        winddir   = (90 - np.angle(wind, deg=True) + ground_heading) % 360   # meteorological convention otherwise
+
+    The device writes speed / direction planes (float64, or float32 with dtype=np.float32) instead of complex128, which
+    halves (quarters) the device->host copy.  Same arguments as `invert_from_model` plus `ground_heading` (degrees;
+    scalar or raster) and `dtype`.  Returns (windspeed, winddir) for a co-pol model, the wind speed for a cross-pol
+    model (as `invert_from_model`), ((windspeed_co, winddir_co), (windspeed_dual, winddir_dual)) for dual-pol.
+    """
+    if np.dtype(dtype) not in (np.dtype(np.float32), np.dtype(np.float64)):
+        raise ValueError("dtype must be float32 or float64")
+    return _invert(inc, sigma0, sigma0_dual, ancillary_wind, dsig_co, dsig_cr, model, kwargs, speed_dir=True,
+                   ground_heading=ground_heading, out_f32=np.dtype(dtype) == np.dtype(np.float32))
+
+
+def _invert(inc, sigma0, sigma0_dual, ancillary_wind, dsig_co, dsig_cr, model, kwargs, speed_dir=False,
+            ground_heading=None, out_f32=False):
     models = model if isinstance(model, tuple) else (model, None)
     models = tuple(get_model(m) if m is not None else None for m in models)
     anc_given = ancillary_wind is not None
@@ -233,6 +377,7 @@ def invert_from_model(inc, sigma0, sigma0_dual=None, /, ancillary_wind=None, dsi
     template = sigma0_co if sigma0_co is not None else sigma0_cr
     dual = sigma0_dual is not None
     cross_only = sigma0_co is None
+    epi = dict(speed_dir=speed_dir, ground_heading=ground_heading, out_f32=out_f32)
 
     if any(_xr.is_dask(v) for v in (inc, sigma0_co, sigma0_cr, ancillary_wind, dsig_cr) if v is not None):
         ws_co, ws_cr_or_dual = _invert_dask(models, dsig_co, kwargs, inc, sigma0_co, sigma0_cr, dsig_cr, ancillary_wind,
@@ -243,38 +388,57 @@ def invert_from_model(inc, sigma0, sigma0_dual=None, /, ancillary_wind=None, dsi
             import xarray as xr
 
             ws_cr_or_dual = xr.where((abs(ws_co) < 5) | (abs(ws_cr_or_dual) < 5), ws_co, ws_cr_or_dual)
+        if speed_dir:  # lazy containers: the callers' own expressions, evaluated block-wise by dask
+            def planes(z):
+                ang = np.angle(z, deg=True)
+                d = ang if ground_heading is None else (90 - ang + ground_heading) % 360
+                sp = abs(z)
+                return (sp.astype(np.float32), d.astype(np.float32)) if out_f32 else (sp, d)
+
+            ws_co = None if cross_only else planes(ws_co)
+            ws_cr_or_dual = ws_cr_or_dual if cross_only else planes(ws_cr_or_dual)
     elif _is_tensor(inc):
         plan = _get_plan(models[0], models[1] if sigma0_cr is not None else None, dsig_co, kwargs)
         ws_co, ws_cr_or_dual = _run_resident(plan, inc, sigma0_co, sigma0_cr, dsig_cr, ancillary_wind if anc_given else None,
-                                             merge_dual=dual, cr_abs=cross_only)
+                                             merge_dual=dual, cr_abs=cross_only, **epi)
+        if speed_dir:
+            ws_co = None if ws_co is None else (ws_co[0], ws_co[1])
+            ws_cr_or_dual = ws_cr_or_dual if cross_only else (ws_cr_or_dual[0], ws_cr_or_dual[1])
     else:
         plan = _get_plan(models[0], models[1] if sigma0_cr is not None else None, dsig_co, kwargs)
         dsig_in = dsig_cr if np.isscalar(dsig_cr) else _values(dsig_cr)
+        gh_in = ground_heading if (ground_heading is None or np.isscalar(ground_heading)) else _values(ground_heading)
+        epi["ground_heading"] = gh_in
         oc, ox = _run_device(plan, _values(inc), _values(sigma0_co), _values(sigma0_cr), dsig_in,
                              _values(ancillary_wind) if anc_given else None, sigma0_db=False, merge_dual=dual,
-                             cr_abs=cross_only)
-        if _xr.is_labelled(template):
-            ws_co = None if oc is None else _xr.like(template, oc, name="windspeed_gmf")
-            ws_cr_or_dual = _xr.like(template, ox, name="windspeed_gmf")
+                             cr_abs=cross_only, **epi)
+        lab = _xr.is_labelled(template)
+        wrap = (lambda a, name: _xr.like(template, a, name=name)) if lab else (lambda a, name: a)
+        if speed_dir:
+            ws_co = None if oc is None else (wrap(oc[0], "windspeed"), wrap(oc[1], "winddir"))
+            ws_cr_or_dual = wrap(ox, "windspeed") if cross_only else (wrap(ox[0], "windspeed"), wrap(ox[1], "winddir"))
         else:
-            ws_co, ws_cr_or_dual = oc, ox
+            ws_co = None if oc is None else wrap(oc, "windspeed_gmf")
+            ws_cr_or_dual = wrap(ox, "windspeed_gmf")
 
     # attrs and returns, windspeed.py:395-439
-    if models[0] is not None and models[0].iscopol and hasattr(ws_co, "attrs"):
-        ws_co.attrs["comment"] = f"wind speed and direction inverted from model {models[0].name} ({models[0].pol})"
-        ws_co.attrs["model"] = models[0].name
+    def set_attrs(obj, **attrs):
+        for o in (obj if isinstance(obj, tuple) else (obj,)):
+            if hasattr(o, "attrs"):
+                o.attrs.update(attrs)
+
+    if models[0] is not None and models[0].iscopol:
+        set_attrs(ws_co, comment=f"wind speed and direction inverted from model {models[0].name} ({models[0].pol})",
+                  model=models[0].name)
     if not dual:
         if not cross_only:
             return ws_co
-        if hasattr(ws_cr_or_dual, "attrs"):
-            ws_cr_or_dual.attrs["comment"] = f"wind speed inverted from model {models[1].name} ({models[1].pol})"
-            ws_cr_or_dual.attrs["model"] = models[1].name
-            ws_cr_or_dual.attrs["units"] = "m/s"
+        set_attrs(ws_cr_or_dual, comment=f"wind speed inverted from model {models[1].name} ({models[1].pol})",
+                  model=models[1].name, units="m/s")
         return ws_cr_or_dual
-    if hasattr(ws_cr_or_dual, "attrs"):
-        ws_cr_or_dual.attrs["comment"] = (f"wind speed and direction inverted from model {models[0].name} "
-                                          f"({models[0].pol}) and {models[1].name} ({models[1].pol})")
-        ws_cr_or_dual.attrs["model"] = f"{models[0].name} {models[1].name}"
+    set_attrs(ws_cr_or_dual, comment=(f"wind speed and direction inverted from model {models[0].name} "
+                                      f"({models[0].pol}) and {models[1].name} ({models[1].pol})"),
+              model=f"{models[0].name} {models[1].name}")
     return ws_co, ws_cr_or_dual
 
 
