@@ -38,6 +38,7 @@ size_t ws_layout(int n_inc, int64_t n_px, unsigned flags, char *base, Workspace 
     char *fb = take(sizeof(unsigned) * (size_t)(n_inc > 0 ? n_px : 0));
     char *pr = take(sizeof(PixRec) * (size_t)n_list);
     char *rr = take(sizeof(RefRec) * (size_t)n_list);
+    char *hd = take(sizeof(unsigned) * (size_t)n_list);
     char *it = take((flags & XS_FLAG_OUT_SPEED_DIR) ? sizeof(int) * (size_t)n_px : 0);
     if (w) {
         w->counters = (u64 *)c;
@@ -49,6 +50,7 @@ size_t ws_layout(int n_inc, int64_t n_px, unsigned flags, char *base, Workspace 
         w->fallback = (unsigned *)fb;
         w->pix = (PixRec *)pr;
         w->rec = (RefRec *)rr;
+        w->hard = (unsigned *)hd;
         w->idx_tmp = (int *)it;
         w->n_list = n_list;
     }
@@ -616,7 +618,7 @@ extern "C" int xs_plan_create(const xs_plan_desc *d, void *stream, xs_plan **out
         pl->n_wspd_pad = (d->n_wspd + kRowPad - 1) / kRowPad * kRowPad;
         // the scan's ring streams kStages chunks ahead, at most into the next tile: a slab needs at least kStages chunks
         pl->fast_ok = kp_ok && std::isfinite(d->dsig_co) && d->dsig_co != 0.0 && std::isfinite(wmax) &&
-                      d->n_inc <= kMaxIncBins && pl->n_wspd_pad <= 16384 && pl->n_wspd_pad > (kStages - 1) * kChunkRows;
+                      d->n_inc <= kMaxIncBins && pl->n_wspd_pad <= 256 * kChunkRows && pl->n_wspd_pad > (kStages - 1) * kChunkRows;
         if (pl->fast_ok) {
             const size_t n_scan = (size_t)d->n_inc * pl->n_wspd_pad * pl->nph_pad;
             if ((rc = xs::check(cudaMalloc(&pl->scan, sizeof(float) * n_scan), "cudaMalloc scan image")) != XS_OK) return fail(rc);

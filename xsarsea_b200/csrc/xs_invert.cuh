@@ -284,7 +284,7 @@ struct __align__(16) PixRec {  // 32 B
 struct __align__(16) RefRec {  // 32 B
     float thr, cs, nq;         // band threshold m32 + 2E, warp centre, k = -2 (s/dsig - cs): what re-creates the FP32 costs
     unsigned cont, wide;       // lanes with exactly one / with several chunks inside the band (0, 0: exhaustive FP64 needed)
-    unsigned ch_lo, ch_hi;     // best-chunk indices of the first `cap` cont lanes (8 x 8 bit when n_chunks <= 256, else 4 x 16)
+    unsigned ch_lo, ch_hi;     // best-chunk indices of the cont lanes, 8 bits each in lane order (at most 8 cont lanes)
     unsigned spare;
 };
 static_assert(sizeof(PixRec) == 32 && sizeof(RefRec) == 32, "record layout");
@@ -300,6 +300,7 @@ struct Workspace {
     unsigned *fallback;    // [n_px] pixels for the exhaustive kernel
     PixRec *pix;           // [n_list]
     RefRec *rec;           // [n_list]
+    unsigned *hard;        // [n_list] list positions k_refine_easy leaves to k_refine_co (counters[12])
     int *idx_tmp;          // [n_px] co-pol argmin when the caller gave no idx_co and the outputs are speed/direction planes
     int64_t n_list;        // n_px + kTilePad * n_inc rounded up to a sort run
 };

@@ -23,6 +23,7 @@
 //   k_refine_co     a warp per pixel: re-creates the FP32 costs (bit-identical operations) of the (lane, chunk) cells
 //                   inside the band; a single member settles the pixel, several are evaluated in FP64 with the reference's
 //                   operation order and reduced by a warp-shuffle lexicographic (J, index) argmin = numpy's first minimum.
+#include <stdio.h>
 #include <stdlib.h>
 
 #include "xs_invert.cuh"
@@ -230,12 +231,11 @@ __global__ void __launch_bounds__(NW * 32, MB) k_scan_co(xs_plan pl, Workspace w
             }
         }
         float m[P], best[P], second[P];
-        int bchunk[P];
+        unsigned bch[(P + 3) / 4];  // index of the best chunk, one byte per pixel (n_chunks <= 256)
 #pragma unroll
-        for (int p = 0; p < P; ++p) {
-            m[p] = best[p] = second[p] = CUDART_INF_F;
-            bchunk[p] = 0;
-        }
+        for (int p = 0; p < P; ++p) m[p] = best[p] = second[p] = CUDART_INF_F;
+#pragma unroll
+        for (int w = 0; w < (P + 3) / 4; ++w) bch[w] = 0u;
         const u64 ncs2 = pack2(-cs, -cs);
 
         // ---- the slab, 16 wspd rows at a time ----
@@ -295,7 +295,8 @@ __global__ void __launch_bounds__(NW * 32, MB) k_scan_co(xs_plan pl, Workspace w
                 const bool lt = m[p] < best[p];
                 second[p] = fminf(second[p], fmaxf(best[p], m[p]));
                 best[p] = fminf(best[p], m[p]);
-                bchunk[p] = lt ? c : bchunk[p];
+                constexpr unsigned kSel[4] = {0x3214u, 0x3240u, 0x3410u, 0x4210u};  // byte p & 3 <- c
+                bch[p >> 2] = lt ? __byte_perm(bch[p >> 2], (unsigned)c, kSel[p & 3]) : bch[p >> 2];
                 m[p] = CUDART_INF_F;
             }
             if (++stage == NS) {
@@ -311,7 +312,7 @@ __global__ void __launch_bounds__(NW * 32, MB) k_scan_co(xs_plan pl, Workspace w
         // lies in S = {c : J''_fp32(c) <= m32 + 2E}; k_refine_co collects S from the cells recorded here.
         const float lmax = pl.slab_absmax[bin];
         const float W = (float)pl.w_absmax * 1.0000002f;
-        const int cap = n_chunks <= 256 ? 8 : 4, bits = n_chunks <= 256 ? 8 : 16;
+        constexpr int cap = 8, bits = 8;  // a record holds the best-chunk index of 8 lanes
 #pragma unroll
         for (int p = 0; p < P; ++p) {
             if (mine[p].state != 1) continue;  // warp-uniform
@@ -341,7 +342,8 @@ __global__ void __launch_bounds__(NW * 32, MB) k_scan_co(xs_plan pl, Workspace w
             const unsigned over = __ballot_sync(0xffffffffu, mine_c && rank >= cap);
             cont &= ~over;
             wide |= over;
-            const u64 idv = (mine_c && rank < cap) ? ((u64)(unsigned)bchunk[p] << (bits * rank)) : 0ull;
+            const unsigned bchunk = (bch[p >> 2] >> (8 * (p & 3))) & 0xffu;
+            const u64 idv = (mine_c && rank < cap) ? ((u64)bchunk << (bits * rank)) : 0ull;
             const unsigned ch_lo = __reduce_or_sync(0xffffffffu, (unsigned)idv);
             const unsigned ch_hi = __reduce_or_sync(0xffffffffu, (unsigned)(idv >> 32));
             if (lane == 0) {
@@ -361,67 +363,184 @@ __global__ void __launch_bounds__(NW * 32, MB) k_scan_co(xs_plan pl, Workspace w
 }
 
 // ---- exact refinement ---------------------------------------------------------------------------------------------------
-// One warp settles RP consecutive list positions per iteration; the work is organised in phases across the RP pixels
-// (records -> membership of the first cell of every pixel -> counts and the rare further cells -> FP64) so that their
-// dependent loads overlap.
-template <int KP, int RP>
-__global__ void __launch_bounds__(256, 3) k_refine_co(xs_plan pl, Workspace ws, OutSpec out, int tile_px) {
-    const int lane = threadIdx.x & 31;
+// FP32 cost of candidate k of cell (lane L, rows row0...) of a pixel, exactly as the scan computed it; true if it is inside
+// the pixel's band.  flat = w * n_phi + phi index of the candidate.
+template <int KP>
+__device__ __forceinline__ bool band_member(const xs_plan &pl, const PixRec &px, const RefRec &rc, int L, int row0, int k,
+                                            int n_cand, int &flat) {
+    const int iw = row0 + k / (2 * KP);
+    const int slot = k % (2 * KP);
+    const int ip = 2 * (L + 32 * (slot >> 1)) + (slot & 1);
+    flat = iw * pl.n_phi + ip;
+    if (k >= n_cand || iw >= pl.n_wspd || ip >= pl.n_phi) return false;
+    const float2 rt = pl.rowtab[iw];
+    const float *slab32 = pl.scan + (size_t)px.bin * pl.n_wspd_pad * pl.nph_pad;
+    const float lc = __fadd_rn(slab32[(size_t)iw * pl.nph_pad + ip], -rc.cs);
+    const float mm = __fmaf_rn(lc, lc, rt.y);
+    const float aa = __fmaf_rn(rc.nq, lc, mm);
+    return __fmaf_rn(rt.x, g32(px.qa, px.qb, pl.cos_phi[ip], pl.sin_phi[ip]), aa) <= rc.thr;
+}
+
+// Pass 1: eight lanes per list position (four positions per warp at a time, so four times as many pixels are in flight
+// as with a warp per pixel -- this pass is bound by the latency of its dependent loads and by instruction issue, not by
+// arithmetic).  Settles padding, NaN slabs (answer = first NaN), pixels for the exhaustive kernel, and every pixel whose
+// band touches only "cont" cells (one 16-row chunk of one lane each, at most 8): lane `sub` of the group owns rows sub and
+// sub + 8 of a cell and all 2 KP phi slots, so g(phi) is evaluated once per slot; a single band member settles the pixel,
+// several are evaluated in FP64 with the reference's operation order and reduced to the lexicographic (J, flat index)
+// minimum = numpy's first minimum.  Pixels with "wide" lanes (several chunks of one lane in the band) go to pass 2.
+template <int KP>
+__global__ void __launch_bounds__(256, 3) k_refine_easy(xs_plan pl, Workspace ws, OutSpec out, int tile_px) {
+    const int lane = threadIdx.x & 31, sub = lane & 7, grp = lane >> 3;
+    const unsigned gmask = 0xffu << (8 * grp);
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int64_t n_pos = (int64_t)ws.counters[0] * tile_px;
+    static_assert(kChunkRows == 16, "two rows per lane of a group");
+    unsigned n_settled = 0, n_cells = 0, n_fp64 = 0;
+    for (int64_t e0 = warp * 4; e0 < n_pos; e0 += n_warps * 4) {
+        const int64_t e = e0 + grp;
+        if (e >= n_pos) continue;
+        const PixRec px = ws.pix[e];
+        const RefRec rc = ws.rec[e];  // loaded together with the pixel (only meaningful for state 1)
+        if (px.state == 0) continue;  // uniform within the group; no warp-wide synchronisation below
+        if (px.state != 1 || (rc.cont | rc.wide) == 0u) {
+            if (sub == 0) {
+                if (px.state == 2)
+                    write_co(pl, out, pl.first_nan[px.bin], px.neg, px.px);  // J is NaN exactly where L is NaN
+                else  // non-finite inputs, or the scan could not bound its error for this pixel
+                    ws.fallback[atomicAdd(&ws.counters[1], 1ull)] = px.px;
+            }
+            continue;
+        }
+        if (rc.wide != 0u) {
+            if (sub == 0) ws.hard[atomicAdd(&ws.counters[12], 1ull)] = (unsigned)e;
+            continue;
+        }
+        const float *slab32 = pl.scan + (size_t)px.bin * pl.n_wspd_pad * pl.nph_pad;
+        const double *slab64 = pl.co_lut + (size_t)px.bin * pl.n_wspd * pl.n_phi;
+        int n_loc = 0, one_loc = -1;
+        double bj = CUDART_INF;  // FP64 pass: lexicographic (J, flat index) minimum of this lane's members
+        int bi = 0x7fffffff;
+        // walk the cont cells: count the band members (exact == false) or evaluate them in FP64 (true)
+        auto walk = [&](bool exact) {
+            unsigned cells = rc.cont;
+            u64 ids = ((u64)rc.ch_hi << 32) | rc.ch_lo;
+#pragma unroll 1
+            while (cells) {  // uniform within the group
+                const int L = __ffs(cells) - 1;
+                cells &= cells - 1;
+                const int row0 = (int)(ids & 0xffu) * kChunkRows + sub;
+                ids >>= 8;
+                float gq[2 * KP];
+#pragma unroll
+                for (int sl = 0; sl < 2 * KP; ++sl) {
+                    const int ip = 2 * (L + 32 * (sl >> 1)) + (sl & 1);
+                    gq[sl] = ip < pl.n_phi ? g32(px.qa, px.qb, pl.cos_phi[ip], pl.sin_phi[ip]) : 0.f;
+                }
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int iw = row0 + 8 * h;
+                    if (iw >= pl.n_wspd) continue;
+                    const float2 rt = pl.rowtab[iw];
+                    const float2 *rowp = reinterpret_cast<const float2 *>(slab32 + (size_t)iw * pl.nph_pad) + L;
+#pragma unroll
+                    for (int j = 0; j < KP; ++j) {
+                        const float2 v = rowp[32 * j];
+#pragma unroll
+                        for (int o = 0; o < 2; ++o) {  // exactly the scan's operations
+                            const int ip = 2 * (L + 32 * j) + o;
+                            const float lc = __fadd_rn(o ? v.y : v.x, -rc.cs);
+                            const float aa = __fmaf_rn(rc.nq, lc, __fmaf_rn(lc, lc, rt.y));
+                            if (ip >= pl.n_phi || !(__fmaf_rn(rt.x, gq[2 * j + o], aa) <= rc.thr)) continue;
+                            const int flat = iw * pl.n_phi + ip;
+                            if (!exact) {
+                                ++n_loc;
+                                one_loc = flat;
+                            } else {  // J is never NaN here: finite inputs, NaN-free slab
+                                const double J = exact_cost_co(pl.wspd_grid[iw], pl.cos_phi[ip], pl.sin_phi[ip], slab64[flat], px.qa,
+                                                               px.qb, px.s, pl.dsig_co);
+                                if (J < bj || (J == bj && flat < bi)) {
+                                    bj = J;
+                                    bi = flat;
+                                }
+                            }
+                        }
+                    }
+                }
+                if (sub == 0 && !exact) ++n_cells;
+            }
+        };
+        walk(false);
+        int n_in = n_loc, result = one_loc;
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+            n_in += __shfl_xor_sync(gmask, n_in, o);
+            result = max(result, __shfl_xor_sync(gmask, result, o));  // the member itself when there is exactly one
+        }
+        if (n_in > 1) {  // FP64 with the reference's operation order over the members, first minimum wins
+            walk(true);
+#pragma unroll
+            for (int o = 4; o > 0; o >>= 1) {
+                const double oj = __shfl_xor_sync(gmask, bj, o);
+                const int oi = __shfl_xor_sync(gmask, bi, o);
+                if (oj < bj || (oj == bj && oi < bi)) {
+                    bj = oj;
+                    bi = oi;
+                }
+            }
+            result = bi;
+            if (sub == 0) ++n_fp64;
+        }
+        if (sub == 0) {
+            if (n_in >= 1) {
+                write_co(pl, out, result, px.neg, px.px);
+                ++n_settled;
+            } else  // cannot happen if the re-created costs equal the scan's; be safe
+                ws.fallback[atomicAdd(&ws.counters[1], 1ull)] = px.px;
+        }
+    }
+    n_settled = __reduce_add_sync(0xffffffffu, n_settled);
+    n_cells = __reduce_add_sync(0xffffffffu, n_cells);
+    n_fp64 = __reduce_add_sync(0xffffffffu, n_fp64);
+    if (lane == 0) {
+        if (n_settled) atomicAdd(&ws.counters[2], (u64)n_settled);
+        if (n_cells) atomicAdd(&ws.counters[3], (u64)n_cells);
+        if (n_fp64) atomicAdd(&ws.counters[11], (u64)n_fp64);
+    }
+}
+
+// Pass 2: a warp per hard pixel (RP at a time so that their dependent loads overlap): collects the band members of all
+// contending cells; a single member settles the pixel, several are evaluated in FP64 with the reference's operation order
+// and reduced by a warp-shuffle lexicographic (J, flat index) argmin = numpy's first minimum.
+template <int KP, int RP>
+__global__ void __launch_bounds__(256, 3) k_refine_co(xs_plan pl, Workspace ws, OutSpec out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t n_hard = (int64_t)ws.counters[12];
     const int n_chunks = (pl.n_wspd_pad + kChunkRows - 1) / kChunkRows;
-    const int bits = n_chunks <= 256 ? 8 : 16;
-    constexpr int kCand = kChunkRows * 2 * KP;  // candidates of one (lane, chunk) cell
+    constexpr int kCand = kChunkRows * 2 * KP;
     constexpr int kIter = (kCand + 31) / 32;
     u64 n_scanned = 0, n_cells = 0, n_fp64 = 0;
 
-    for (int64_t e0 = warp * RP; e0 < n_pos; e0 += n_warps * RP) {
+    for (int64_t h0 = warp * RP; h0 < n_hard; h0 += n_warps * RP) {
         PixRec px[RP];
         RefRec rc[RP];
         bool act[RP];
 #pragma unroll
         for (int i = 0; i < RP; ++i) {
-            const int64_t e = e0 + i;
-            px[i].state = 0;
-            if (e < n_pos) px[i] = ws.pix[e];
-            act[i] = false;
-        }
-#pragma unroll
-        for (int i = 0; i < RP; ++i) {
-            if (px[i].state == 1) {
-                rc[i] = ws.rec[e0 + i];
-                act[i] = (rc[i].cont | rc[i].wide) != 0u;
-                if (!act[i]) px[i].state = 3;  // the scan could not bound its error for this pixel
-            }
-            if (lane == 0) {
-                if (px[i].state == 2)
-                    write_co(pl, out, pl.first_nan[px[i].bin], px[i].neg, px[i].px);  // J is NaN exactly where L is NaN
-                else if (px[i].state == 3)
-                    ws.fallback[atomicAdd(&ws.counters[1], 1ull)] = px[i].px;
+            act[i] = h0 + i < n_hard;
+            if (act[i]) {
+                const unsigned e = ws.hard[h0 + i];
+                px[i] = ws.pix[e];
+                rc[i] = ws.rec[e];
             }
         }
-
-        // FP32 cost of candidate k of cell (L, row0) for pixel i, exactly as the scan computed it
-        auto member = [&](int i, int L, int row0, int k, int n_cand, int &flat) {
-            const int iw = row0 + k / (2 * KP);
-            const int slot = k % (2 * KP);
-            const int ip = 2 * (L + 32 * (slot >> 1)) + (slot & 1);
-            flat = iw * pl.n_phi + ip;
-            if (k >= n_cand || iw >= pl.n_wspd || ip >= pl.n_phi) return false;
-            const float2 rt = pl.rowtab[iw];
-            const float *slab32 = pl.scan + (size_t)px[i].bin * pl.n_wspd_pad * pl.nph_pad;
-            const float lc = __fadd_rn(slab32[(size_t)iw * pl.nph_pad + ip], -rc[i].cs);
-            const float mm = __fmaf_rn(lc, lc, rt.y);
-            const float aa = __fmaf_rn(rc[i].nq, lc, mm);
-            return __fmaf_rn(rt.x, g32(px[i].qa, px[i].qb, pl.cos_phi[ip], pl.sin_phi[ip]), aa) <= rc[i].thr;
-        };
         auto chunk_of = [&](int i, int L) {  // best chunk of cont lane L
             const int rank = __popc(rc[i].cont & ((1u << L) - 1u));
             const u64 ids = ((u64)rc[i].ch_hi << 32) | rc[i].ch_lo;
-            return (int)((ids >> (bits * rank)) & ((1u << bits) - 1u));
+            return (int)((ids >> (8 * rank)) & 0xffu);
         };
-
         // membership in S of the candidates of the first contender cell of every pixel (loads batched)
         bool in0[RP][kIter];
         int flat0[RP][kIter];
@@ -439,11 +558,11 @@ __global__ void __launch_bounds__(256, 3) k_refine_co(xs_plan pl, Workspace ws, 
                 rest[i] &= rest[i] - 1;
                 const int row0 = chunk_of(i, L) * kChunkRows;
 #pragma unroll
-                for (int q = 0; q < kIter; ++q) in0[i][q] = member(i, L, row0, lane + 32 * q, kCand, flat0[i][q]);
+                for (int q = 0; q < kIter; ++q) in0[i][q] = band_member<KP>(pl, px[i], rc[i], L, row0, lane + 32 * q, kCand, flat0[i][q]);
                 ++n_cells;
             }
         }
-        // count the members, look at the remaining cells (rare), settle
+        // count the members, look at the remaining cells, settle
 #pragma unroll
         for (int i = 0; i < RP; ++i) {
             if (!act[i]) continue;
@@ -461,7 +580,7 @@ __global__ void __launch_bounds__(256, 3) k_refine_co(xs_plan pl, Workspace ws, 
             auto visit = [&](int L, int row0, int n_cand, bool exact) {
                 for (int k0 = 0; k0 < n_cand; k0 += 32) {
                     int flat;
-                    if (!member(i, L, row0, k0 + lane, n_cand, flat)) continue;
+                    if (!band_member<KP>(pl, px[i], rc[i], L, row0, k0 + lane, n_cand, flat)) continue;
                     if (!exact) {
                         ++n_loc;
                         one_loc = flat;
@@ -512,37 +631,45 @@ __global__ void __launch_bounds__(256, 3) k_refine_co(xs_plan pl, Workspace ws, 
 }
 
 // ---- launch ----------------------------------------------------------------------------------------------------------
-// pixels per warp P and CTAs per SM by phi pairs per lane KP (register budget: g[P][KP] packed pairs live across the slab)
-template <int KP>
-struct ScanShape {
-    static constexpr int P = KP <= 3 ? 8 : 4;
-    static constexpr int NW = 4;
-    static constexpr int MB = KP <= 3 ? 4 : (KP == 4 ? 3 : 2);
+// pixels per warp P and CTAs per SM by phi pairs per lane KP (register budget: g[P][KP] packed pairs live across the slab).
+// XS_SCAN_SHAPE="P,MB" (environment, development aid) selects another instantiation for KP == 3.
+struct Shape {
+    int p, nw, mb;
 };
-
-int scan_tile_px(int kp) {
-    switch (kp) {
-        case 1: return ScanShape<1>::P * ScanShape<1>::NW;
-        case 2: return ScanShape<2>::P * ScanShape<2>::NW;
-        case 3: return ScanShape<3>::P * ScanShape<3>::NW;
-        case 4: return ScanShape<4>::P * ScanShape<4>::NW;
-        default: return ScanShape<6>::P * ScanShape<6>::NW;
+static Shape scan_shape(int kp) {
+    if (kp > 3) return {4, 4, kp == 4 ? 3 : 2};
+    Shape s = {8, 4, 4};
+    if (kp == 3) {
+        static int ep = -1, em = -1;
+        if (ep < 0) {
+            const char *e = getenv("XS_SCAN_SHAPE");
+            ep = 0;
+            if (e) sscanf(e, "%d,%d", &ep, &em);
+        }
+        if (ep == 8 && em == 3) s = {8, 4, 3};
+        if (ep == 7 && em == 4) s = {7, 4, 4};
+        if (ep == 6 && em == 4) s = {6, 4, 4};
+        if (ep == 6 && em == 5) s = {6, 4, 5};
     }
+    return s;
+}
+int scan_tile_px(int kp) {
+    const Shape s = scan_shape(kp);
+    return s.p * s.nw;
 }
 
-template <int KP>
-static int launch_kp(const xs_plan *pl, const RasterArgs &ra, const Workspace &ws, const OutSpec &out, int64_t n_px,
-                     xs_timer *timer, cudaStream_t st) {
-    using S = ScanShape<KP>;
-    constexpr int TP = S::P * S::NW;
-    static_assert(kSortRun % 1 == 0 && TP <= kTilePad, "tile size");
+template <int KP, int P, int NW, int MB>
+static int launch_shape(const xs_plan *pl, const RasterArgs &ra, const Workspace &ws, const OutSpec &out, int64_t n_px,
+                        xs_timer *timer, cudaStream_t st) {
+    constexpr int TP = P * NW;
+    static_assert(TP <= kTilePad && TP <= kSortRun, "tile size");
     int sms = kNumSMs;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, pl->device);
     const int64_t max_tiles = ceil_div(n_px, TP) + pl->n_inc;
     XS_LAUNCH(k_list_prepare, (unsigned)ceil_div(max_tiles, kSortRun / TP), kSortRun, 0, st, *pl, ra, ws, TP);
 
-    auto kern = k_scan_co<KP, S::P, S::NW, S::MB>;
-    const size_t smem = sizeof(ScanSmem<KP, S::P, S::NW>) + sizeof(float2) * (size_t)pl->n_wspd_pad;
+    auto kern = k_scan_co<KP, P, NW, MB>;
+    const size_t smem = sizeof(ScanSmem<KP, P, NW>) + sizeof(float2) * (size_t)pl->n_wspd_pad;
     if (smem > 200 * 1024) {
         set_error("xs_invert: wspd grid too long for the shared-memory row table");
         return XS_E_UNSUPPORTED;
@@ -550,12 +677,13 @@ static int launch_kp(const xs_plan *pl, const RasterArgs &ra, const Workspace &w
     // per launch, not once per process: the attribute belongs to the current device's context
     XS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     int per_sm = 1;
-    XS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, S::NW * 32, smem));
+    XS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NW * 32, smem));
     if (per_sm < 1) per_sm = 1;
     if (timer) XS_CUDA(cudaEventRecord(timer->ev[0], st));
-    XS_LAUNCH(kern, sms * per_sm, S::NW * 32, smem, st, *pl, ws);
+    XS_LAUNCH(kern, sms * per_sm, NW * 32, smem, st, *pl, ws);
     if (timer) XS_CUDA(cudaEventRecord(timer->ev[1], st));
-    XS_LAUNCH((k_refine_co<KP, 2>), sms * 6, 256, 0, st, *pl, ws, out, TP);
+    XS_LAUNCH(k_refine_easy<KP>, sms * 6, 256, 0, st, *pl, ws, out, TP);
+    XS_LAUNCH((k_refine_co<KP, 2>), sms * 6, 256, 0, st, *pl, ws, out);
     if (timer) {
         XS_CUDA(cudaEventRecord(timer->ev[2], st));
         timer->recorded = 1;
@@ -565,13 +693,21 @@ static int launch_kp(const xs_plan *pl, const RasterArgs &ra, const Workspace &w
 
 int launch_scan_pipeline(const xs_plan *pl, const RasterArgs &ra, const Workspace &ws, const OutSpec &out, int64_t n_px,
                          xs_timer *timer, cudaStream_t st) {
-    switch (pl->kp) {
-        case 1: return launch_kp<1>(pl, ra, ws, out, n_px, timer, st);
-        case 2: return launch_kp<2>(pl, ra, ws, out, n_px, timer, st);
-        case 3: return launch_kp<3>(pl, ra, ws, out, n_px, timer, st);
-        case 4: return launch_kp<4>(pl, ra, ws, out, n_px, timer, st);
-        default: return launch_kp<6>(pl, ra, ws, out, n_px, timer, st);
-    }
+    const Shape s = scan_shape(pl->kp);
+#define XS_SHAPE(KP_, P_, MB_) \
+    if (pl->kp == KP_ && s.p == P_ && s.mb == MB_) return launch_shape<KP_, P_, 4, MB_>(pl, ra, ws, out, n_px, timer, st)
+    XS_SHAPE(1, 8, 4);
+    XS_SHAPE(2, 8, 4);
+    XS_SHAPE(3, 8, 4);
+    XS_SHAPE(3, 8, 3);
+    XS_SHAPE(3, 7, 4);
+    XS_SHAPE(3, 6, 4);
+    XS_SHAPE(3, 6, 5);
+    XS_SHAPE(4, 4, 3);
+    XS_SHAPE(6, 4, 2);
+#undef XS_SHAPE
+    set_error("xs_invert: no scan instantiation for kp=%d", pl->kp);
+    return XS_E_UNSUPPORTED;
 }
 
 }  // namespace xs
