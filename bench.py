@@ -5,7 +5,15 @@ A "step" is one full inversion of a synthetic Sentinel-1 IW GRD-sized dual-pol s
 incidence 30..46 deg) on every rank: `value` times the C-ABI call `xs_invert` with the rasters resident in HBM;
 `e2e` times the public API `xsarsea_b200.windspeed.invert_from_model` with pinned HOST numpy arrays (host->device
 and device->host copies inside the timed region).  With N > 1 ranks every GPU inverts its own scene (the batch-of-
-scenes sharding of BASELINE.json configs[4]; no data-path collective), so scaling is "weak".
+scenes sharding of BASELINE.json configs[4]; no data-path collective), so the headline scaling is "weak"; the same run
+also times the north-star split -- ONE scene row-partitioned over the N GPUs, results gathered on the device over NCCL
+into rank 0 -- and reports it under `strong`.
+
+At N = 1 the line also carries
+  parity        the GPU end-to-end result compared with the CPU oracle on the pixels the CPU baseline inverts
+  cpu_baseline  the reference's CPU program shape (oracle/numba_port.py) timed on a crop of the same host scene
+  aux           the other BASELINE.json configs (co-pol 1000^2, LUT generation, cross-pol-only 10000^2, one EW scene with
+                a dsig raster + sigma0_detrend), a hostile scene, the fused speed/direction epilogue and a measured FP32 peak
 
 `--impl reference` times the reference's CPU path instead (the in-repo numba port of windspeed.py:183-323 with the
 reference's own guvectorize arguments -- xarray/dask are not installable here) on a bounded sample
@@ -22,6 +30,7 @@ import sys
 import tempfile
 import threading
 import time
+import warnings
 
 import numpy as np
 
@@ -31,41 +40,46 @@ if ROOT not in sys.path:
 
 LINES, SAMPLES = 16700, 25000
 INC_NEAR, INC_FAR = 30.0, 46.0
-FLOP_PER_PX = 8 * 499 * 181 + 6 * 771  # 8 flop per co-pol candidate + 6 per cross-pol candidate
+FLOP_CO = 8 * 499 * 181            # 8 flop per co-pol candidate
+FLOP_PER_PX = FLOP_CO + 6 * 771    # + 6 per cross-pol candidate
 METRIC = "inverted pixels/sec (dual-pol cmod5n+ms1ahw)"
 
 
 def workload_text(args):
     """The workload both arms of the bench report (config.workload)."""
+    scene = "" if args.scene == "friendly" else f", scene={args.scene}"
     return (f"dual-pol invert: gmf_cmod5n (default LUT 501x499x181) + nc_lut_cmodms1ahw (synthetic stand-in 331x771), "
-            f"S1 IW {args.lines}x{args.samples} px per GPU, inc {INC_NEAR}-{INC_FAR} deg, 1% NaN, dsig_cr=0.1, ancillary wind")
+            f"S1 IW {args.lines}x{args.samples} px per GPU, inc {INC_NEAR}-{INC_FAR} deg, 1% NaN, dsig_cr=0.1, ancillary wind{scene}")
 
 
-def peaks():
-    p = {}
+def measured_peaks():
     try:
-        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
-        pass
+        return {}
+
+
+def fp32_peaks(measured_tflops=None):
+    p = measured_peaks()
     sm_mhz = float(p.get("sm_max_mhz", 1965.0))
-    return dict(fp32_tflops=148 * 128 * 2 * sm_mhz * 1e6 / 1e12, sm_max_mhz=sm_mhz,
-                source="148 SM x 128 lanes x 2 x sm_max_mhz of MEASURED_PEAKS.json" if p else
-                "148 SM x 128 lanes x 2 x 1965 MHz (fallback: MEASURED_PEAKS.json absent)")
+    return dict(nominal_tflops=148 * 128 * 2 * sm_mhz * 1e6 / 1e12, measured_tflops=measured_tflops, sm_max_mhz=sm_mhz,
+                source=("148 SM x 128 lanes x 2 x sm_max_mhz of MEASURED_PEAKS.json (the file has no FP32 figure)" if p else
+                        "148 SM x 128 lanes x 2 x 1965 MHz (fallback: MEASURED_PEAKS.json absent)"))
 
 
-def profiled_traffic_per_px():
-    """DRAM bytes per pixel of k_scan_co from the committed `ncu --set full` capture (profiles/): that capture was taken
-    on `bench.py --lines 400` (10 Mpx per launch); traffic is proportional to the pixel count (rasters in, results out,
-    4 B/px of pixel list), so it is reported scaled to this run's launch size."""
-    path = os.path.join(ROOT, "profiles", "r1_k_scan_co_ncu_raw_selected.csv")
+def hbm_peak():
+    p = measured_peaks()
+    if "hbm_gbs" in p:
+        return float(p["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (copy, read+write bytes)"
+    return 6650.0, "fallback 6.65 TB/s of B200_PROFILING.md (MEASURED_PEAKS.json absent)"
+
+
+def profiled_counters():
+    """Hardware counters of k_scan_co from the committed `ncu --set full` capture (profiles/): DRAM bytes per pixel, FMA
+    pipe and issue-slot utilisation.  Not measured in this run -- labelled "from profile" in the line."""
+    path = os.path.join(ROOT, "profiles", "r2_k_scan_co_ncu_selected.json")
     try:
-        vals = {}
-        for line in open(path):
-            f = line.strip().split(",")
-            if f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
-                scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[f[1]]
-                vals[f[0]] = float(f[2]) * scale
-        return (vals["dram__bytes_read.sum"] + vals["dram__bytes_write.sum"]) / (400 * 25000)
+        return json.load(open(path))
     except Exception:
         return None
 
@@ -134,8 +148,11 @@ def write_ms1ahw_standin(dirname):
     return path
 
 
-def synth_scene_device(lines, samples, seed):
-    """SURVEY.md D2 recipe generated on the device (torch CUDA generator, seed stated in the JSON line)."""
+def synth_scene_device(lines, samples, seed, inc_near=INC_NEAR, inc_far=INC_FAR, scene="friendly"):
+    """SURVEY.md D2 recipe generated on the device (torch CUDA generator, seed stated in the JSON line).
+
+    scene="hostile" (VERDICT r1 item 6): per-pixel random incidence over 17-50 deg, sigma0 alternating sea / land levels
+    (+-15 dB) in short runs along the line, ancillary wind 10 m/s and 90 deg off the truth, 20 % NaN."""
     import torch
 
     from xsarsea_b200 import _device as D
@@ -143,25 +160,39 @@ def synth_scene_device(lines, samples, seed):
 
     g = torch.Generator(device="cuda").manual_seed(seed)
     f64 = dict(device="cuda", dtype=torch.float64)
-    inc = (INC_NEAR + (INC_FAR - INC_NEAR) * torch.arange(samples, **f64) / (samples - 1)).expand(lines, samples).contiguous()
+    hostile = scene == "hostile"
+    if hostile:
+        inc = 17 + 33 * torch.rand(lines, samples, generator=g, **f64)
+    else:
+        inc = (inc_near + (inc_far - inc_near) * torch.arange(samples, **f64) / max(samples - 1, 1)).expand(lines, samples).contiguous()
     wspd = 2 + 23 * torch.rand(lines, samples, generator=g, **f64)
     phi = 360 * torch.rand(lines, samples, generator=g, **f64)
     s_co = D.gmf_eval(nat.GMF_IDS["gmf_cmod5n"], inc, wspd, phi)
     s_co *= torch.exp(0.05 * torch.randn(lines, samples, generator=g, **f64))
     s_cr = D.gmf_eval(nat.GMF_IDS["gmf_s1_v2"], inc, wspd, None)
     s_cr *= torch.exp(0.05 * torch.randn(lines, samples, generator=g, **f64))
-    wa = wspd + 2 * torch.randn(lines, samples, generator=g, **f64)
-    pa = torch.deg2rad(phi + 20 * torch.randn(lines, samples, generator=g, **f64))
+    if hostile:
+        # sea / land contrast: runs of 37 samples alternately scaled by +15 dB and -15 dB
+        sign = ((torch.arange(samples, device="cuda") // 37) % 2).to(torch.float64) * 2 - 1
+        s_co *= 10 ** (1.5 * sign)
+        s_cr *= 10 ** (1.5 * sign)
+        wa = wspd + 10.0
+        pa = torch.deg2rad(phi + 90.0)
+    else:
+        wa = wspd + 2 * torch.randn(lines, samples, generator=g, **f64)
+        pa = torch.deg2rad(phi + 20 * torch.randn(lines, samples, generator=g, **f64))
     anc = torch.polar(wa.abs(), pa + (wa < 0) * np.pi)
-    land = torch.rand(lines, samples, generator=g, device="cuda") < 0.01   # 1 % NaN (land mask)
+    land = torch.rand(lines, samples, generator=g, device="cuda") < (0.20 if hostile else 0.01)   # NaN (land mask)
     s_co[land] = float("nan")
     s_cr[land] = float("nan")
     return inc, s_co, s_cr, anc
 
 
-def make_cpu_port(threads=None):
+def make_cpu_port(luts=None, threads=None):
     """The reference's CPU program shape (oracle/numba_port.py: the numba gufunc of windspeed.py:183-323 with the
-    reference's decorator arguments) for the bench workload.  Returns run(sample) -> (px/s, threads, seconds)."""
+    reference's decorator arguments) for the bench workload.  luts = (co_lut, gi, gw, gp, cr_lut, gic, gwc) to use given
+    LUT arrays (the parity leg passes the device-built ones), None: built by the oracle.
+    Returns run(sample) -> (px/s, threads, seconds, wind_co, wind_cr)."""
     import numba
 
     import oracle
@@ -170,9 +201,12 @@ def make_cpu_port(threads=None):
 
     if threads:
         numba.set_num_threads(threads)
-    co_lut, (gi, gw, gp) = olut.to_lut("gmf_cmod5n", units="dB")
-    gic, gwc = np.linspace(17.0, 50.0, 331), np.linspace(3.0, 80.0, 771)
-    cr_lut = 10 * np.log10(oracle.lut_build("gmf_s1_v2", gic, gwc) + 1e-15)
+    if luts is None:
+        co_lut, (gi, gw, gp) = olut.to_lut("gmf_cmod5n", units="dB")
+        gic, gwc = np.linspace(17.0, 50.0, 331), np.linspace(3.0, 80.0, 771)
+        cr_lut = 10 * np.log10(oracle.lut_build("gmf_s1_v2", gic, gwc) + 1e-15)
+    else:
+        co_lut, gi, gw, gp, cr_lut, gic, gwc = luts
     f = numba_port.make_inverter(co_lut, gi, gw, gp, cr_lut, gic, gwc)
     tiny = (np.full((2, 8), 35.0), np.full((2, 8), -15.0), np.full((2, 8), -25.0), np.full((2, 8), 0.1),
             np.full((2, 8), 5 + 5j))
@@ -184,16 +218,16 @@ def make_cpu_port(threads=None):
             co_db, cr_db = 10 * np.log10(s_co + 1e-15), 10 * np.log10(s_cr + 1e-15)   # windspeed.py:126-128
         dsig = np.full(inc.shape, 0.1)
         t0 = time.perf_counter()
-        f(inc, co_db, cr_db, dsig, anc)
+        o_co, o_cr = f(inc, co_db, cr_db, dsig, anc)
         dt = time.perf_counter() - t0
-        return inc.size / dt, numba.get_num_threads(), dt
+        return inc.size / dt, numba.get_num_threads(), dt, o_co, o_cr
 
     return run
 
 
 def sized_cpu_lines(port, make_sample, target_s, lo=16, hi=4096):
     """Number of 1000-sample lines that keeps one CPU pass near `target_s` seconds (probe with `lo` lines first)."""
-    rate, _, _ = port(make_sample(lo))
+    rate = port(make_sample(lo))[0]
     return int(min(hi, max(lo, round(target_s * rate / 1000.0 / 16) * 16)))
 
 
@@ -221,7 +255,7 @@ def run_reference(args, rank, world):
     rates, secs = [], []
     threads = None
     for it in range(args.warmup + args.steps):
-        r, threads, dt = port(sample)
+        r, threads, dt, _, _ = port(sample)
         if it >= args.warmup:
             rates.append(r)
             secs.append(dt)
@@ -237,6 +271,174 @@ def run_reference(args, rank, world):
     }))
 
 
+# ---- helpers of the GPU arm ------------------------------------------------------------------------------------------
+def timeit(fn, warm=3, reps=5, inner=1):
+    """best / mean over `reps` CUDA-event timings of `inner` back-to-back calls (inner > 1 for sub-millisecond
+    operations, so that launch latency is not what is measured)."""
+    import torch
+
+    for _ in range(warm):
+        fn()
+    ts = []
+    for _ in range(reps):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(inner):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) / inner)
+    return float(np.min(ts)), float(np.mean(ts))
+
+
+def wind_diff(got, want):
+    """Parity statistics of two complex wind rasters (windspeed.py:183-282 outputs)."""
+    got, want = np.asarray(got).ravel(), np.asarray(want).ravel()
+    nan_g, nan_w = np.isnan(got.real) | np.isnan(got.imag), np.isnan(want.real) | np.isnan(want.imag)
+    ok = ~(nan_g | nan_w)
+    g, w = got[ok], want[ok]
+    with np.errstate(all="ignore"):
+        dspd = np.abs(np.abs(g) - np.abs(w))
+        ddir = np.abs(np.angle(g * np.conj(w), deg=True))
+        ddir[(np.abs(w) == 0) | (np.abs(g) == 0)] = 0
+    return dict(n_px=int(got.size), n_valid=int(ok.sum()), nan_pattern_equal=bool(np.array_equal(nan_g, nan_w)),
+                value_mismatch=int((np.abs(g - w) > 1e-9).sum()), outside_tolerance=int(((dspd > 1e-3) | (ddir > 0.1)).sum()),
+                max_dspeed=float(dspd.max()) if g.size else 0.0, max_ddir_deg=float(ddir.max()) if g.size else 0.0)
+
+
+def run_aux(args, plan, model, peak_tflops, hbm_gbs, hbm_src):
+    """The other BASELINE.json configs, a hostile scene and the F2 epilogue, each with its own roofline (N = 1 only)."""
+    import torch
+
+    import xsarsea_b200
+    from xsarsea_b200 import _device as D
+    from xsarsea_b200 import _native as nat
+    from xsarsea_b200 import windspeed
+
+    aux = {}
+    f64 = dict(device="cuda", dtype=torch.float64)
+    fp32_src = "xs_bench_fp32_peak (FFMA2 loop measured in this run)"
+
+    def fp32_roof(flop_per_px, n_px, ms):
+        ach = flop_per_px * n_px / (ms * 1e-3) / 1e12
+        return {"bound": "fp32 cuda-core (FMA pipe)", "achieved": ach, "peak": peak_tflops, "unit": "TFLOP/s",
+                "frac": ach / peak_tflops, "peak_source": fp32_src}
+
+    def hbm_roof(bytes_per_unit, n, ms, note=None):
+        ach = bytes_per_unit * n / (ms * 1e-3) / 1e9
+        r = {"bound": "hbm", "achieved": ach, "peak": hbm_gbs, "unit": "GB/s", "frac": ach / hbm_gbs,
+             "algorithmic_bytes_per_unit": bytes_per_unit, "peak_source": hbm_src}
+        if note:
+            r["note"] = note
+        return r
+
+    # ---- config 1: co-pol only, 1000 x 1000, default cmod5n LUT (windspeed.py:183-247) ----
+    plan_c = D.InversionPlan(co=(plan.co_lut, *plan.co_grids))
+    H = W = 1000
+    g = torch.Generator(device="cuda").manual_seed(args.seed)
+    inc = (17.5 + 32 * torch.arange(W, **f64) / (W - 1)).expand(H, W).contiguous()
+    w = 2 + 23 * torch.rand(H, W, generator=g, **f64)
+    p = 360 * torch.rand(H, W, generator=g, **f64)
+    s_co = D.gmf_eval(nat.GMF_IDS["gmf_cmod5n"], inc, w, p) * torch.exp(0.05 * torch.randn(H, W, generator=g, **f64))
+    anc = torch.polar((w + 2 * torch.randn(H, W, generator=g, **f64)).abs(), torch.deg2rad(p + 20 * torch.randn(H, W, generator=g, **f64)))
+    oc, ox = torch.empty_like(anc), torch.empty_like(anc)
+    best, mean = timeit(lambda: plan_c.invert(inc, s_co, None, 0.1, anc, out_co=oc, out_cr=ox))
+    aux["config1_copol_1000x1000"] = dict(value=H * W / (best * 1e-3), unit="px/s", ms=best, ms_mean=mean,
+                                          roofline=fp32_roof(FLOP_CO, H * W, best), stats=plan_c.last_stats(),
+                                          note="1 Mpx is 53 tiles per CTA: launch, binning and the kernel's tail are a visible share")
+    plan_c.close()
+    del inc, w, p, s_co, anc, oc, ox
+
+    # ---- config 2: LUT generation (gmfs.py:218-230 / models.py:154-230) ----
+    gi, gw, gp = np.linspace(16, 66, 501), np.linspace(0.2, 50, 499), np.linspace(0, 180, 181)
+    n_ev = gi.size * gw.size * gp.size
+    best, mean = timeit(lambda: D.lut_build(nat.GMF_IDS["gmf_cmod5n"], gi, gw, gp), warm=5, reps=7, inner=5)
+    aux["config2_lut_direct_501x499x181"] = dict(
+        value=n_ev / (best * 1e-3), unit="GMF evaluations/s", ms=best, ms_mean=mean,
+        roofline=hbm_roof(8, n_ev, best, "write-only FP64 LUT (8 B per node); the kernel is bound by FP64 transcendental throughput "
+                                         "(exp / log / tanh / cos per evaluation on the 64-lane/SM FP64 pipe), not by HBM"))
+    li, lw, lp = np.linspace(16, 66, 51), np.linspace(0.2, 50, 250), np.linspace(0, 180, 73)
+
+    def default_path():
+        lut = D.lut_build(nat.GMF_IDS["gmf_cmod5n"], li, lw, lp)
+        lut = D.lut_interp_axis(lut, 0, li, gi)
+        lut = D.lut_interp_axis(lut, 1, lw, gw)
+        lut = D.lut_interp_axis(lut, 2, lp, gp)
+        return D.lut_to_db(lut)
+
+    best, mean = timeit(default_path, warm=5, reps=7, inner=5)
+    # bytes: low-res build (write) + three interpolation passes + dB pass, each reading its input and writing its output once
+    n0, n1, n2, n3 = 51 * 250 * 73, 501 * 250 * 73, 501 * 499 * 73, n_ev
+    lut_bytes = 8 * (n0 + (n0 + n1) + (n1 + n2) + (n2 + n3) + 2 * n3)
+    aux["config2_to_lut_default_path"] = dict(value=n_ev / (best * 1e-3), unit="LUT nodes/s", ms=best, ms_mean=mean,
+                                              roofline=hbm_roof(lut_bytes / n_ev, n_ev, best,
+                                                                "low-res GMF + 3 interpolation passes + dB pass (FP64 log10 bound)"))
+
+    # ---- config 4: cross-pol only, 10 000 x 10 000, NetCDF-LUT model (models.py:350-410, windspeed.py:252-279) ----
+    plan_x = D.InversionPlan(cr=(plan.cr_lut, *plan.cr_grids))
+    H = W = 10000
+    inc, s_co, s_cr, anc = synth_scene_device(H, W, args.seed + 3, 20.0, 49.0)
+    del s_co, anc
+    o = torch.empty(inc.shape, dtype=torch.float64, device="cuda")
+    best, mean = timeit(lambda: plan_x.invert(inc, None, s_cr, 0.1, None, cr_abs=True, out_cr=o))
+    aux["config4_crosspol_10000x10000"] = dict(
+        value=H * W / (best * 1e-3), unit="px/s", ms=best, ms_mean=mean,
+        roofline=hbm_roof(24, H * W, best, "inc + sigma0 in (16 B/px), float64 wind speed out (8 B/px); after the exact interval "
+                                           "search the pass is no longer FP32-bound"))
+    s32, i32 = s_cr.float(), inc.float()
+    best, mean = timeit(lambda: plan_x.invert(i32, None, s32, 0.1, None, cr_abs=True, out_cr=o))
+    aux["config4_crosspol_10000x10000_f32_rasters"] = dict(value=H * W / (best * 1e-3), unit="px/s", ms=best, ms_mean=mean,
+                                                           roofline=hbm_roof(16, H * W, best, "f32 rasters in (8 B/px), f64 out"))
+    plan_x.close()
+    del inc, s_cr, o, s32, i32
+
+    # ---- config 5: one of the 8 EW scenes (10 000 x 10 400, inc 19-47): dual-pol with a dsig_cr raster + sigma0_detrend ----
+    H, W = 10000, 10400
+    inc, s_co, s_cr, anc = synth_scene_device(H, W, args.seed + 5, 19.0, 47.0)
+    dsig = windspeed.get_dsig("nc_lut_cmodms1ahw", inc, s_cr, 10 ** -3.2)   # (1.25 / (s/n))**4, utils.py:83-87
+    oc, ox = torch.empty_like(anc), torch.empty_like(anc)
+    best, mean = timeit(lambda: plan.invert(inc, s_co, s_cr, dsig, anc, merge_dual=True, out_co=oc, out_cr=ox, timed=True), warm=2, reps=3)
+    scan_ms, refine_ms = plan.last_scan_ms()
+    st = plan.last_stats()
+    aux["config5_ew_scene_dualpol_dsig_raster"] = dict(
+        value=H * W / (best * 1e-3), unit="px/s", ms=best, ms_mean=mean, stats=st,
+        roofline=dict(fp32_roof(FLOP_CO, st["scan_pixels"], scan_ms), kernel="k_scan_co", scan_ms=scan_ms, refine_ms=refine_ms))
+    best, mean = timeit(lambda: xsarsea_b200.sigma0_detrend(s_co, inc, model="gmf_cmod5n"), warm=5, reps=5, inner=5)
+    aux["config5_sigma0_detrend_10000x10400"] = dict(value=H * W / (best * 1e-3), unit="px/s", ms=best, ms_mean=mean,
+                                                     roofline=hbm_roof(16, H * W, best, "sigma0 in + detrended sigma0 out; public API call incl. the GMF profile"))
+    # ---- F2 epilogue on the same scene: speed / direction planes instead of complex128 (half / quarter of the output bytes)
+    best, mean = timeit(lambda: plan.invert(inc, s_co, s_cr, dsig, anc, merge_dual=True, speed_dir=True, ground_heading=190.0, out_f32=True),
+                        warm=2, reps=3)
+    aux["f2_epilogue_speed_dir_f32_planes"] = dict(value=H * W / (best * 1e-3), unit="px/s", ms=best, ms_mean=mean,
+                                                   d2h_bytes_per_px=16, d2h_bytes_per_px_complex128=32)
+    del inc, s_co, s_cr, anc, dsig, oc, ox
+    torch.cuda.empty_cache()
+
+    # ---- hostile scene (same LUTs): random incidence per pixel, +-15 dB sea/land runs, ancillary 10 m/s / 90 deg off, 20 % NaN
+    Hh = min(args.lines, args.hostile_lines)
+    oc = torch.empty(Hh, args.samples, dtype=torch.complex128, device="cuda")
+    ox = torch.empty_like(oc)
+    res = {}
+    for name in ("friendly", "hostile"):
+        inc, s_co, s_cr, anc = synth_scene_device(Hh, args.samples, args.seed + 9, scene=name)
+        best, mean = timeit(lambda: plan.invert(inc, s_co, s_cr, 0.1, anc, merge_dual=True, out_co=oc, out_cr=ox, timed=True), warm=2, reps=3)
+        st = plan.last_stats()
+        n_co = max(st["scan_pixels"] + st["exhaustive_pixels"], 1)
+        sm, rm = plan.last_scan_ms()
+        res[name] = dict(value=Hh * args.samples / (best * 1e-3), unit="px/s", ms=best, co_pixels=n_co,
+                         co_px_per_s=n_co / (best * 1e-3), refined_cells_per_px=st["fp64_chunks"] / n_co,
+                         fp64_pixels_frac=st["fp64_pixels"] / n_co, exhaustive_pixels=st["exhaustive_pixels"],
+                         scan_ms=sm, refine_ms=rm)
+        del inc, s_co, s_cr, anc
+    res["hostile_over_friendly_px_rate"] = res["hostile"]["value"] / res["friendly"]["value"]
+    res["hostile_over_friendly_co_px_rate"] = res["hostile"]["co_px_per_s"] / res["friendly"]["co_px_per_s"]
+    res["lines"] = Hh
+    res["note"] = "20 % of the hostile scene's pixels are NaN and skip the co-pol scan: compare the co-pol pixel rates"
+    aux["hostile_scene"] = res
+    return aux
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -246,10 +448,14 @@ def main():
     ap.add_argument("--lines", type=int, default=LINES)
     ap.add_argument("--samples", type=int, default=SAMPLES)
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--scene", default="friendly", choices=["friendly", "hostile"])
+    ap.add_argument("--hostile-lines", type=int, default=4000, help="lines of the hostile / friendly pair timed in aux")
     ap.add_argument("--cpu-lines", type=int, default=0, help="lines of the 1000-sample crop timed on the CPU (0: sized for --cpu-seconds)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target duration of one CPU pass")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-aux", action="store_true")
+    ap.add_argument("--no-strong", action="store_true")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -265,11 +471,13 @@ def main():
     stdout_fd = os.dup(1)
     os.dup2(2, 1)
 
+    import ctypes
+
     import torch
     import torch.distributed as dist
 
     from xsarsea_b200 import _native as nat
-    from xsarsea_b200 import windspeed
+    from xsarsea_b200 import parallel, windspeed
     from xsarsea_b200.windspeed import windspeed as ws_impl
 
     if not torch.cuda.is_available():
@@ -300,8 +508,11 @@ def main():
     plan = ws_impl._get_plan(windspeed.get_model(model[0]), windspeed.get_model(model[1]), 0.1, {})
     torch.cuda.synchronize()
     lut_s = time.perf_counter() - t0
+    tf = ctypes.c_double()
+    nat.check(nat.load().xs_bench_fp32_peak(ctypes.byref(tf), nat.stream_ptr()), "xs_bench_fp32_peak")
+    pk = fp32_peaks(float(tf.value))
 
-    inc, s_co, s_cr, anc = synth_scene_device(args.lines, args.samples, args.seed + rank)
+    inc, s_co, s_cr, anc = synth_scene_device(args.lines, args.samples, args.seed + rank, scene=args.scene)
     n_px = inc.numel()
     out_co = torch.empty_like(anc)
     out_cr = torch.empty_like(anc)
@@ -317,12 +528,14 @@ def main():
     if rank == 0:
         sampler.start()
     launches0 = nat.launch_count()
-    scan_ms = []
+    scan_ms, refine_ms = [], []
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
         step()
-        scan_ms.append(plan.last_scan_ms()[0])   # waits for this step's scan + refine kernels only
+        a, b = plan.last_scan_ms()   # waits for this step's scan + refinement kernels only
+        scan_ms.append(a)
+        refine_ms.append(b)
     e1.record()
     barrier()
     ms = max_over_ranks(e0.elapsed_time(e1))
@@ -330,14 +543,73 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     stats = plan.last_stats()
     value = world * n_px * args.steps / (ms * 1e-3)
-    scan_avg_ms = float(np.mean(scan_ms))
-    pk = peaks()
-    achieved = FLOP_PER_PX * n_px / (scan_avg_ms * 1e-3) / 1e12
-    bpp = profiled_traffic_per_px()
+    scan_avg_ms, refine_avg_ms = float(np.mean(scan_ms)), float(np.mean(refine_ms))
+    # the scan kernel does the co-pol candidates of the pixels it scans (NaN pixels are never listed; the cross-pol
+    # candidates belong to k_cross): 8 flop x 499 x 181 per scanned pixel
+    scan_px = stats["scan_pixels"]
+    achieved = FLOP_CO * scan_px / (scan_avg_ms * 1e-3) / 1e12
+    prof = profiled_counters()
+    roofline = {"bound": "fp32 cuda-core (FMA pipe)", "kernel": "k_scan_co", "achieved": achieved,
+                "peak": pk["measured_tflops"], "unit": "TFLOP/s", "frac": achieved / pk["measured_tflops"],
+                "peak_source": "xs_bench_fp32_peak: register-resident FFMA2 loop measured in this run",
+                "peak_nominal": pk["nominal_tflops"], "frac_of_nominal": achieved / pk["nominal_tflops"],
+                "peak_nominal_source": pk["source"], "scan_ms_per_launch": scan_avg_ms, "refine_ms_per_launch": refine_avg_ms,
+                "frac_incl_refinement": FLOP_CO * scan_px / ((scan_avg_ms + refine_avg_ms) * 1e-3) / 1e12 / pk["measured_tflops"],
+                "flop_per_px": FLOP_CO, "px_per_launch": scan_px, "share_of_step": scan_avg_ms / (ms / args.steps),
+                "accounting": "algorithmic: the reference's 8 flop per candidate (SURVEY D4); the centred form executes ~4.5",
+                "traffic": None if prof is None else prof["dram_bytes_per_px"] * scan_px,
+                "traffic_note": None if prof is None else "from profile (not measured in this run): DRAM read+write bytes of k_scan_co "
+                                "per scanned pixel x pixels of this launch, %s" % prof.get("source", ""),
+                "fma_pipe_pct": None if prof is None else prof.get("fma_pipe_pct"),
+                "issue_slots_pct": None if prof is None else prof.get("issue_slots_pct"),
+                "counters_note": None if prof is None else "from profile (ncu --set full of the shipped kernel), not this run"}
+
+    # ---- strong scaling: ONE scene (same seed on every rank) row-partitioned, results gathered on the device into rank 0 ----
+    strong = None
+    if world > 1 and not args.no_strong:
+        del inc, s_co, s_cr, anc, out_co, out_cr
+        torch.cuda.empty_cache()
+        full = synth_scene_device(args.lines, args.samples, args.seed, scene=args.scene)
+        lo, hi = parallel.row_shard(args.lines, world, rank)
+        blk = [t[lo:hi] for t in full]   # contiguous row blocks (views)
+        res = None
+        for _ in range(2):
+            res = parallel.invert_rows_resident(plan, blk, args.lines, lo, hi, dst=0, merge_dual=True)
+        barrier()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        ev[0].record()
+        res = parallel.invert_rows_resident(plan, blk, args.lines, lo, hi, dst=0, merge_dual=True, events=ev[1:])
+        barrier()
+        t_all = max_over_ranks(ev[0].elapsed_time(ev[2]))
+        t_inv = max_over_ranks(ev[0].elapsed_time(ev[1]))
+        t_gat = max_over_ranks(ev[1].elapsed_time(ev[2]))
+        ok = True
+        if rank == 0:   # rank 0's own rows must equal its block result bit for bit, and every other block must have arrived
+            co_full, du_full = res
+            mine = plan.invert(*[t.contiguous() for t in blk[:3]], 0.1, blk[3].contiguous(), merge_dual=True)
+            bits = lambda z: torch.view_as_real(z).contiguous().view(torch.int64)
+            ok = torch.equal(bits(co_full[lo:hi]), bits(mine[0])) and torch.equal(bits(du_full[lo:hi]), bits(mine[1]))
+            for r in range(1, world):
+                rlo, rhi = parallel.row_shard(args.lines, world, r)
+                ok = ok and bool(torch.isfinite(torch.view_as_real(co_full[rlo:rhi])).any())
+        per_gpu = value / world
+        strong = {"what": "one scene row-partitioned over N GPUs, results gathered on the device into rank 0",
+                  "ms_total": t_all, "ms_invert": t_inv, "ms_gather": t_gat, "px_per_s": n_px / (t_all * 1e-3),
+                  "efficiency_vs_n1": n_px / (t_all * 1e-3) / (world * per_gpu), "gather_share_of_step": t_gat / t_all,
+                  "efficiency_note": "against N x the per-GPU rate of the weak leg of this run",
+                  "collective": "ncclSend/ncclRecv (torch.distributed batch_isend_irecv) into row slices of rank 0's result",
+                  "gather_bytes_into_rank0": 2 * 16 * (n_px - (parallel.row_shard(args.lines, world, 0)[1]) * args.samples),
+                  "self_check": bool(ok)}
+        del full, blk, res
+        torch.cuda.empty_cache()
+        inc = s_co = s_cr = anc = out_co = out_cr = None
 
     # ---- end to end through the public API with pinned host arrays ----
     e2e = None
+    cpu_src = gpu_host = None
     if not args.no_e2e:
+        if inc is None:
+            inc, s_co, s_cr, anc = synth_scene_device(args.lines, args.samples, args.seed + rank, scene=args.scene)
         host = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in (inc, s_co, s_cr, anc)]
         for h, t in zip(host, (inc, s_co, s_cr, anc)):
             h.copy_(t)
@@ -347,12 +619,13 @@ def main():
         d2h = 2 * n_px * 16
         del inc, s_co, s_cr, anc, out_co, out_cr
         torch.cuda.empty_cache()
-        import warnings
+        last = {}
 
-        def e2e_step():
+        def e2e_step(arrs=(h_inc, h_co, h_cr, h_anc)):
             with warnings.catch_warnings():
                 warnings.simplefilter("ignore")
-                co, dual = windspeed.invert_from_model(h_inc, h_co, h_cr, ancillary_wind=h_anc, dsig_cr=0.1, model=model)
+                co, dual = windspeed.invert_from_model(arrs[0], arrs[1], arrs[2], ancillary_wind=arrs[3], dsig_cr=0.1, model=model)
+            last["co"], last["dual"] = co, dual
             return float(np.nanmean(np.abs(dual[0])))  # read of the result on the host
 
         e2e_steps = max(1, min(args.steps, 2))
@@ -363,30 +636,71 @@ def main():
         barrier()
         dt = max_over_ranks(time.perf_counter() - t0)
         e2e = {"value": world * n_px * e2e_steps / dt, "unit": "px/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-               "steps": e2e_steps, "api": "xsarsea_b200.windspeed.invert_from_model(numpy f64/c128, pinned host)",
+               "steps": e2e_steps, "api": "xsarsea_b200.windspeed.invert_from_model(numpy f64/c128: pinned host inputs, ordinary "
+               "pageable numpy outputs filled through block-sized pinned staging buffers)",
                "check_mean_abs_dual_line0": chk[-1]}
+        if world == 1:   # the same call with ordinary pageable numpy inputs (staged through pinned blocks too)
+            pg = [np.array(a) for a in (h_inc, h_co, h_cr, h_anc)]
+            t0 = time.perf_counter()
+            e2e_step(pg)
+            e2e["value_pageable_inputs"] = n_px / (time.perf_counter() - t0)
+            del pg
+            # F2 epilogue end to end: float32 speed / direction planes (a quarter of the device->host bytes)
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                k = min(64, args.lines)
+                windspeed.invert_to_speed_dir(h_inc[:k], h_co[:k], h_cr[:k], ancillary_wind=h_anc[:k], model=model,
+                                              ground_heading=190.0, dtype=np.float32)
+                t0 = time.perf_counter()
+                windspeed.invert_to_speed_dir(h_inc, h_co, h_cr, ancillary_wind=h_anc, dsig_cr=0.1, model=model,
+                                              ground_heading=190.0, dtype=np.float32)
+                e2e["value_speed_dir_f32_planes"] = n_px / (time.perf_counter() - t0)
+                e2e["d2h_bytes_per_step_speed_dir_f32"] = 4 * n_px * 4
         cpu_src = (h_inc, h_co, h_cr, h_anc)
-    else:
-        cpu_src = None
+        gpu_host = last
 
-    cpu = None
-    if rank == 0 and not args.no_cpu_baseline:
+    # ---- CPU baseline + parity of the benchmarked configuration (N = 1, rank 0) ----
+    cpu = parity = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and cpu_src is not None:
         step_s = max(1, args.samples // 1000)
 
         def make_sample(lines):
             lines = min(lines, args.lines)
             sl = (slice(0, lines), slice(0, step_s * 1000, step_s))
-            if cpu_src is not None:
-                return tuple(np.ascontiguousarray(a[sl]) for a in cpu_src)
-            return tuple(t[sl].contiguous().cpu().numpy() for t in (inc, s_co, s_cr, anc))
+            return tuple(np.ascontiguousarray(a[sl]) for a in cpu_src)
 
-        port = make_cpu_port()
+        # the oracle gets the LUTs the device inverted with (downloaded): what is compared is the inversion, not the ~1e-16
+        # difference between device and host libm in the LUT values
+        luts = (plan.co_lut.cpu().numpy(), *plan.co_grids, plan.cr_lut.cpu().numpy(), *plan.cr_grids)
+        port = make_cpu_port(luts)
         lines = args.cpu_lines or sized_cpu_lines(port, make_sample, args.cpu_seconds)
         sample = make_sample(lines)
-        r, threads, dt = port(sample)
+        r, threads, dt, o_co, o_cr = port(sample)
         cpu = {"value": r, "unit": "px/s", "cores": threads, "kind": "port", "seconds": dt,
                "sample": f"{sample[0].shape[0]}x{sample[0].shape[1]} px crop across the swath of the same scene, numba "
                          f"gufunc with the reference's decorator arguments (oracle/numba_port.py), JIT excluded"}
+        sl = (slice(0, sample[0].shape[0]), slice(0, step_s * 1000, step_s))
+        with np.errstate(all="ignore"):
+            o_dual = np.where((np.abs(o_co) < 5) | (np.abs(o_cr) < 5), o_co, o_cr)   # windspeed.py:426-428
+        pc, pd = wind_diff(gpu_host["co"][sl], o_co), wind_diff(gpu_host["dual"][sl], o_dual)
+        parity = {"what": "GPU end-to-end result (invert_from_model, this run) vs the CPU oracle (numba port of windspeed.py:183-282 "
+                          "+ merge :426-428) on the pixels the CPU baseline inverts, same LUT arrays on both sides",
+                  "n_px": pc["n_px"], "n_valid": pc["n_valid"],
+                  "nan_pattern_equal": pc["nan_pattern_equal"] and pd["nan_pattern_equal"],
+                  "idx_or_value_mismatch": pc["value_mismatch"] + pd["value_mismatch"],
+                  "outside_tolerance_1e-3ms_0.1deg": pc["outside_tolerance"] + pd["outside_tolerance"],
+                  "max_dspeed": max(pc["max_dspeed"], pd["max_dspeed"]), "max_ddir_deg": max(pc["max_ddir_deg"], pd["max_ddir_deg"]),
+                  "wind_co": pc, "wind_dual": pd,
+                  "note": "value mismatch = |dz| > 1e-9 (an index flip moves z by >= 0.1 m/s); documented near-ties: DESIGN.md section 7"}
+    del cpu_src, gpu_host
+
+    aux = None
+    if rank == 0 and world == 1 and not args.no_aux:
+        torch.cuda.empty_cache()
+        hbm, hbm_src = hbm_peak()
+        aux = run_aux(args, plan, model, pk["measured_tflops"], hbm, hbm_src)
+        aux["fp32_peak"] = {"measured_tflops": pk["measured_tflops"], "nominal_tflops": pk["nominal_tflops"],
+                            "how": "xs_bench_fp32_peak: 148 x 8 CTAs x 256 threads, 16 independent fma.rn.f32x2 chains per thread"}
 
     sys.stdout.flush()
     os.dup2(stdout_fd, 1)
@@ -397,18 +711,10 @@ def main():
             "dtype": "f32 scan + f64 refinement (f64/c128 rasters)", "data": f"synthetic (SURVEY D2 recipe, torch CUDA generator, seed {args.seed}+rank)",
             "config": {"workload": workload_text(args),
                        "l2": "inputs (40 B/px x %.1f Mpx = %.1f GB) exceed L2 (126 MB)" % (n_px / 1e6, 40 * n_px / 1e9),
-                       "sharding": "one scene per GPU, no data-path collective", "lut_build_s": lut_s},
-            "roofline": {"bound": "fp32 cuda-core (FMA pipe)", "kernel": "k_scan_co", "achieved": achieved,
-                         "peak": pk["fp32_tflops"], "unit": "TFLOP/s", "frac": achieved / pk["fp32_tflops"],
-                         "traffic": None if bpp is None else bpp * n_px,
-                         "traffic_note": "DRAM read+write bytes per launch, scaled by pixel count from the ncu --set full "
-                                         "capture of a 10 Mpx launch (profiles/r1_k_scan_co_ncu_raw_selected.csv: %s B/px; "
-                                         "algorithmic 40 B/px in + 16 B/px out + 4 B/px list)" % (None if bpp is None else round(bpp, 1)),
-                         "peak_source": pk["source"], "scan_ms_per_launch": scan_avg_ms,
-                         "flop_per_px": FLOP_PER_PX, "px_per_launch": n_px,
-                         "share_of_step": scan_avg_ms / (ms / args.steps)},
-            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
-            "stats": stats,
+                       "sharding": "one scene per GPU, no data-path collective (see `strong` for one scene over N GPUs)",
+                       "lut_build_s": lut_s},
+            "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "e2e": e2e, "strong": strong, "gpu_launches": launches,
+            "clocks": clocks, "stats": stats, "aux": aux,
         }))
     sys.stdout.flush()
     os.dup2(2, 1)

@@ -65,6 +65,10 @@ const char *xs_last_error(void);
 /* Number of kernel launches issued by this library in this process so far (bench.py's gpu_launches). */
 int64_t xs_launch_count(void);
 
+/* Measurement aid (bench.py): FP32 FMA-pipe peak of the current device in TFLOP/s, measured with a register-resident
+ * fma.rn.f32x2 loop (best of three ~10 ms launches on `stream`, synchronous). */
+int xs_bench_fp32_peak(double *tflops, void *stream);
+
 /* A pair of CUDA events owned by the library, handed to xs_invert through xs_invert_args.scan_timer to time the co-pol
  * scan on the launching stream (bench.py's roofline of the dominant kernel).  One timer per in-flight call: timers, like
  * workspaces, belong to the call and not to the plan, so concurrent calls on one plan do not share any mutable state. */

@@ -1,0 +1,303 @@
+"""Round-2 GPU tests: oracle parity on the benchmarked scenes (BASELINE.json configs[0] and configs[2]), re-entrancy of the
+plans, the fused speed / direction epilogue (row F2), the hostile scene, and the device-resident
+row-sharded gather over NCCL (row E1; needs two GPUs, skipped otherwise)."""
+import os
+import socket
+import sys
+import threading
+import warnings
+
+import numpy as np
+import pytest
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def env():
+    import torch
+
+    assert torch.cuda.is_available()
+    from xsarsea_b200 import _device, _native, windspeed
+    from xsarsea_b200.windspeed import windspeed as impl
+
+    return torch, _device, _native, windspeed, impl
+
+
+def reset_steps(m):
+    for k, v in dict(inc_step=0.1, wspd_step=0.1, phi_step=1.0, inc_step_lr=1.0, wspd_step_lr=0.2, phi_step_lr=2.5).items():
+        setattr(m, k, v)
+    return m
+
+
+def default_plan(ws, impl):
+    plan = impl._get_plan(reset_steps(ws.get_model("gmf_cmod5n")), reset_steps(ws.get_model("gmf_s1_v2")), 0.1, {})
+    assert plan.co_lut.shape == (501, 499, 181) and plan.cr_lut.shape == (501, 771)
+    return plan
+
+
+def oracle_sample(plan, idx, inc, s_co, s_cr, anc, dsig=0.1):
+    """oracle.invert (windspeed.py:183-282) on the pixels `idx`, with the LUTs the device inverted with (downloaded) and the
+    dB prologue of windspeed.py:126-128 done by numpy."""
+    h = lambda t: t.reshape(-1)[idx].cpu().numpy()
+    kw = dict(co_lut=plan.co_lut.cpu().numpy(), inc_grid=plan.co_grids[0], wspd_grid=plan.co_grids[1], phi_grid=plan.co_grids[2])
+    if s_cr is not None:
+        kw.update(cr_lut=plan.cr_lut.cpu().numpy(), inc_cr_grid=plan.cr_grids[0], wspd_cr_grid=plan.cr_grids[1])
+    with np.errstate(all="ignore"):
+        co_db = 10 * np.log10(h(s_co) + 1e-15)
+        cr_db = 10 * np.log10(h(s_cr) + 1e-15) if s_cr is not None else np.full(idx.numel(), np.nan)
+        return oracle.invert(h(inc), co_db, cr_db, dsig, h(anc), **kw)
+
+
+def assert_same_winds(got, want, what):
+    """NaN pattern identical; values identical up to 1e-9 except ulp-level near-ties of the fused log10 prologue
+    (at most 1e-4 of the pixels)."""
+    assert np.array_equal(np.isnan(got), np.isnan(want)), what
+    ok = ~np.isnan(want)
+    bad = np.abs(got[ok] - want[ok]) > 1e-9
+    assert bad.mean() <= 1e-4, f"{what}: {bad.sum()} of {bad.size} pixels differ"
+
+
+def test_config3_full_iw_scene_sampled_against_the_oracle(env):
+    """BASELINE.json configs[2], the benchmarked workload (bench.py's scene recipe, dual-pol, default LUTs): 24 000 pixels
+    sampled over a 4 000-line strip of the scene equal the oracle, index for index."""
+    torch, D, nat, ws, impl = env
+    import bench
+
+    plan = default_plan(ws, impl)
+    inc, s_co, s_cr, anc = bench.synth_scene_device(4000, 25000, 0)
+    co, du, ic, ix = plan.invert(inc, s_co, s_cr, 0.1, anc, merge_dual=False, want_idx=True)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    idx = torch.randint(0, inc.numel(), (24000,), generator=g, device="cuda")
+    o_co, o_du, o_ic, o_ix = oracle_sample(plan, idx, inc, s_co, s_cr, anc)
+    h = lambda t: t.reshape(-1)[idx].cpu().numpy()
+    assert_same_winds(h(co), o_co, "wind_co")
+    assert_same_winds(h(du), o_du, "wind_dual")
+    assert (h(ic) != o_ic).mean() <= 1e-4 and (h(ix) != o_ix).mean() <= 1e-4
+    # merged output (windspeed.py:426-428) of the same call path the bench times
+    _, merged, _, _ = plan.invert(inc, s_co, s_cr, 0.1, anc, merge_dual=True)
+    with np.errstate(invalid="ignore"):
+        want = np.where((np.abs(o_co) < 5) | (np.abs(o_du) < 5), o_co, o_du)
+    assert_same_winds(h(merged), want, "merged dual")
+
+
+def test_config1_scene_sampled_against_the_oracle(env):
+    """BASELINE.json configs[0] (1000 x 1000 co-pol, default cmod5n LUT): 20 000 sampled pixels equal the oracle."""
+    torch, D, nat, ws, impl = env
+    plan = default_plan(ws, impl)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    H = W = 1000
+    f64 = dict(device="cuda", dtype=torch.float64)
+    inc = (17.5 + 32 * torch.arange(W, **f64) / (W - 1)).expand(H, W).contiguous()
+    w = 2 + 23 * torch.rand(H, W, generator=g, **f64)
+    p = 360 * torch.rand(H, W, generator=g, **f64)
+    s_co = D.gmf_eval(nat.GMF_IDS["gmf_cmod5n"], inc, w, p) * torch.exp(0.05 * torch.randn(H, W, generator=g, **f64))
+    anc = torch.polar((w + 2 * torch.randn(H, W, generator=g, **f64)).abs(), torch.deg2rad(p + 20 * torch.randn(H, W, generator=g, **f64)))
+    co, _, ic, _ = plan.invert(inc, s_co, None, 0.1, anc, want_idx=True)
+    idx = torch.randint(0, H * W, (20000,), generator=g, device="cuda")
+    o_co, _, o_ic, _ = oracle_sample(plan, idx, inc, s_co, None, anc)
+    assert_same_winds(co.reshape(-1)[idx].cpu().numpy(), o_co, "wind_co")
+    assert (ic.reshape(-1)[idx].cpu().numpy() != o_ic).mean() <= 1e-4
+
+
+def test_hostile_scene_fast_equals_fp64(env):
+    """bench.py's hostile scene (random incidence per pixel, +-15 dB sea/land runs, ancillary wind 10 m/s and 90 deg off,
+    20 % NaN): the FP32 scan + refinement gives exactly the indices of the exhaustive FP64 kernel."""
+    torch, D, nat, ws, impl = env
+    import bench
+
+    plan = default_plan(ws, impl)
+    inc, s_co, s_cr, anc = bench.synth_scene_device(60, 25000, 3, scene="hostile")
+    a, ax, ia, ixa = plan.invert(inc, s_co, s_cr, 0.1, anc, merge_dual=True, want_idx=True)
+    st = plan.last_stats()
+    b, bx, ib, ixb = plan.invert(inc, s_co, s_cr, 0.1, anc, merge_dual=True, want_idx=True, mode=nat.MODE_FP64)
+    assert torch.equal(ia, ib) and torch.equal(ixa, ixb)
+    bits = lambda z: torch.view_as_real(z).contiguous().view(torch.int64)
+    assert torch.equal(bits(a), bits(b)) and torch.equal(bits(ax), bits(bx))
+    n_co = int((ia >= 0).sum())
+    assert st["scan_pixels"] + st["exhaustive_pixels"] == n_co and 0.7 * inc.numel() < n_co < 0.9 * inc.numel()
+
+
+def test_concurrent_calls_on_shared_plans(env):
+    """SURVEY.md section 8 B2 / ADVICE r1: the operator is called concurrently by dask's threaded scheduler.  Four host
+    threads, each on its own CUDA stream, alternate between two model pairs through the numpy-level operator while the
+    plan cache holds a single plan (every switch evicts the plan another thread may be using): results must be
+    bit-identical to the serial ones."""
+    torch, D, nat, ws, impl = env
+    kw = dict(inc_step_lr=2.0, wspd_step_lr=1.0, phi_step_lr=10.0, inc_step=0.5, wspd_step=0.25, phi_step=2.5)
+    rng = np.random.default_rng(5)
+    n = 40000
+    inc = rng.uniform(18, 48, n)
+    w, p = rng.uniform(2, 25, n), rng.uniform(0, 360, n)
+    with np.errstate(all="ignore"):
+        co_db = 10 * np.log10(oracle.gmf_eval("gmf_cmod5n", inc, w, p) * np.exp(rng.normal(0, 0.05, n)) + 1e-15)
+        cr_db = 10 * np.log10(oracle.gmf_eval("gmf_s1_v2", inc, w) * np.exp(rng.normal(0, 0.05, n)) + 1e-15)
+    anc = (w + rng.normal(0, 2, n)) * np.exp(1j * np.deg2rad(p + rng.normal(0, 20, n)))
+    dsig = np.full(n, 0.1)
+    pairs = [(ws.get_model("gmf_cmod5n"), ws.get_model("gmf_s1_v2")), (ws.get_model("gmf_cmodifr2"), ws.get_model("gmf_rs2_v2"))]
+    serial = [impl._invert_from_model_numpy(m, 0.1, dict(kw), inc, co_db, cr_db, dsig, anc) for m in pairs]
+    old_max, impl._PLAN_CACHE_MAX = impl._PLAN_CACHE_MAX, 1
+    errors, results = [], {}
+
+    def work(tid):
+        try:
+            with torch.cuda.stream(torch.cuda.Stream()):
+                for it in range(6):
+                    k = (tid + it) % 2
+                    results[(tid, it)] = (k, impl._invert_from_model_numpy(pairs[k], 0.1, dict(kw), inc, co_db, cr_db, dsig, anc))
+        except Exception as e:  # pragma: no cover
+            errors.append(e)
+
+    try:
+        threads = [threading.Thread(target=work, args=(t,)) for t in range(4)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+    finally:
+        impl._PLAN_CACHE_MAX = old_max
+    assert not errors, errors
+    assert len(results) == 24
+    for (tid, it), (k, (oc, ox)) in results.items():
+        assert np.array_equal(oc, serial[k][0], equal_nan=True) and np.array_equal(ox, serial[k][1], equal_nan=True), (tid, it)
+
+
+def test_speed_direction_epilogue(env):
+    """Row F2: the fused epilogue equals the callers' post-processing of the complex result
+    (docs/examples/windspeed_retrieval_L1.ipynb cell 33: np.abs, (90 - np.angle(deg) + ground_heading) % 360)."""
+    torch, D, nat, ws, impl = env
+    kw = dict(inc_step_lr=2.0, wspd_step_lr=1.0, phi_step_lr=10.0, inc_step=0.5, wspd_step=0.25, phi_step=2.5)
+    rng = np.random.default_rng(8)
+    shape = (50, 120)
+    inc = rng.uniform(18, 48, shape)
+    w, p = rng.uniform(2, 25, shape), rng.uniform(0, 360, shape)
+    s_co = oracle.gmf_eval("gmf_cmod5n", inc, w, p) * np.exp(rng.normal(0, 0.05, shape))
+    s_cr = oracle.gmf_eval("gmf_s1_v2", inc, w) * np.exp(rng.normal(0, 0.05, shape))
+    anc = (w + rng.normal(0, 2, shape)) * np.exp(1j * np.deg2rad(p + rng.normal(0, 20, shape)))
+    s_co[rng.uniform(size=shape) < 0.02] = np.nan
+    inc[0, :5] = np.nan
+    gh = rng.uniform(0, 360, shape)
+    model = ("gmf_cmod5n", "gmf_s1_v2")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        co, dual = ws.invert_from_model(inc, s_co, s_cr, ancillary_wind=anc, model=model, **kw)
+        (sp_co, d_co), (sp_du, d_du) = ws.invert_to_speed_dir(inc, s_co, s_cr, ancillary_wind=anc, model=model, ground_heading=gh, **kw)
+        (sa_co, da_co), _ = ws.invert_to_speed_dir(inc, s_co, s_cr, ancillary_wind=anc, model=model, **kw)       # antenna convention
+        (s32, d32), _ = ws.invert_to_speed_dir(inc, s_co, s_cr, ancillary_wind=anc, model=model, ground_heading=190.0,
+                                               dtype=np.float32, **kw)
+        mono = ws.invert_to_speed_dir(inc, s_co, ancillary_wind=anc, model="gmf_cmod5n", ground_heading=gh, **kw)
+        xonly = ws.invert_to_speed_dir(inc, s_cr, model="gmf_s1_v2", **kw)
+        x_ref = ws.invert_from_model(inc, s_cr, model="gmf_s1_v2", **kw)
+        t = lambda a: torch.from_numpy(a).cuda()
+        (ts, td), _ = ws.invert_to_speed_dir(t(inc), t(s_co), t(s_cr), ancillary_wind=t(anc), model=model, ground_heading=t(gh), **kw)
+    for z, sp, dr in ((co, sp_co, d_co), (dual, sp_du, d_du)):
+        assert sp.shape == shape and sp.dtype == np.float64
+        np.testing.assert_allclose(sp, np.abs(z), rtol=1e-13, atol=0, equal_nan=True)
+        want = (90 - np.angle(z, deg=True) + gh) % 360
+        d = np.abs(dr - want)
+        d = np.minimum(d, 360 - d)          # 359.999.. vs 0 at the wrap
+        assert np.array_equal(np.isnan(dr), np.isnan(want)) and np.nanmax(d) < 1e-9
+        assert np.nanmin(dr) >= 0 and np.nanmax(dr) <= 360
+    np.testing.assert_allclose(sa_co, np.abs(co), rtol=1e-13, equal_nan=True)
+    np.testing.assert_allclose(da_co, np.angle(co, deg=True), rtol=0, atol=1e-9, equal_nan=True)
+    assert s32.dtype == np.float32 and d32.dtype == np.float32
+    np.testing.assert_allclose(s32, np.abs(co).astype(np.float32), rtol=1e-6, equal_nan=True)
+    np.testing.assert_allclose(mono[0], sp_co, rtol=0, atol=0, equal_nan=True)
+    np.testing.assert_allclose(mono[1], d_co, rtol=0, atol=0, equal_nan=True)
+    np.testing.assert_array_equal(xonly, x_ref)
+    assert ts.is_cuda and np.array_equal(ts.cpu().numpy(), sp_co, equal_nan=True) and np.array_equal(td.cpu().numpy(), d_co, equal_nan=True)
+
+
+def test_streamed_blocks_pageable_and_pinned_inputs(env, monkeypatch):
+    """The host path stages pageable inputs and all outputs through block-sized pinned buffers: results must not depend on
+    the block size, on the inputs being page-locked, or on a previous call's staging buffers being reused."""
+    torch, D, nat, ws, impl = env
+    kw = dict(inc_step_lr=2.0, wspd_step_lr=1.0, phi_step_lr=10.0, inc_step=0.5, wspd_step=0.25, phi_step=2.5)
+    rng = np.random.default_rng(2)
+    shape = (37, 211)
+    inc = rng.uniform(18, 48, shape)
+    w, p = rng.uniform(2, 25, shape), rng.uniform(0, 360, shape)
+    s_co = oracle.gmf_eval("gmf_cmod5n", inc, w, p)
+    s_cr = oracle.gmf_eval("gmf_s1_v2", inc, w)
+    anc = w * np.exp(1j * np.deg2rad(p + rng.normal(0, 20, shape)))
+    model = ("gmf_cmod5n", "gmf_s1_v2")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ref = ws.invert_from_model(inc, s_co, s_cr, ancillary_wind=anc, model=model, **kw)
+        monkeypatch.setattr(impl, "BLOCK_PIXELS", 1000)       # 8 blocks, the last one ragged
+        for _ in range(2):
+            got = ws.invert_from_model(inc, s_co, s_cr, ancillary_wind=anc, model=model, **kw)
+            assert all(np.array_equal(a, b, equal_nan=True) for a, b in zip(got, ref))
+        pin = lambda a: torch.from_numpy(a).pin_memory().numpy()
+        got = ws.invert_from_model(pin(inc), pin(s_co), pin(s_cr), ancillary_wind=pin(anc), model=model, **kw)
+        assert all(np.array_equal(a, b, equal_nan=True) for a, b in zip(got, ref))
+        sd = ws.invert_to_speed_dir(inc, s_co, s_cr, ancillary_wind=anc, model=model, ground_heading=10.0, **kw)
+    np.testing.assert_allclose(sd[1][0], np.abs(ref[1]), rtol=1e-13, equal_nan=True)
+
+
+def _nccl_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+
+    sys.path.insert(0, ROOT)
+    import bench
+    from xsarsea_b200 import parallel, windspeed
+    from xsarsea_b200.windspeed import windspeed as impl
+
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world,
+                            device_id=torch.device("cuda", rank))
+    try:
+        kw = dict(inc_step_lr=2.0, wspd_step_lr=1.0, phi_step_lr=10.0, inc_step=0.5, wspd_step=0.25, phi_step=2.5)
+        plan = impl._get_plan(windspeed.get_model("gmf_cmod5n"), windspeed.get_model("gmf_s1_v2"), 0.1, kw)
+        lines = 101
+        full = bench.synth_scene_device(lines, 700, 7, 20.0, 45.0)          # same seed on every rank: the same scene
+        lo, hi = parallel.row_shard(lines, world, rank)
+        res = parallel.invert_rows_resident(plan, [t[lo:hi] for t in full], lines, lo, hi, dst=0, merge_dual=True)
+        ok = True
+        if rank == 0:
+            single = plan.invert(*full[:3], 0.1, full[3], merge_dual=True)
+            bits = lambda z: torch.view_as_real(z).contiguous().view(torch.int64)
+            ok = torch.equal(bits(res[0]), bits(single[0])) and torch.equal(bits(res[1]), bits(single[1]))
+        else:
+            ok = res == (None, None)
+        # the host-array API on top of it
+        h = [t.cpu().numpy() for t in full]
+        import warnings as w
+
+        with w.catch_warnings():
+            w.simplefilter("ignore")
+            out = parallel.invert_sharded(h[0], h[1], h[2], ancillary_wind=h[3], model=("gmf_cmod5n", "gmf_s1_v2"), gather=0, **kw)
+            if rank == 0:
+                one = windspeed.invert_from_model(h[0], h[1], h[2], ancillary_wind=h[3], model=("gmf_cmod5n", "gmf_s1_v2"), **kw)
+                ok = ok and all(np.array_equal(a, b, equal_nan=True) for a, b in zip(out, one))
+            else:
+                ok = ok and out is None
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_row_sharded_gather_nccl_world2(env):
+    """Row E1: one scene row-partitioned over 2 GPUs, results gathered on the device over NCCL into rank 0: bit-identical
+    to the single-GPU inversion."""
+    torch = env[0]
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=300) for _ in procs)
+    for p in procs:
+        p.join(60)
+    assert res == [(0, True), (1, True)]

@@ -171,10 +171,11 @@ def test_row_shard_partition():
 
 
 def _gloo_worker(rank, world, port, q):
+    import torch
     import torch.distributed as dist
 
     sys.path.insert(0, ROOT)
-    from xsarsea_b200.parallel import invert_sharded, row_shard
+    from xsarsea_b200.parallel import invert_rows_resident, invert_sharded, row_shard
 
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
     try:
@@ -185,19 +186,37 @@ def _gloo_worker(rank, world, port, q):
         seen = {}
 
         def stub(i, a, b=None, ancillary_wind=None, dsig_cr=0.1, model=None):
+            assert isinstance(i, torch.Tensor)      # the sharded path hands the backend's tensors to the inversion
             seen["rows"] = i.shape[0]
             co = (i + a) * ancillary_wind
             return (co, co * dsig_cr + b) if b is not None else co
 
-        full = invert_sharded(inc, s0, s1, ancillary_wind=anc, dsig_cr=0.5, model="m", _invert=stub)
+        full = invert_sharded(inc, s0, s1, ancillary_wind=anc, dsig_cr=0.5, model="m", gather="all", _invert=stub)
         lo, hi = row_shard(11, world, rank)
         ok = seen["rows"] == hi - lo
         want_co = (inc + s0) * anc
         ok &= np.array_equal(full[0], want_co) and np.array_equal(full[1], want_co * 0.5 + s1)
-        only0 = invert_sharded(inc, s0, ancillary_wind=anc, model="m", gather=0, _invert=stub)
+        only0 = invert_sharded(inc, s0, ancillary_wind=anc, model="m", _invert=stub)          # default: rank 0 gets the result
         ok &= (only0 is None) if rank != 0 else np.array_equal(only0, want_co)
+        only1 = invert_sharded(inc, s0, s1, ancillary_wind=anc, dsig_cr=0.5, model="m", gather=1, _invert=stub)
+        ok &= (only1 is None) if rank != 1 else (np.array_equal(only1[0], want_co) and np.array_equal(only1[1], want_co * 0.5 + s1))
         mine = invert_sharded(inc, s0, ancillary_wind=anc, model="m", gather=None, _invert=stub)
         ok &= np.array_equal(mine, want_co[lo:hi])
+        # fewer lines than ranks: a rank without rows still takes part in the gather
+        one = invert_sharded(inc[:1], s0[:1], ancillary_wind=anc[:1], model="m", gather="all", _invert=stub)
+        ok &= np.array_equal(one, want_co[:1])
+        # the device-resident form bench.py times (here: CPU tensors, a stub in place of plan.invert)
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a[lo:hi]))
+
+        def stub_rows(i, a, b, d, c, oc, ox):
+            oc.copy_((i + a) * c)
+            ox.copy_((i + a) * c * d + b)
+
+        co_f, cr_f = invert_rows_resident(None, (t(inc), t(s0), t(s1), t(anc)), 11, lo, hi, dst=0, dsig_cr=0.5, _invert=stub_rows)
+        if rank == 0:
+            ok &= np.array_equal(co_f.numpy(), want_co) and np.array_equal(cr_f.numpy(), want_co * 0.5 + s1)
+        else:
+            ok &= co_f is None and cr_f is None
         q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()

@@ -41,7 +41,7 @@ GMF_IDS = {
 }
 
 EXPORTS = [
-    "xs_abi_version", "xs_last_error", "xs_launch_count", "xs_gmf_eval", "xs_lut_build", "xs_lut_interp_axis",
+    "xs_abi_version", "xs_last_error", "xs_launch_count", "xs_bench_fp32_peak", "xs_gmf_eval", "xs_lut_build", "xs_lut_interp_axis",
     "xs_lut_to_db", "xs_lut_to_linear", "xs_plan_create", "xs_plan_destroy", "xs_invert_workspace_bytes",
     "xs_invert", "xs_timer_create", "xs_timer_destroy", "xs_timer_elapsed_ms", "xs_detrend",
     "xs_dsig", "xs_dsig_wspd", "xs_nesz_flatten_workspace_bytes", "xs_nesz_flatten",
@@ -137,6 +137,8 @@ def load():
         L.xs_last_error.argtypes = []
         L.xs_launch_count.restype = i64
         L.xs_launch_count.argtypes = []
+        L.xs_bench_fp32_peak.restype = i32
+        L.xs_bench_fp32_peak.argtypes = [ctypes.POINTER(dbl), vp]
         L.xs_gmf_eval.restype = i32
         L.xs_gmf_eval.argtypes = [i32, i32, vp, vp, vp, vp, i64, vp]
         L.xs_lut_build.restype = i32

@@ -444,10 +444,13 @@ def _invert(inc, sigma0, sigma0_dual, ancillary_wind, dsig_co, dsig_cr, model, k
 
 def _invert_dask(models, dsig_co, kwargs, inc, sigma0_co, sigma0_cr, dsig_cr, ancillary_wind, template):
     """dask-backed inputs: lazy `da.apply_gufunc` over blocks with the sample axis as core dimension, like
-    windspeed.py:356-364; every block goes through the numpy-level operator (and hence the GPU)."""
-    import dask.array as da  # pragma: no cover - dask is absent from the build image
+    windspeed.py:356-364; every block goes through the numpy-level operator (and hence the GPU).  dask and xarray are
+    absent from the build image: tests/test_dask_stub.py executes this path with minimal stand-ins for both."""
+    import dask.array as da
     import xarray as xr
 
+    if not _xr.is_labelled(template):  # the result mirrors the first labelled input
+        template = next(v for v in (sigma0_co, sigma0_cr, inc, ancillary_wind, dsig_cr) if v is not None and _xr.is_labelled(v))
     nan = template * np.nan
     sigma0_co = nan if sigma0_co is None else sigma0_co
     sigma0_cr = nan if sigma0_cr is None else sigma0_cr
