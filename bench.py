@@ -292,8 +292,9 @@ def timeit(fn, warm=3, reps=5, inner=1):
     return float(np.min(ts)), float(np.mean(ts))
 
 
-def wind_diff(got, want):
-    """Parity statistics of two complex wind rasters (windspeed.py:183-282 outputs)."""
+def wind_diff(got, want, tie=None):
+    """Parity statistics of two complex wind rasters (windspeed.py:183-282 outputs).  `tie` marks pixels of a documented
+    near-tie; they are counted separately."""
     got, want = np.asarray(got).ravel(), np.asarray(want).ravel()
     nan_g, nan_w = np.isnan(got.real) | np.isnan(got.imag), np.isnan(want.real) | np.isnan(want.imag)
     ok = ~(nan_g | nan_w)
@@ -302,9 +303,18 @@ def wind_diff(got, want):
         dspd = np.abs(np.abs(g) - np.abs(w))
         ddir = np.abs(np.angle(g * np.conj(w), deg=True))
         ddir[(np.abs(w) == 0) | (np.abs(g) == 0)] = 0
+    bad = np.abs(g - w) > 1e-9
+    if tie is not None:   # documented near-tie: pixels sitting on the merge threshold
+        t = tie.ravel()[ok]
+        n_tie = int((bad & t).sum())
+        bad &= ~t
+        dspd, ddir = dspd[~t], ddir[~t]
+    else:
+        n_tie = 0
     return dict(n_px=int(got.size), n_valid=int(ok.sum()), nan_pattern_equal=bool(np.array_equal(nan_g, nan_w)),
-                value_mismatch=int((np.abs(g - w) > 1e-9).sum()), outside_tolerance=int(((dspd > 1e-3) | (ddir > 0.1)).sum()),
-                max_dspeed=float(dspd.max()) if g.size else 0.0, max_ddir_deg=float(ddir.max()) if g.size else 0.0)
+                value_mismatch=int(bad.sum()), merge_threshold_ties=n_tie,
+                outside_tolerance=int(((dspd > 1e-3) | (ddir > 0.1)).sum()),
+                max_dspeed=float(dspd.max()) if dspd.size else 0.0, max_ddir_deg=float(ddir.max()) if ddir.size else 0.0)
 
 
 def run_aux(args, plan, model, peak_tflops, hbm_gbs, hbm_src):
@@ -641,6 +651,7 @@ def main():
                "check_mean_abs_dual_line0": chk[-1]}
         if world == 1:   # the same call with ordinary pageable numpy inputs (staged through pinned blocks too)
             pg = [np.array(a) for a in (h_inc, h_co, h_cr, h_anc)]
+            e2e_step(pg)   # the first call page-locks the input staging blocks (1.3 GB, ~2 s): not timed, like every warm-up
             t0 = time.perf_counter()
             e2e_step(pg)
             e2e["value_pageable_inputs"] = n_px / (time.perf_counter() - t0)
@@ -648,7 +659,7 @@ def main():
             # F2 epilogue end to end: float32 speed / direction planes (a quarter of the device->host bytes)
             with warnings.catch_warnings():
                 warnings.simplefilter("ignore")
-                k = min(64, args.lines)
+                k = min(2 * 672, args.lines)   # two full blocks: the staging buffers of this output format get page-locked here
                 windspeed.invert_to_speed_dir(h_inc[:k], h_co[:k], h_cr[:k], ancillary_wind=h_anc[:k], model=model,
                                               ground_heading=190.0, dtype=np.float32)
                 t0 = time.perf_counter()
@@ -682,12 +693,17 @@ def main():
         sl = (slice(0, sample[0].shape[0]), slice(0, step_s * 1000, step_s))
         with np.errstate(all="ignore"):
             o_dual = np.where((np.abs(o_co) < 5) | (np.abs(o_cr) < 5), o_co, o_cr)   # windspeed.py:426-428
-        pc, pd = wind_diff(gpu_host["co"][sl], o_co), wind_diff(gpu_host["dual"][sl], o_dual)
+            # the merge compares |wind| with 5 m/s; 5.0 is a node of both wspd grids, and numpy's abs(w * exp(1j * phi)) of a
+            # wind sitting on that node is 5 -+ 1 ulp depending on libm: there the merged output may legitimately pick the
+            # other branch
+            tie = (np.abs(np.abs(o_co) - 5) < 1e-9) | (np.abs(np.abs(o_cr) - 5) < 1e-9)
+        pc, pd = wind_diff(gpu_host["co"][sl], o_co), wind_diff(gpu_host["dual"][sl], o_dual, tie)
         parity = {"what": "GPU end-to-end result (invert_from_model, this run) vs the CPU oracle (numba port of windspeed.py:183-282 "
                           "+ merge :426-428) on the pixels the CPU baseline inverts, same LUT arrays on both sides",
                   "n_px": pc["n_px"], "n_valid": pc["n_valid"],
                   "nan_pattern_equal": pc["nan_pattern_equal"] and pd["nan_pattern_equal"],
                   "idx_or_value_mismatch": pc["value_mismatch"] + pd["value_mismatch"],
+                  "merge_threshold_ties": pd["merge_threshold_ties"],
                   "outside_tolerance_1e-3ms_0.1deg": pc["outside_tolerance"] + pd["outside_tolerance"],
                   "max_dspeed": max(pc["max_dspeed"], pd["max_dspeed"]), "max_ddir_deg": max(pc["max_ddir_deg"], pd["max_ddir_deg"]),
                   "wind_co": pc, "wind_dual": pd,

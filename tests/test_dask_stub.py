@@ -10,6 +10,7 @@ import pytest
 
 import _stubs
 import oracle
+import xsarsea_b200  # noqa: F401  (imported BEFORE the stand-ins are installed: the package must not mistake them for xarray)
 from oracle import lut as olut
 
 KW = dict(inc_step_lr=2.0, wspd_step_lr=1.0, phi_step_lr=10.0, inc_step=1.0, wspd_step=0.5, phi_step=5.0)
@@ -102,11 +103,19 @@ def test_dask_xarray_container_paths_on_the_gpu(monkeypatch):
     da, xr = _stubs.install(monkeypatch)
     from xsarsea_b200 import windspeed as ws
 
+    from xsarsea_b200.windspeed import windspeed as impl
+
     def numpy_call(inc, s_co, s_cr, anc, model):
         if s_co is None:
             return ws.invert_from_model(inc, s_cr, model=model, **KW)
         if s_cr is None:
             return ws.invert_from_model(inc, s_co, ancillary_wind=anc, model=model, **KW)
-        return ws.invert_from_model(inc, s_co, s_cr, ancillary_wind=anc, dsig_cr=0.1, model=model, **KW)
+        # dual-pol: the lazy branch merges on the host (xr.where of numpy's abs) like the reference, the eager numpy branch
+        # merges in the kernel; where a wind speed sits exactly on the 5 m/s node the two abs() may round differently
+        # (DESIGN.md section 7 item 1), so the expectation is built from the unmerged operator output
+        with np.errstate(all="ignore"):
+            oc, ox = impl._invert_from_model_numpy(tuple(ws.get_model(m) for m in model), 0.1, dict(KW), inc, 10 * np.log10(s_co + 1e-15),
+                                                   10 * np.log10(s_cr + 1e-15), np.full(inc.shape, 0.1), anc)
+            return oc, np.where((np.abs(oc) < 5) | (np.abs(ox) < 5), oc, ox)
 
     run_all(ws, da, xr, numpy_call)

@@ -81,7 +81,13 @@ def test_config3_full_iw_scene_sampled_against_the_oracle(env):
     _, merged, _, _ = plan.invert(inc, s_co, s_cr, 0.1, anc, merge_dual=True)
     with np.errstate(invalid="ignore"):
         want = np.where((np.abs(o_co) < 5) | (np.abs(o_du) < 5), o_co, o_du)
-    assert_same_winds(h(merged), want, "merged dual")
+        # 5.0 is a node of both wspd grids: numpy's abs(w * exp(1j * phi)) of a wind on that node is 5 -+ 1 ulp depending
+        # on libm, so there the merge may legitimately pick the other branch
+        tie = (np.abs(np.abs(o_co) - 5) < 1e-9) | (np.abs(np.abs(o_du) - 5) < 1e-9)
+    got = h(merged)
+    assert 0 < tie.sum() < 0.02 * tie.size
+    assert_same_winds(got[~tie], want[~tie], "merged dual")
+    assert np.all(np.isclose(got[tie], o_co[tie], atol=1e-9) | np.isclose(got[tie], o_du[tie], atol=1e-9))
 
 
 def test_config1_scene_sampled_against_the_oracle(env):
