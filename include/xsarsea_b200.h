@@ -197,7 +197,8 @@ int xs_invert(const xs_plan *plan, const xs_invert_args *args, void *stream);
  * the stream has reached the end of the call): [0] co-pol tiles, [1] pixels sent to the exhaustive FP64 scan,
  * [2] co-pol pixels settled by the FP32 scan (+ refinement), [3] (lane, chunk) cells re-examined by the refinement,
  * [4..7], [9], [10] clock64 sums per phase when an instrumented scan variant is selected (development aid), else 0,
- * [8] tile hand-out cursor, [11] pixels the refinement settled in FP64 (more than one candidate inside the band). */
+ * [8] tile hand-out cursor, [11] pixels the refinement settled in FP64 (more than one candidate inside the band),
+ * [12] pixels left to the second refinement pass, [13] record positions scanned in shared-sigma0 mode. */
 
 /* ---- detrend -------------------------------------------------------------------------------- */
 

@@ -1,4 +1,4 @@
-"""CPU check of the error bound of the centred FP32 scan (`k_scan_co` with kMath 5).
+"""CPU check of the error bounds of the centred FP32 scan (`k_scan_co`, both modes).
 
 The kernel's exactness rests on `E >= |J''_fp32 - J''_exact|` for every candidate that can still win.  This test
 re-creates the kernel's FP32 operation sequence in numpy (every FP32 operation is evaluated exactly in float64 -- a
@@ -37,7 +37,7 @@ def slabs():
 
 
 def kernel_E(m32, sc_abs, amag, lmax, wmax):
-    """Mirror of the kMath == 5 branch of the settle section of k_scan_co (float arithmetic there, float64 here)."""
+    """Mirror of the band section of k_scan_co (float arithmetic there, float64 here): bound of the full centred form."""
     A, W = amag, wmax * 1.0000002
     T = W * A + 0.25 * W * W
     SC = sc_abs
@@ -104,36 +104,57 @@ def test_centred_scan_error_bound(slabs, spread_db):
     assert 0 < worst <= 1.0
 
 
-def test_direct_form_error_bound(slabs):
-    """Same check for the direct form (XS_SCAN_VARIANT=99): d = L32 - s32, t = fma(-w/2, g, w^2/4), J' = fma(d, d, t) with
-    E = 1.5 u [3T + 2D(Lmax + |q| + D) + |m32| + A^2/4 + T]."""
+def test_shared_sigma0_mode_band_and_second_filter(slabs):
+    """Shared-sigma0 mode of k_scan_co: the scanned cost leaves k lambda out (J_a = fma(-w/2, g, M)) and the band is widened
+    by 2 |sigma| Lam; k_refine_easy then keeps only the members within 2 efp of the smallest FULL FP32 cost.  Checked: the
+    exact argmin (first minimum, ties included) is a member of the wide band, survives the second filter, and every
+    candidate of the wide band has |lambda| <= Lam (which is what both bounds assume)."""
     lut_db, gw, gp = slabs
     dsig = 0.1
-    rng = np.random.default_rng(3)
+    rng = np.random.default_rng(21)
     cphi, sphi = np.cos(np.radians(gp)), np.sin(np.radians(gp))
     nwh32, w2q32 = f32(-0.5 * gw), f32(0.25 * gw * gw)
+    n_checked = 0
     for b in range(lut_db.shape[0]):
         Ls = lut_db[b] / dsig
         L32 = f32(Ls)
         lmax = np.abs(L32).max() * 1.0000002
-        for trial in range(12):
-            s = rng.uniform(-35.0, 5.0)
-            a_w, a_p = rng.uniform(0.0, 60.0), rng.uniform(0.0, np.pi)
+        for trial in range(30):
+            kind = trial % 5
+            iw, ip = rng.integers(0, gw.size), rng.integers(0, gp.size)
+            s = lut_db[b, iw, ip] if kind == 0 else rng.uniform(-35.0, 5.0)
+            if kind == 4:
+                s = rng.uniform(-45.0, 12.0)                                  # outside the LUT range: large lambda at the minimum
+            a_w, a_p = (gw[iw], np.radians(gp[ip])) if kind == 0 else (rng.uniform(0.0, 40.0), rng.uniform(0.0, np.pi))
             qa, qb = a_w * np.cos(a_p), a_w * np.sin(a_p)
-            nq32 = float(F32(-(s / dsig)))
+            sc = rng.uniform(-1.0, 1.0) * 10.0 ** rng.uniform(-4, -1.5)       # |sigma| of a sorted list: 1e-4 .. 3e-2
+            cs = float(F32(s / dsig - sc))
+            sc = s / dsig - cs
             g64 = qa * cphi + qb * sphi
-            d32 = f32(L32 + nq32)
-            t32 = fma32(nwh32[:, None], f32(g64)[None, :], w2q32[:, None])
-            J32 = fma32(d32, d32, t32)
-            dx = Ls.astype(np.longdouble) - np.longdouble(s / dsig)
-            Jx = dx * dx + (np.longdouble(0.25) * gw * gw)[:, None] - (np.longdouble(0.5) * gw)[:, None] * g64.astype(
-                np.longdouble)[None, :]
-            m32 = J32.min()
-            A, W = float(F32(np.hypot(qa, qb))) * 1.0000002, gw.max() * 1.0000002
-            T = W * A + 0.25 * W * W
-            D = np.sqrt(max(m32, 0.0) + 0.25 * A * A + 1.0)
-            E = 5.9604645e-8 * 1.5 * (3 * T + 2 * D * (lmax + abs(nq32) + D) + (abs(m32) + 0.25 * A * A + T))
-            assert E < 0.25
-            can_win = np.abs(Ls - s / dsig) <= D
-            assert np.abs(J32 - Jx.astype(np.float64))[can_win].max() <= E
-            assert J32[np.unravel_index(np.argmin(Jx), Jx.shape)] <= m32 + 2 * E
+            g32 = f32(g64)
+            Lc = f32(L32 - cs)
+            M = fma32(Lc, Lc, w2q32[:, None])
+            Ja = fma32(nwh32[:, None], g32[None, :], M)                       # the shared-mode scan
+            kfull = float(F32(-2.0 * sc))
+            Jf = fma32(nwh32[:, None], g32[None, :], fma32(kfull, Lc, M))     # the refinement's full FP32 cost
+            lam = Ls.astype(np.longdouble) - np.longdouble(cs)
+            Jx = lam * lam - 2 * np.longdouble(sc) * lam + (np.longdouble(0.25) * gw * gw)[:, None] - (
+                np.longdouble(0.5) * gw)[:, None] * g64.astype(np.longdouble)[None, :]
+            m32 = Ja.min()
+            amag = float(F32(np.hypot(qa, qb))) * 1.000001
+            SC = abs(sc) * 1.0000002
+            efp, D = kernel_E(m32, SC, amag, lmax, gw.max())
+            Lam = D + SC
+            E = efp + 2.0 * SC * Lam * 1.000001
+            if not (E < 0.25):      # the kernel sends such pixels to the exhaustive FP64 kernel
+                continue
+            band = Ja <= m32 + 2 * E
+            ix = np.unravel_index(np.argmin(Jx), Jx.shape)
+            assert band[ix], (b, trial, kind)
+            assert (np.abs(Lc)[band] <= Lam).all()
+            assert np.abs(Jf - Jx.astype(np.float64))[band].max() <= efp
+            assert Jf[ix] <= Jf[band].min() + 2 * efp
+            ties = Jx == Jx[ix]                                               # every exact tie must survive too
+            assert (band & (Jf <= Jf[band].min() + 2 * efp))[ties].all()
+            n_checked += 1
+    assert n_checked > 100

@@ -27,15 +27,21 @@ size_t ws_layout(int n_inc, int64_t n_px, unsigned flags, char *base, Workspace 
         off += align_up(bytes, 256);
         return p;
     };
-    // list positions: every bin's segment is padded to whole tiles, and the last sort run may overhang
-    const int64_t n_list = n_inc > 0 ? n_px + (int64_t)kTilePad * n_inc + 256 : 0;
+    // record positions: every bin is padded to whole tiles
+    const int64_t n_list = n_inc > 0 ? n_px + (int64_t)kTilePad * n_inc : 0;
+    const int64_t n_sort = n_inc > 0 ? n_px : 0;
     char *c = take(XS_N_COUNTERS * sizeof(u64));
     char *h = take(sizeof(unsigned) * (size_t)(n_inc + 1));
     char *bs = take(sizeof(unsigned) * (size_t)(n_inc + 1));
-    char *cu = take(sizeof(unsigned) * (size_t)(n_inc + 1));
+    char *ub = take(sizeof(unsigned) * (size_t)(n_inc + 1));
     char *ts = take(sizeof(unsigned) * (size_t)(n_inc + 1));
-    char *li = take(sizeof(unsigned) * (size_t)n_list);
-    char *fb = take(sizeof(unsigned) * (size_t)(n_inc > 0 ? n_px : 0));
+    char *k0 = take(sizeof(unsigned) * (size_t)n_sort);
+    char *k1 = take(sizeof(unsigned) * (size_t)n_sort);
+    char *v0 = take(sizeof(unsigned) * (size_t)n_sort);
+    char *v1 = take(sizeof(unsigned) * (size_t)n_sort);
+    const size_t sort_bytes = n_inc > 0 ? kSortTempBytes : 0;
+    char *st = take(sort_bytes);
+    char *fb = take(sizeof(unsigned) * (size_t)n_sort);
     char *pr = take(sizeof(PixRec) * (size_t)n_list);
     char *rr = take(sizeof(RefRec) * (size_t)n_list);
     char *hd = take(sizeof(unsigned) * (size_t)n_list);
@@ -44,9 +50,14 @@ size_t ws_layout(int n_inc, int64_t n_px, unsigned flags, char *base, Workspace 
         w->counters = (u64 *)c;
         w->hist = (unsigned *)h;
         w->bin_start = (unsigned *)bs;
-        w->cursor = (unsigned *)cu;
+        w->ubase = (unsigned *)ub;
         w->tile_start = (unsigned *)ts;
-        w->list = (unsigned *)li;
+        w->key[0] = (unsigned *)k0;
+        w->key[1] = (unsigned *)k1;
+        w->val[0] = (unsigned *)v0;
+        w->val[1] = (unsigned *)v1;
+        w->sort_temp = st;
+        w->sort_temp_bytes = sort_bytes;
         w->fallback = (unsigned *)fb;
         w->pix = (PixRec *)pr;
         w->rec = (RefRec *)rr;
@@ -73,10 +84,20 @@ __global__ void k_build_scan(xs_plan pl) {
             v = (float)(L / pl.dsig_co);
             if (isnan(L))
                 atomicMin(&pl.first_nan[bin], row * pl.n_phi + slot);
-            else if (!isinf(v))
+            else if (!isinf(v)) {
                 atomicMax(reinterpret_cast<unsigned *>(&pl.slab_absmax[bin]), __float_as_uint(fabsf(v)));
+                atomicMin(&pl.slab_range[2 * bin], float_order_key(v));
+                atomicMax(&pl.slab_range[2 * bin + 1], float_order_key(v));
+            }
         }
         pl.scan[i] = v;
+    }
+}
+__global__ void k_init_slab_range(xs_plan pl) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < pl.n_inc) {
+        pl.slab_range[2 * i] = 0x7fffffff;
+        pl.slab_range[2 * i + 1] = (int)0x80000000;
     }
 }
 __global__ void k_build_rowtab(xs_plan pl) {
@@ -121,27 +142,54 @@ __global__ void k_fix_first_nan(xs_plan pl) {
     if (i < pl.n_inc && pl.first_nan[i] == 0x7f7f7f7f) pl.first_nan[i] = -1;
 }
 
-// ---- counting sort of the co-pol pixels by incidence bin -----------------------------------------------------
+// ---- ordering of the co-pol pixels by (incidence bin, sigma0) ----------------------------------------------------
+// k_bin_keys: one 32-bit sort key per pixel -- the bin in the top bits, sigma0 quantised monotonically below (23 bits for a
+// 501-bin LUT: steps of ~3e-5 dB) -- plus the per-bin histogram; pixels that take no co-pol inversion get the largest key
+// and sort to the end.  xs_sort.cu sorts (key, pixel index) pairs; k_bin_offsets turns the histogram into padded tile
+// ranges; k_list_prepare (xs_scan.cu) gathers the sorted pixels into the padded per-tile records.
 constexpr int kBinThreads = 256;
 constexpr int kBinPxPerCta = 256 * 32;
 
-__global__ void __launch_bounds__(kBinThreads) k_bin_count(xs_plan pl, RasterArgs a, int64_t n_px, Workspace ws) {
+__device__ __forceinline__ unsigned sigma0_order_key(double s, bool is_db, int bits) {
+    unsigned q;  // 23-bit monotone key
+    if (is_db) {  // dB in: linear quantisation of [-200, 60] dB
+        const double t = fmin(fmax((s + 200.0) * (1.0 / 260.0), 0.0), 1.0);
+        q = (unsigned)(t * 8388607.0);
+    } else {  // linear in: 6 exponent bits (2^-57 .. 2^6) + 17 mantissa bits of the float = steps of <= 3.3e-5 dB
+        const unsigned b = __float_as_uint(fmaxf((float)s, 0.f));
+        const int e = min(max((int)(b >> 23) - 70, 0), 63);
+        q = ((unsigned)e << 17) | ((b >> 6) & 0x1ffffu);
+        if ((int)(b >> 23) - 70 < 0) q = 0;
+        if ((int)(b >> 23) - 70 > 63) q = 0x7fffffu;
+    }
+    return bits >= 23 ? q << (bits - 23) : q >> (23 - bits);
+}
+
+__global__ void __launch_bounds__(kBinThreads) k_bin_keys(xs_plan pl, RasterArgs a, int64_t n_px, Workspace ws, int bin_bits) {
     extern __shared__ unsigned sh_hist[];
     for (int b = threadIdx.x; b < pl.n_inc; b += blockDim.x) sh_hist[b] = 0;
     __syncthreads();
     const int64_t lo = (int64_t)blockIdx.x * kBinPxPerCta;
     const int64_t hi = min(lo + (int64_t)kBinPxPerCta, n_px);
+    const int s_bits = 32 - bin_bits;
     for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
         int bin;
-        if (pixel_co_bin(pl, a, i, &bin)) atomicAdd(&sh_hist[bin], 1u);
+        unsigned key = 0xffffffffu;
+        if (pixel_co_bin(pl, a, i, &bin)) {
+            atomicAdd(&sh_hist[bin], 1u);
+            key = ((unsigned)bin << s_bits) | sigma0_order_key(load_real(a.s_co, i, a.dtype), a.flags & XS_FLAG_SIGMA0_DB, s_bits);
+            if (key == 0xffffffffu) key = 0xfffffffeu;
+        }
+        ws.key[0][i] = key;
+        ws.val[0][i] = (unsigned)i;
     }
     __syncthreads();
     for (int b = threadIdx.x; b < pl.n_inc; b += blockDim.x)
         if (sh_hist[b]) atomicAdd(&ws.hist[b], sh_hist[b]);
 }
 
-// single CTA: exclusive scan of the bins' tile counts; a bin's segment of the list starts at tile_start * tile_px (every
-// segment is padded to whole tiles, so tile t covers the list positions [t * tile_px, (t + 1) * tile_px) of one bin)
+// single CTA: exclusive scans of the bins' pixel and tile counts; a bin's records start at tile_start * tile_px (every
+// bin is padded to whole tiles, so tile t covers the record positions [t * tile_px, (t + 1) * tile_px) of one bin)
 __global__ void k_bin_offsets(int n_inc, int tile_px, Workspace ws) {
     __shared__ unsigned carry_px, carry_tiles;
     __shared__ unsigned sh_px[1024], sh_tl[1024];
@@ -168,7 +216,7 @@ __global__ void k_bin_offsets(int n_inc, int tile_px, Workspace ws) {
         if (b < n_inc) {
             const unsigned et = carry_tiles + sh_tl[threadIdx.x] - tiles;
             ws.bin_start[b] = et * tile_px;
-            ws.cursor[b] = et * tile_px;
+            ws.ubase[b] = carry_px + sh_px[threadIdx.x] - cnt;  // position of the bin's first pixel in the sorted array
             ws.tile_start[b] = et;
         }
         __syncthreads();
@@ -182,30 +230,6 @@ __global__ void k_bin_offsets(int n_inc, int tile_px, Workspace ws) {
         ws.bin_start[n_inc] = carry_tiles * tile_px;
         ws.tile_start[n_inc] = carry_tiles;
         ws.counters[0] = carry_tiles;
-    }
-}
-
-__global__ void __launch_bounds__(kBinThreads) k_bin_scatter(xs_plan pl, RasterArgs a, int64_t n_px, Workspace ws) {
-    extern __shared__ unsigned sh[];  // [n_inc] counts -> bases, [n_inc] local cursors
-    unsigned *sh_base = sh, *sh_cur = sh + pl.n_inc;
-    for (int b = threadIdx.x; b < pl.n_inc; b += blockDim.x) {
-        sh_base[b] = 0;
-        sh_cur[b] = 0;
-    }
-    __syncthreads();
-    const int64_t lo = (int64_t)blockIdx.x * kBinPxPerCta;
-    const int64_t hi = min(lo + (int64_t)kBinPxPerCta, n_px);
-    for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-        int bin;
-        if (pixel_co_bin(pl, a, i, &bin)) atomicAdd(&sh_base[bin], 1u);
-    }
-    __syncthreads();
-    for (int b = threadIdx.x; b < pl.n_inc; b += blockDim.x)
-        if (sh_base[b]) sh_base[b] = atomicAdd(&ws.cursor[b], sh_base[b]);
-    __syncthreads();
-    for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-        int bin;
-        if (pixel_co_bin(pl, a, i, &bin)) ws.list[sh_base[bin] + atomicAdd(&sh_cur[bin], 1u)] = (unsigned)i;
     }
 }
 
@@ -551,6 +575,7 @@ extern "C" void xs_plan_destroy(xs_plan *pl) {
     cudaFree(pl->rowtab);
     cudaFree(pl->first_nan);
     cudaFree(pl->slab_absmax);
+    cudaFree(pl->slab_range);
     cudaFree(pl->inc_cr_grid);
     cudaFree(pl->wspd_cr_grid);
     cudaFree(pl->wspd_cr_half);
@@ -624,6 +649,7 @@ extern "C" int xs_plan_create(const xs_plan_desc *d, void *stream, xs_plan **out
             if ((rc = xs::check(cudaMalloc(&pl->scan, sizeof(float) * n_scan), "cudaMalloc scan image")) != XS_OK) return fail(rc);
             if ((rc = xs::check(cudaMalloc(&pl->rowtab, sizeof(float2) * (size_t)pl->n_wspd_pad), "cudaMalloc")) != XS_OK) return fail(rc);
             if ((rc = xs::check(cudaMalloc(&pl->slab_absmax, sizeof(float) * (size_t)d->n_inc), "cudaMalloc")) != XS_OK) return fail(rc);
+            if ((rc = xs::check(cudaMalloc(&pl->slab_range, sizeof(int) * 2 * (size_t)d->n_inc), "cudaMalloc")) != XS_OK) return fail(rc);
         }
     }
     if (has_cr) {
@@ -651,6 +677,7 @@ extern "C" int xs_plan_create(const xs_plan_desc *d, void *stream, xs_plan **out
         XS_CUDA(cudaMemsetAsync(pl->first_nan, 0x7f, sizeof(int) * (size_t)pl->n_inc, st));  // 0x7f7f7f7f > any index
         if (pl->fast_ok) {
             XS_CUDA(cudaMemsetAsync(pl->slab_absmax, 0, sizeof(float) * (size_t)pl->n_inc, st));
+            XS_LAUNCH(k_init_slab_range, (int)ceil_div(pl->n_inc, 256), 256, 0, st, *pl);
             XS_LAUNCH(k_build_scan, kNumSMs * 8, 256, 0, st, *pl);
             XS_LAUNCH(k_build_rowtab, (int)ceil_div(pl->n_wspd_pad, 256), 256, 0, st, *pl);
         } else {
@@ -776,11 +803,14 @@ extern "C" int xs_invert(const xs_plan *pl, const xs_invert_args *ar, void *stre
         if (fast) {
             const int tile_px = scan_tile_px(pl->kp);
             const int bin_grid = (int)ceil_div(n, kBinPxPerCta);
-            XS_CUDA(cudaMemsetAsync(ws.list, 0xff, sizeof(unsigned) * (size_t)ws.n_list, st));  // padding sentinel
-            XS_LAUNCH(k_bin_count, bin_grid, kBinThreads, sizeof(unsigned) * pl->n_inc, st, *pl, ra, n, ws);
+            int bin_bits = 1;
+            while ((1 << bin_bits) < pl->n_inc + 1) ++bin_bits;  // + 1: the all-ones key of unlisted pixels stays the largest
+            XS_LAUNCH(k_bin_keys, bin_grid, kBinThreads, sizeof(unsigned) * pl->n_inc, st, *pl, ra, n, ws, bin_bits);
             XS_LAUNCH(k_bin_offsets, 1, 1024, 0, st, pl->n_inc, tile_px, ws);
-            XS_LAUNCH(k_bin_scatter, bin_grid, kBinThreads, 2 * sizeof(unsigned) * pl->n_inc, st, *pl, ra, n, ws);
-            const int rc = launch_scan_pipeline(pl, ra, ws, out, n, ar->scan_timer, st);
+            int which = 0;
+            int rc = sort_pairs_u32(ws.key, ws.val, n, ws.sort_temp, ws.sort_temp_bytes, st, &which);
+            if (rc != XS_OK) return rc;
+            rc = launch_scan_pipeline(pl, ra, ws, ws.val[which], out, n, ar->scan_timer, st);
             if (rc != XS_OK) return rc;
             XS_LAUNCH(k_exact, sms * 8, 256, 0, st, *pl, ra, n, ws.fallback, ws.counters + 1, out);
         } else {

@@ -1,6 +1,7 @@
 // Internal declarations shared by the inversion translation units of libxsarsea_b200 (sm_100a).
 #pragma once
 #include <math_constants.h>
+#include <string.h>
 
 #include "xs_common.cuh"
 
@@ -17,6 +18,7 @@ struct xs_plan {
     float2 *rowtab;     // [n_wspd_pad] {-w/2, w*w/4} (0,0 in the padding)
     int *first_nan;     // [n_inc] flat index (w*n_phi+p) of the first NaN of the slab, or -1
     float *slab_absmax; // [n_inc] max finite |scan value| of the slab
+    int *slab_range;    // [2 n_inc] {smallest, largest} finite scan value of the slab as order-preserving int keys
     int kp;             // float2 pairs per lane: nph_pad = 64*kp
     int nph_pad, n_wspd_pad;
     int fast_ok;        // the FP32 scan can be used for this plan
@@ -48,6 +50,7 @@ namespace xs {
 constexpr int kChunkRows = 16;     // wspd rows per staged chunk = granularity of the argmin bookkeeping
 constexpr int kRowPad = 8;         // the scan image pads the wspd axis to a multiple of this (+inf rows)
 constexpr int kStages = 3;         // shared-memory ring depth of the scan
+constexpr float kBandMargin = 0.5f;  // every accepted error band is narrower than this (2 E < kBandMargin)
 constexpr int kTilePad = 32;       // upper bound of the pixels per scan tile (the bin segments of the pixel list are padded to tiles)
 constexpr int kMaxIncBins = 6144;  // bins whose two shared-memory histograms (k_bin_scatter) fit the default 48 KB
 
@@ -268,12 +271,24 @@ __device__ __forceinline__ unsigned atom_add_acq_rel_shared(unsigned *p, unsigne
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// order-preserving float <-> int map (for atomicMin / atomicMax on floats)
+__host__ __device__ __forceinline__ int float_order_key(float v) {
+#ifdef __CUDA_ARCH__
+    const int k = __float_as_int(v);
+#else
+    int k;
+    memcpy(&k, &v, 4);
+#endif
+    return k ^ ((k >> 31) & 0x7fffffff);
+}
+__device__ __forceinline__ float float_from_order_key(int k) { return __int_as_float(k ^ ((k >> 31) & 0x7fffffff)); }
+
 // ---- per-call workspace ------------------------------------------------------------------------------------------
-// The pixels that take the co-pol inversion are counting-sorted by incidence bin; every bin's segment of the list is
-// padded to whole scan tiles (sentinel entries), so tile t is the list positions [t*tile_px, (t+1)*tile_px) and all of a
-// tile's pixels share one LUT slab.  k_list_prepare then orders runs of the list by sigma0 and materialises one PixRec
-// per list position (what the scan streams in with one bulk copy per tile); k_scan_co leaves one RefRec per scanned
-// pixel (the error band and the contending (lane, chunk) cells) for k_refine_co.
+// The pixels that take the co-pol inversion are sorted by (incidence bin, sigma0); every bin is padded to whole scan tiles,
+// so tile t is the record positions [t*tile_px, (t+1)*tile_px), all of a tile's pixels share one LUT slab and the pixels
+// of a warp have nearly the same sigma0.  k_list_prepare materialises one PixRec per record position (what the scan
+// streams in with one bulk copy per tile); k_scan_co leaves one RefRec per scanned pixel (the error band and the
+// contending (lane, chunk) cells) for the refinement kernels.
 struct __align__(16) PixRec {  // 32 B
     double qa, qb, s;          // m_antenna, m_azi (|.| if phi_180), sigma0 in dB
     unsigned px;               // raster index
@@ -282,21 +297,25 @@ struct __align__(16) PixRec {  // 32 B
     unsigned char neg;         // Im(ancillary) < 0 (direction sign, windspeed.py:234-242)
 };
 struct __align__(16) RefRec {  // 32 B
-    float thr, cs, nq;         // band threshold m32 + 2E, warp centre, k = -2 (s/dsig - cs): what re-creates the FP32 costs
-    unsigned cont, wide;       // lanes with exactly one / with several chunks inside the band (0, 0: exhaustive FP64 needed)
-    unsigned ch_lo, ch_hi;     // best-chunk indices of the cont lanes, 8 bits each in lane order (at most 8 cont lanes)
-    unsigned spare;
+    float thr, cs, nq;         // band threshold m32 + 2E, warp centre, k = -2 (s/dsig - cs) (0: shared-sigma0 mode): what
+                               // re-creates the scanned FP32 costs
+    float efp;                 // bound of the full centred form's FP32 error (second filter of shared-sigma0 records)
+    unsigned cont;             // lanes holding band members (0: the scan could not bound its error -> exhaustive FP64)
+    unsigned mask[3];          // chunk masks (bit = chunk >> mask_sh) of the first three cont lanes
 };
 static_assert(sizeof(PixRec) == 32 && sizeof(RefRec) == 32, "record layout");
 
 // counters (u64): see XS_N_COUNTERS in the public header
 struct Workspace {
     u64 *counters;         // [16]
-    unsigned *hist;        // [n_inc]
-    unsigned *bin_start;   // [n_inc + 1] padded list position of the bin's first entry
-    unsigned *cursor;      // [n_inc]
+    unsigned *hist;        // [n_inc] listed pixels per bin
+    unsigned *bin_start;   // [n_inc + 1] record position of the bin's first pixel (bins padded to whole tiles)
+    unsigned *ubase;       // [n_inc] position of the bin's first pixel in the sorted (key, pixel) arrays
     unsigned *tile_start;  // [n_inc + 1]
-    unsigned *list;        // [n_list] pixel indices grouped by bin, 0xffffffff = padding
+    unsigned *key[2];      // [n_px] sort keys (bin | quantised sigma0) and their alternate buffer
+    unsigned *val[2];      // [n_px] pixel indices carried by the sort
+    void *sort_temp;       // CUB's scratch
+    size_t sort_temp_bytes;
     unsigned *fallback;    // [n_px] pixels for the exhaustive kernel
     PixRec *pix;           // [n_list]
     RefRec *rec;           // [n_list]
@@ -362,8 +381,10 @@ __device__ __forceinline__ void write_co(const xs_plan &pl, const OutSpec &o, in
     if (!(o.flags & XS_FLAG_OUT_SPEED_DIR)) reinterpret_cast<double2 *>(o.co)[px] = co_from_idx(pl, idx, anc_im_neg);
 }
 
-int launch_scan_pipeline(const xs_plan *pl, const RasterArgs &ra, const Workspace &ws, const OutSpec &out, int64_t n_px,
-                         xs_timer *timer, cudaStream_t st);
+constexpr size_t kSortTempBytes = 16u << 20;  // CUB radix sort scratch with double buffers: per-pass histograms only
+int sort_pairs_u32(unsigned *keys[2], unsigned *vals[2], int64_t n, void *temp, size_t temp_bytes, cudaStream_t st, int *which);
+int launch_scan_pipeline(const xs_plan *pl, const RasterArgs &ra, const Workspace &ws, const unsigned *sorted_px,
+                         const OutSpec &out, int64_t n_px, xs_timer *timer, cudaStream_t st);
 int scan_tile_px(int kp);
 
 }  // namespace xs

@@ -9,20 +9,25 @@
 //     k = -2 sigma (per pixel),   g = a cos phi + b sin phi (per pixel and phi node)
 // i.e. per pixel and candidate pair two FFMA2 and one FMNMX3.
 //
-// Three kernels, all on the caller's stream, no host synchronisation:
-//   k_list_prepare  orders runs of the bin-grouped pixel list by sigma0 (so that a warp's pixels have a small |sigma|) and
-//                   materialises one 32-byte PixRec per list position
-//   k_scan_co       persistent CTAs (4 per SM, 4 warps, 128 registers): a tile = 32 list positions of one bin; the tile's
+// Shared-sigma0 mode.  The listed pixels arrive sorted by (bin, sigma0) (xs_sort.cu), so the 8 pixels of a warp usually have
+// |sigma| of a few 1e-3; then the warp leaves k lambda out of the scanned cost altogether (J'' ~ M + (-w/2) g: ONE FFMA2
+// and one FMNMX3 per pixel and candidate pair) and widens the error band by the bound 2 |sigma| Lam of the omitted term;
+// the refinement filters the members of the wider band once more with the full FP32 cost before any FP64 work.
+//
+// Kernels, all on the caller's stream, no host synchronisation:
+//   k_list_prepare  one 32-byte PixRec per record position from the sorted pixel indices (bins padded to whole tiles)
+//   k_scan_co       persistent CTAs (4 per SM, 4 warps, 128 registers): a tile = 32 record positions of one bin; the tile's
 //                   PixRecs and the bin's slab of the FP32 scan image arrive by bulk-async (TMA) copies -- records
 //                   double-buffered one tile ahead, slab chunks of 16 wspd rows through a 3-stage ring that keeps
 //                   streaming across tile boundaries; there is no producer thread and no CTA barrier: the warp that is
 //                   the last to finish a chunk refills its stage (shared-memory arrival counter), so no warp ever waits
 //                   for another one to release a stage.  Lane l owns the phi pairs {2(l+32j), 2(l+32j)+1}; per lane and
-//                   pixel only the best 16-row chunk, its index and the runner-up chunk minimum are kept.  After the
-//                   slab: warp-shuffle min, the rigorous FP32 error band E, and one RefRec per pixel.
-//   k_refine_co     a warp per pixel: re-creates the FP32 costs (bit-identical operations) of the (lane, chunk) cells
-//                   inside the band; a single member settles the pixel, several are evaluated in FP64 with the reference's
-//                   operation order and reduced by a warp-shuffle lexicographic (J, index) argmin = numpy's first minimum.
+//                   pixel only the running minimum and a bit mask of the chunks whose minimum came within kBandMargin of it
+//                   are kept.  After the slab: warp-shuffle min, the rigorous error band, and one RefRec per pixel.
+//   k_refine_easy   eight lanes per pixel: re-creates the FP32 costs (bit-identical operations) of the recorded (lane,
+//                   chunk) cells; a single band member settles the pixel, several are evaluated in FP64 with the
+//                   reference's operation order, lexicographic (J, index) minimum = numpy's first minimum
+//   k_refine_co     a warp per pixel for the rare records with more than three contending lanes
 #include <stdio.h>
 #include <stdlib.h>
 
@@ -31,87 +36,46 @@
 namespace xs {
 
 constexpr unsigned kTileEnd = 0xffffffffu;
-constexpr int kTileBatch = 8;   // tiles a CTA takes per global atomic
-constexpr int kSortRun = 256;   // list positions ordered together by k_list_prepare (a whole number of tiles fits)
+constexpr int kTileBatch = 8;  // tiles a CTA takes per global atomic
 
-// ---- list preparation: local order by sigma0 + pixel records ----------------------------------------------------------
-// The centred scan shares (L - c)^2 between the 8 pixels of a warp, which keeps its error band tight only if those pixels
-// have similar sigma0.  Every run of list positions (<= 256, a whole number of tiles, possibly across bin boundaries) is
-// sorted by (incidence bin, sigma0) in shared memory: bins stay contiguous and in order, padding stays at the end of its
-// bin's segment, and a warp's 8 pixels span 1/32 of the run's sigma0 range.
-__global__ void __launch_bounds__(kSortRun) k_list_prepare(xs_plan pl, RasterArgs a, Workspace ws, int tile_px) {
-    __shared__ unsigned long long key[kSortRun];
-    __shared__ unsigned val[kSortRun];
-    const unsigned n_tiles = (unsigned)ws.counters[0];
-    const unsigned tiles_per_run = kSortRun / tile_px;
-    const unsigned t0 = blockIdx.x * tiles_per_run;
-    if (t0 >= n_tiles) return;
-    const unsigned first = t0 * tile_px;
-    const unsigned count = (min(t0 + tiles_per_run, n_tiles) - t0) * tile_px;  // <= kSortRun
-    unsigned long long k = ~0ull;
-    unsigned v = 0xffffffffu;
-    int bin = 0;
-    if (threadIdx.x < count) {
-        const unsigned e = first + threadIdx.x;
-        v = ws.list[e];
-        int lo = 0, hi = pl.n_inc;  // bin of list position e: last b with bin_start[b] <= e
+// ---- pixel records --------------------------------------------------------------------------------------------------------
+// One PixRec per record position: position e of bin b (bin_start[b] <= e < bin_start[b + 1]) holds the (e - bin_start[b])-th
+// pixel of the bin in sigma0 order, or padding behind the bin's last pixel.
+__global__ void __launch_bounds__(256) k_list_prepare(xs_plan pl, RasterArgs a, Workspace ws, const unsigned *__restrict__ sorted_px,
+                                                      int tile_px) {
+    const int64_t n_pos = (int64_t)ws.counters[0] * tile_px;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n_pos; e += stride) {
+        int lo = 0, hi = pl.n_inc;  // bin of record position e: last b with bin_start[b] <= e
         while (hi - lo > 1) {
             const int mid = (lo + hi) >> 1;
-            if (ws.bin_start[mid] <= e)
+            if (ws.bin_start[mid] <= (unsigned)e)
                 lo = mid;
             else
                 hi = mid;
         }
-        bin = lo;
-        unsigned b = 0xffffffffu;  // padding sorts behind every pixel of its bin
-        if (v != 0xffffffffu) {
-            const float sf = (float)load_real(a.s_co, v, a.dtype);  // linear or dB: monotone either way
-            b = __float_as_uint(sf);
-            b = (b & 0x80000000u) ? ~b : (b | 0x80000000u);  // order-preserving map of the float bits
-            if (b == 0xffffffffu) b = 0xfffffffeu;
+        const int bin = lo;
+        const unsigned r = (unsigned)e - ws.bin_start[bin];
+        PixRec rec;
+        rec.qa = rec.qb = rec.s = 0.0;
+        rec.px = 0xffffffffu;
+        rec.bin = (unsigned short)bin;
+        rec.state = 0;
+        rec.neg = 0;
+        if (r < ws.hist[bin]) {
+            const unsigned px = sorted_px[ws.ubase[bin] + r];
+            const double2 anc = load_cplx(a.anc, px, a.dtype);
+            const double s_raw = load_real(a.s_co, px, a.dtype);
+            rec.px = px;
+            rec.qa = anc.x;
+            rec.qb = pl.phi_180 ? fabs(anc.y) : anc.y;
+            rec.neg = anc.y < 0.0;
+            rec.s = (a.flags & XS_FLAG_SIGMA0_DB) ? s_raw : to_db(s_raw);
+            const bool finite_q = isfinite(rec.qa) && isfinite(rec.qb) && isfinite(rec.s);
+            rec.state = !finite_q ? 3 : (pl.first_nan[bin] >= 0 ? 2 : 1);
         }
-        k = ((unsigned long long)lo << 32) | b;
+        ws.pix[e] = rec;
     }
-    key[threadIdx.x] = k;
-    val[threadIdx.x] = v;
-    __syncthreads();
-    for (int size = 2; size <= kSortRun; size <<= 1)
-        for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            const int i = threadIdx.x, j = i ^ stride;
-            if (j > i) {
-                const bool up = (i & size) == 0;
-                const unsigned long long ki = key[i], kj = key[j];
-                if ((ki > kj) == up) {
-                    key[i] = kj;
-                    key[j] = ki;
-                    const unsigned t = val[i];
-                    val[i] = val[j];
-                    val[j] = t;
-                }
-            }
-            __syncthreads();
-        }
-    if (threadIdx.x >= count) return;
-    // the bin of a position does not change (segments keep their extent); its pixel does
-    const unsigned px = val[threadIdx.x];
-    PixRec r;
-    r.qa = r.qb = r.s = 0.0;
-    r.px = px;
-    r.bin = (unsigned short)bin;
-    r.state = 0;
-    r.neg = 0;
-    if (px != 0xffffffffu) {
-        const double2 anc = load_cplx(a.anc, px, a.dtype);
-        const double s_raw = load_real(a.s_co, px, a.dtype);
-        r.qa = anc.x;
-        r.qb = pl.phi_180 ? fabs(anc.y) : anc.y;
-        r.neg = anc.y < 0.0;
-        r.s = (a.flags & XS_FLAG_SIGMA0_DB) ? s_raw : to_db(s_raw);
-        const bool finite_q = isfinite(r.qa) && isfinite(r.qb) && isfinite(r.s);
-        r.state = !finite_q ? 3 : (pl.first_nan[bin] >= 0 ? 2 : 1);
-    }
-    ws.list[first + threadIdx.x] = px;
-    ws.pix[first + threadIdx.x] = r;
 }
 
 // ---- the FP32 scan ----------------------------------------------------------------------------------------------------
@@ -129,7 +93,7 @@ struct ScanSmem {
 };
 
 template <int KP, int P, int NW, int MB>
-__global__ void __launch_bounds__(NW * 32, MB) k_scan_co(xs_plan pl, Workspace ws) {
+__global__ void __launch_bounds__(NW * 32, MB) k_scan_co(xs_plan pl, Workspace ws, float share_tau) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     using Smem = ScanSmem<KP, P, NW>;
     Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
@@ -142,6 +106,8 @@ __global__ void __launch_bounds__(NW * 32, MB) k_scan_co(xs_plan pl, Workspace w
     const unsigned n_tiles = (unsigned)ws.counters[0];
     const int n_chunks = (pl.n_wspd_pad + kChunkRows - 1) / kChunkRows;  // >= NS (plan creation checks); the last may be shorter
     const size_t slab_floats = (size_t)pl.n_wspd_pad * Smem::kRowFloats;
+    int mask_sh = 0;  // chunks per bit of the chunk masks: 2^mask_sh (32 bits cover the slab)
+    while ((n_chunks + (1 << mask_sh) - 1) >> mask_sh > 32) ++mask_sh;
 
     // one chunk of a slab into its ring stage
     auto load_chunk = [&](int bin, int c, int stage) {
@@ -194,6 +160,7 @@ __global__ void __launch_bounds__(NW * 32, MB) k_scan_co(xs_plan pl, Workspace w
 
     int stage = 0;
     uint32_t phase = 0;  // parity of full[stage] for the chunk this warp consumes next
+    unsigned n_shared = 0;  // record positions scanned in shared-sigma0 mode (statistics)
     for (unsigned u = 0;; ++u) {
         const int b = u & 1;
         mbar_wait(&sm.pix_full[b], (u >> 1) & 1);
@@ -217,12 +184,30 @@ __global__ void __launch_bounds__(NW * 32, MB) k_scan_co(xs_plan pl, Workspace w
                 }
             if (any) cs = (float)(0.5 * (smin + smax));
         }
-        float nqs[P];   // k_p = -2 (s_p/dsig - cs)
+        // Shared-sigma0 mode: the list is in sigma0 order, so the warp's pixels usually differ from the centre by a tiny
+        // |sigma|; then k lambda (|k lambda| <= 2 |sigma| Lam) is left out of the scanned cost altogether -- one FFMA2 per
+        // pixel and candidate pair instead of two -- and added to the error band instead (see the band section below).
+        // The omitted term is bounded by 2 |sigma| Lam, and Lam grows with the distance of sigma0 from the slab's value
+        // range (a pixel far outside the LUT has a large lambda at its minimum): the mode is chosen from an estimate of
+        // that product (performance only -- the band below uses the rigorous bound).
+        float budget_need = 0.f;
+        {
+            const float lo = float_from_order_key(pl.slab_range[2 * bin]), hi = float_from_order_key(pl.slab_range[2 * bin + 1]);
+#pragma unroll
+            for (int p = 0; p < P; ++p)
+                if (mine[p].state == 1) {
+                    const float sp = (float)(mine[p].s / pl.dsig_co);
+                    const float dmin = fmaxf(fmaxf(lo - sp, sp - hi), 0.f);
+                    budget_need = fmaxf(budget_need, 2.f * fabsf(sp - cs) * (dmin + 2.5f));
+                }
+        }
+        const bool shared = any && budget_need <= share_tau;  // warp-uniform
+        float nqs[P];   // k_p = -2 (s_p/dsig - cs); 0 in shared mode
         u64 g[P][KP];   // {g(phi_even), g(phi_odd)} as packed FP32
 #pragma unroll
         for (int p = 0; p < P; ++p) {
             const bool on = mine[p].state == 1;
-            nqs[p] = on ? (float)(-2.0 * (mine[p].s / pl.dsig_co - (double)cs)) : 0.f;
+            nqs[p] = (on && !shared) ? (float)(-2.0 * (mine[p].s / pl.dsig_co - (double)cs)) : 0.f;
             const double qa = mine[p].qa, qb = mine[p].qb;
 #pragma unroll
             for (int j = 0; j < KP; ++j) {
@@ -230,18 +215,47 @@ __global__ void __launch_bounds__(NW * 32, MB) k_scan_co(xs_plan pl, Workspace w
                 g[p][j] = on ? pack2(g32(qa, qb, c0.x, c0.y), g32(qa, qb, c1.x, c1.y)) : 0ull;
             }
         }
-        float m[P], best[P], second[P];
-        unsigned bch[(P + 3) / 4];  // index of the best chunk, one byte per pixel (n_chunks <= 256)
+        // per lane and pixel: the running minimum and the set of chunks (bit c >> mask_sh) whose minimum came within
+        // kBandMargin of it.  Any band this kernel accepts is narrower than kBandMargin (2 E < 0.5), so at the end the set
+        // holds every chunk of the lane that can contain a band member (a chunk is only dropped when a later minimum is
+        // lower by more than the margin, i.e. when it is outside every acceptable band).
+        float m[P], best[P];
+        unsigned cmask[P];
 #pragma unroll
-        for (int p = 0; p < P; ++p) m[p] = best[p] = second[p] = CUDART_INF_F;
-#pragma unroll
-        for (int w = 0; w < (P + 3) / 4; ++w) bch[w] = 0u;
+        for (int p = 0; p < P; ++p) {
+            m[p] = best[p] = CUDART_INF_F;
+            cmask[p] = 0u;
+        }
         const u64 ncs2 = pack2(-cs, -cs);
 
         // ---- the slab, 16 wspd rows at a time ----
         for (int c = 0; c < n_chunks; ++c) {
             mbar_wait(&sm.full[stage], phase);
-            if (any) {
+            if (shared) {
+                const u64 *rows = reinterpret_cast<const u64 *>(sm.ring[stage]);
+                const int rows_here = min(kChunkRows, pl.n_wspd_pad - c * kChunkRows);
+#pragma unroll 2
+                for (int r = 0; r < rows_here; ++r) {
+                    const float2 rt = rowtab_s[c * kChunkRows + r];
+                    const u64 nwh = pack2(rt.x, rt.x), w2q = pack2(rt.y, rt.y);
+                    u64 M[KP];
+#pragma unroll
+                    for (int j = 0; j < KP; ++j) {  // M = lambda^2 + w^2/4, shared by the warp's pixels
+                        const u64 lam = fadd2(rows[r * (32 * KP) + lane + 32 * j], ncs2);
+                        M[j] = ffma2(lam, lam, w2q);
+                    }
+#pragma unroll
+                    for (int p = 0; p < P; ++p) {
+#pragma unroll
+                        for (int j = 0; j < KP; ++j) {  // J'' ~ M + (-w/2) g: one FFMA2 per candidate pair
+                            const u64 J = ffma2(nwh, g[p][j], M[j]);
+                            float j0, j1;
+                            unpack2(J, j0, j1);
+                            m[p] = fmin3(m[p], j0, j1);
+                        }
+                    }
+                }
+            } else if (any) {
                 const u64 *rows = reinterpret_cast<const u64 *>(sm.ring[stage]);
                 const int rows_here = min(kChunkRows, pl.n_wspd_pad - c * kChunkRows);  // even (n_wspd_pad is a multiple of 8)
 #pragma unroll 2
@@ -290,13 +304,13 @@ __global__ void __launch_bounds__(NW * 32, MB) k_scan_co(xs_plan pl, Workspace w
                 }
             }
             __syncwarp();
+            const unsigned cbit = 1u << (c >> mask_sh);
 #pragma unroll
             for (int p = 0; p < P; ++p) {
-                const bool lt = m[p] < best[p];
-                second[p] = fminf(second[p], fmaxf(best[p], m[p]));
-                best[p] = fminf(best[p], m[p]);
-                constexpr unsigned kSel[4] = {0x3214u, 0x3240u, 0x3410u, 0x4210u};  // byte p & 3 <- c
-                bch[p >> 2] = lt ? __byte_perm(bch[p >> 2], (unsigned)c, kSel[p & 3]) : bch[p >> 2];
+                const float mp = m[p];
+                cmask[p] = (mp < best[p] - kBandMargin) ? 0u : cmask[p];
+                cmask[p] |= (mp <= best[p] + kBandMargin) ? cbit : 0u;
+                best[p] = fminf(best[p], mp);
                 m[p] = CUDART_INF_F;
             }
             if (++stage == NS) {
@@ -305,6 +319,7 @@ __global__ void __launch_bounds__(NW * 32, MB) k_scan_co(xs_plan pl, Workspace w
             }
         }
         if (!any) continue;
+        if (shared) n_shared += P;
 
         // ---- band of every pixel -> RefRec ---------------------------------------------------------------------------
         // m32 = warp-shuffle min of the FP32 costs; E bounds |J''_fp32 - J''_exact| for every candidate that can still
@@ -312,7 +327,6 @@ __global__ void __launch_bounds__(NW * 32, MB) k_scan_co(xs_plan pl, Workspace w
         // lies in S = {c : J''_fp32(c) <= m32 + 2E}; k_refine_co collects S from the cells recorded here.
         const float lmax = pl.slab_absmax[bin];
         const float W = (float)pl.w_absmax * 1.0000002f;
-        constexpr int cap = 8, bits = 8;  // a record holds the best-chunk index of 8 lanes
 #pragma unroll
         for (int p = 0; p < P; ++p) {
             if (mine[p].state != 1) continue;  // warp-uniform
@@ -329,37 +343,39 @@ __global__ void __launch_bounds__(NW * 32, MB) k_scan_co(xs_plan pl, Workspace w
             // D^2 + sc^2 + T; row-table and g roundings W^2/4 + W A; the W terms add up to W^2 + 2 W A <= 4 T.
             const float D = sqrtf(fmaxf(m32 + SC * SC * 1.0000002f, 0.f) + 0.25f * A * A + 1.0f);
             const float Lam = D + SC;
-            const float E = 5.9604645e-8f * 1.5f * (2.f * Lam * lmax + 2.f * SC * lmax + 4.f * Lam * Lam + 6.f * SC * Lam + SC * SC + D * D + 4.f * T);
+            float E = 5.9604645e-8f * 1.5f * (2.f * Lam * lmax + 2.f * SC * lmax + 4.f * Lam * Lam + 6.f * SC * Lam + SC * SC + D * D + 4.f * T);
+            // shared mode: the scanned cost lacks k lambda = -2 sigma lambda.  Both the scanned minimum's candidate and the
+            // true argmin have |lambda| <= Lam (the "+ 1" under D's root covers the shift of the minimum as long as the total
+            // bound stays below 1, which `sane` checks), so the omission moves their costs by at most 2 |sigma| Lam.
+            const float efp = E;  // bound of the full centred form's FP32 error (the refinement's second filter in shared mode)
+            if (shared) E += 2.f * SC * Lam * 1.000001f;
             const float thr = m32 + 2.f * E;
-            const bool sane = (E < 0.25f) && (m32 < CUDART_INF_F);  // else: magnitudes outside the range of the bound
-            unsigned cont = __ballot_sync(0xffffffffu, sane && best[p] <= thr);
-            // lanes holding two or more chunks inside the band: all of the lane's candidates are looked at
-            unsigned wide = __ballot_sync(0xffffffffu, sane && second[p] <= thr);
-            cont &= ~wide;
-            // the record holds the best-chunk index of `cap` cont lanes; further ones are treated like wide lanes
+            // 2 E < kBandMargin keeps the chunk masks complete; a larger bound means magnitudes outside the range the
+            // bound was derived for
+            const bool sane = (E < 0.5f * kBandMargin) && (m32 < CUDART_INF_F);
+            const unsigned cont = __ballot_sync(0xffffffffu, sane && best[p] <= thr);  // lanes holding band members
+            // the record carries the chunk masks of the first three contending lanes (one or two in 99 % of the pixels);
+            // with more, k_refine_co looks at the lanes whole
             const bool mine_c = (cont >> lane) & 1u;
             const int rank = __popc(cont & ((1u << lane) - 1u));
-            const unsigned over = __ballot_sync(0xffffffffu, mine_c && rank >= cap);
-            cont &= ~over;
-            wide |= over;
-            const unsigned bchunk = (bch[p >> 2] >> (8 * (p & 3))) & 0xffu;
-            const u64 idv = (mine_c && rank < cap) ? ((u64)bchunk << (bits * rank)) : 0ull;
-            const unsigned ch_lo = __reduce_or_sync(0xffffffffu, (unsigned)idv);
-            const unsigned ch_hi = __reduce_or_sync(0xffffffffu, (unsigned)(idv >> 32));
+            const unsigned m0 = __reduce_or_sync(0xffffffffu, (mine_c && rank == 0) ? cmask[p] : 0u);
+            const unsigned m1 = __reduce_or_sync(0xffffffffu, (mine_c && rank == 1) ? cmask[p] : 0u);
+            const unsigned m2 = __reduce_or_sync(0xffffffffu, (mine_c && rank == 2) ? cmask[p] : 0u);
             if (lane == 0) {
                 RefRec rr;
                 rr.thr = thr;
                 rr.cs = cs;
                 rr.nq = nqs[p];
+                rr.efp = efp;
                 rr.cont = cont;
-                rr.wide = wide;
-                rr.ch_lo = ch_lo;
-                rr.ch_hi = ch_hi;
-                rr.spare = 0;
+                rr.mask[0] = m0;
+                rr.mask[1] = m1;
+                rr.mask[2] = m2;
                 ws.rec[(size_t)tile * TP + warp * P + p] = rr;
             }
         }
     }
+    if (lane == 0 && n_shared) atomicAdd(&ws.counters[13], (u64)n_shared);
 }
 
 // ---- exact refinement ---------------------------------------------------------------------------------------------------
@@ -396,6 +412,9 @@ __global__ void __launch_bounds__(256, 3) k_refine_easy(xs_plan pl, Workspace ws
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int64_t n_pos = (int64_t)ws.counters[0] * tile_px;
     static_assert(kChunkRows == 16, "two rows per lane of a group");
+    const int n_chunks = (pl.n_wspd_pad + kChunkRows - 1) / kChunkRows;
+    int mask_sh = 0;
+    while ((n_chunks + (1 << mask_sh) - 1) >> mask_sh > 32) ++mask_sh;
     unsigned n_settled = 0, n_cells = 0, n_fp64 = 0;
     for (int64_t e0 = warp * 4; e0 < n_pos; e0 += n_warps * 4) {
         const int64_t e = e0 + grp;
@@ -403,7 +422,7 @@ __global__ void __launch_bounds__(256, 3) k_refine_easy(xs_plan pl, Workspace ws
         const PixRec px = ws.pix[e];
         const RefRec rc = ws.rec[e];  // loaded together with the pixel (only meaningful for state 1)
         if (px.state == 0) continue;  // uniform within the group; no warp-wide synchronisation below
-        if (px.state != 1 || (rc.cont | rc.wide) == 0u) {
+        if (px.state != 1 || rc.cont == 0u) {
             if (sub == 0) {
                 if (px.state == 2)
                     write_co(pl, out, pl.first_nan[px.bin], px.neg, px.px);  // J is NaN exactly where L is NaN
@@ -412,34 +431,52 @@ __global__ void __launch_bounds__(256, 3) k_refine_easy(xs_plan pl, Workspace ws
             }
             continue;
         }
-        if (rc.wide != 0u) {
+        if (__popc(rc.cont) > 3) {  // more contending lanes than the record has chunk masks for
             if (sub == 0) ws.hard[atomicAdd(&ws.counters[12], 1ull)] = (unsigned)e;
             continue;
         }
         const float *slab32 = pl.scan + (size_t)px.bin * pl.n_wspd_pad * pl.nph_pad;
         const double *slab64 = pl.co_lut + (size_t)px.bin * pl.n_wspd * pl.n_phi;
+        // Shared-sigma0 records (nq == 0): the scanned cost left k lambda out and the band is wider by 2 |sigma| Lam.  The
+        // members of that wide band are filtered a second time with the full centred FP32 cost (k recomputed as the scan's
+        // exact mode would): the true argmin c* is a member, so full32(c*) <= J(c*) + efp <= J(c) + efp <= full32(c) + 2 efp for
+        // every member c -- only members within 2 efp of the smallest full32 can be the argmin.  FP64 is then needed as
+        // rarely as without sharing.
+        const bool two_stage = rc.nq == 0.f;
+        const float kfull = (float)(-2.0 * (px.s / pl.dsig_co - (double)rc.cs));
+        float thr2 = CUDART_INF_F, jmin = CUDART_INF_F;
         int n_loc = 0, one_loc = -1;
         double bj = CUDART_INF;  // FP64 pass: lexicographic (J, flat index) minimum of this lane's members
         int bi = 0x7fffffff;
-        // walk the cont cells: count the band members (exact == false) or evaluate them in FP64 (true)
-        auto walk = [&](bool exact) {
-            unsigned cells = rc.cont;
-            u64 ids = ((u64)rc.ch_hi << 32) | rc.ch_lo;
+        // walk the cont cells.  stage 0: count the band members (and note the smallest full cost); 1: count the members that
+        // pass the second filter; 2: evaluate them in FP64
+        auto walk = [&](int stage) {
+            unsigned lanes = rc.cont;
 #pragma unroll 1
-            while (cells) {  // uniform within the group
-                const int L = __ffs(cells) - 1;
-                cells &= cells - 1;
-                const int row0 = (int)(ids & 0xffu) * kChunkRows + sub;
-                ids >>= 8;
+            for (int li = 0; lanes; ++li) {  // uniform within the group
+                const int L = __ffs(lanes) - 1;
+                lanes &= lanes - 1;
                 float gq[2 * KP];
 #pragma unroll
                 for (int sl = 0; sl < 2 * KP; ++sl) {
                     const int ip = 2 * (L + 32 * (sl >> 1)) + (sl & 1);
                     gq[sl] = ip < pl.n_phi ? g32(px.qa, px.qb, pl.cos_phi[ip], pl.sin_phi[ip]) : 0.f;
                 }
+                // the chunks of this lane that came within the margin of its minimum (a bit covers 2^mask_sh chunks)
+                unsigned cm = li == 0 ? rc.mask[0] : (li == 1 ? rc.mask[1] : rc.mask[2]);
+                int c = 0, c_end = 0;
+#pragma unroll 1
+                for (;;) {
+                    if (c == c_end) {
+                        if (!cm) break;
+                        c = (__ffs(cm) - 1) << mask_sh;
+                        c_end = min(c + (1 << mask_sh), n_chunks);
+                        cm &= cm - 1;
+                    }
+                    if (sub == 0 && stage == 0) ++n_cells;
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
-                    const int iw = row0 + 8 * h;
+                        const int iw = c * kChunkRows + sub + 8 * h;
                     if (iw >= pl.n_wspd) continue;
                     const float2 rt = pl.rowtab[iw];
                     const float2 *rowp = reinterpret_cast<const float2 *>(slab32 + (size_t)iw * pl.nph_pad) + L;
@@ -450,10 +487,16 @@ __global__ void __launch_bounds__(256, 3) k_refine_easy(xs_plan pl, Workspace ws
                         for (int o = 0; o < 2; ++o) {  // exactly the scan's operations
                             const int ip = 2 * (L + 32 * j) + o;
                             const float lc = __fadd_rn(o ? v.y : v.x, -rc.cs);
-                            const float aa = __fmaf_rn(rc.nq, lc, __fmaf_rn(lc, lc, rt.y));
+                            const float mm = __fmaf_rn(lc, lc, rt.y);
+                            const float aa = __fmaf_rn(rc.nq, lc, mm);
                             if (ip >= pl.n_phi || !(__fmaf_rn(rt.x, gq[2 * j + o], aa) <= rc.thr)) continue;
                             const int flat = iw * pl.n_phi + ip;
-                            if (!exact) {
+                            if (two_stage) {
+                                const float jf = __fmaf_rn(rt.x, gq[2 * j + o], __fmaf_rn(kfull, lc, mm));
+                                if (stage == 0) jmin = fminf(jmin, jf);
+                                if (stage > 0 && !(jf <= thr2)) continue;
+                            }
+                            if (stage < 2) {
                                 ++n_loc;
                                 one_loc = flat;
                             } else {  // J is never NaN here: finite inputs, NaN-free slab
@@ -466,19 +509,34 @@ __global__ void __launch_bounds__(256, 3) k_refine_easy(xs_plan pl, Workspace ws
                             }
                         }
                     }
+                    }
+                    ++c;
                 }
-                if (sub == 0 && !exact) ++n_cells;
             }
         };
-        walk(false);
-        int n_in = n_loc, result = one_loc;
+        auto group_count = [&](int &n_in, int &result) {
+            n_in = n_loc;
+            result = one_loc;
 #pragma unroll
-        for (int o = 4; o > 0; o >>= 1) {
-            n_in += __shfl_xor_sync(gmask, n_in, o);
-            result = max(result, __shfl_xor_sync(gmask, result, o));  // the member itself when there is exactly one
+            for (int o = 4; o > 0; o >>= 1) {
+                n_in += __shfl_xor_sync(gmask, n_in, o);
+                result = max(result, __shfl_xor_sync(gmask, result, o));  // the member itself when there is exactly one
+            }
+        };
+        int n_in, result;
+        walk(0);
+        group_count(n_in, result);
+        if (n_in > 1 && two_stage) {
+#pragma unroll
+            for (int o = 4; o > 0; o >>= 1) jmin = fminf(jmin, __shfl_xor_sync(gmask, jmin, o));
+            thr2 = jmin + 2.f * rc.efp;
+            n_loc = 0;
+            one_loc = -1;
+            walk(1);
+            group_count(n_in, result);
         }
-        if (n_in > 1) {  // FP64 with the reference's operation order over the members, first minimum wins
-            walk(true);
+        if (n_in > 1) {  // FP64 with the reference's operation order over the remaining members, first minimum wins
+            walk(2);
 #pragma unroll
             for (int o = 4; o > 0; o >>= 1) {
                 const double oj = __shfl_xor_sync(gmask, bj, o);
@@ -509,119 +567,63 @@ __global__ void __launch_bounds__(256, 3) k_refine_easy(xs_plan pl, Workspace ws
     }
 }
 
-// Pass 2: a warp per hard pixel (RP at a time so that their dependent loads overlap): collects the band members of all
-// contending cells; a single member settles the pixel, several are evaluated in FP64 with the reference's operation order
-// and reduced by a warp-shuffle lexicographic (J, flat index) argmin = numpy's first minimum.
-template <int KP, int RP>
+// Pass 2: a warp per record with more than three contending lanes (rare: flat cost surfaces, equal-cost plateaus).  The
+// contending lanes are looked at whole: every candidate of the lane is re-created in FP32; a single band member settles the
+// pixel, several are evaluated in FP64 with the reference's operation order and reduced by a warp-shuffle lexicographic
+// (J, flat index) argmin = numpy's first minimum.
+template <int KP>
 __global__ void __launch_bounds__(256, 3) k_refine_co(xs_plan pl, Workspace ws, OutSpec out) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int64_t n_hard = (int64_t)ws.counters[12];
     const int n_chunks = (pl.n_wspd_pad + kChunkRows - 1) / kChunkRows;
-    constexpr int kCand = kChunkRows * 2 * KP;
-    constexpr int kIter = (kCand + 31) / 32;
     u64 n_scanned = 0, n_cells = 0, n_fp64 = 0;
-
-    for (int64_t h0 = warp * RP; h0 < n_hard; h0 += n_warps * RP) {
-        PixRec px[RP];
-        RefRec rc[RP];
-        bool act[RP];
-#pragma unroll
-        for (int i = 0; i < RP; ++i) {
-            act[i] = h0 + i < n_hard;
-            if (act[i]) {
-                const unsigned e = ws.hard[h0 + i];
-                px[i] = ws.pix[e];
-                rc[i] = ws.rec[e];
-            }
-        }
-        auto chunk_of = [&](int i, int L) {  // best chunk of cont lane L
-            const int rank = __popc(rc[i].cont & ((1u << L) - 1u));
-            const u64 ids = ((u64)rc[i].ch_hi << 32) | rc[i].ch_lo;
-            return (int)((ids >> (8 * rank)) & 0xffu);
-        };
-        // membership in S of the candidates of the first contender cell of every pixel (loads batched)
-        bool in0[RP][kIter];
-        int flat0[RP][kIter];
-        unsigned rest[RP];  // contender cells not looked at yet
-#pragma unroll
-        for (int i = 0; i < RP; ++i) {
-            rest[i] = act[i] ? rc[i].cont : 0u;
-#pragma unroll
-            for (int q = 0; q < kIter; ++q) {
-                in0[i][q] = false;
-                flat0[i][q] = 0;
-            }
-            if (rest[i]) {  // warp-uniform
-                const int L = __ffs(rest[i]) - 1;
-                rest[i] &= rest[i] - 1;
-                const int row0 = chunk_of(i, L) * kChunkRows;
-#pragma unroll
-                for (int q = 0; q < kIter; ++q) in0[i][q] = band_member<KP>(pl, px[i], rc[i], L, row0, lane + 32 * q, kCand, flat0[i][q]);
-                ++n_cells;
-            }
-        }
-        // count the members, look at the remaining cells, settle
-#pragma unroll
-        for (int i = 0; i < RP; ++i) {
-            if (!act[i]) continue;
-            int n_loc = 0, one_loc = -1;  // members of S seen by this lane so far (count, and the flat index of one of them)
-#pragma unroll
-            for (int q = 0; q < kIter; ++q)
-                if (in0[i][q]) {
-                    ++n_loc;
-                    one_loc = flat0[i][q];
-                }
-            ArgMin am;
-            am.init();
-            const double *slab64 = pl.co_lut + (size_t)px[i].bin * pl.n_wspd * pl.n_phi;
-            // generic walk over cell (L, row0, n_cand): note members (exact == false) or FP64 argmin (true)
-            auto visit = [&](int L, int row0, int n_cand, bool exact) {
+    for (int64_t h = warp; h < n_hard; h += n_warps) {
+        const unsigned e = ws.hard[h];
+        const PixRec px = ws.pix[e];
+        const RefRec rc = ws.rec[e];
+        const double *slab64 = pl.co_lut + (size_t)px.bin * pl.n_wspd * pl.n_phi;
+        const int n_cand = pl.n_wspd * 2 * KP;
+        int n_loc = 0, one_loc = -1;
+        ArgMin am;
+        am.init();
+        auto sweep = [&](bool exact) {
+            unsigned lanes = rc.cont;
+            while (lanes) {
+                const int L = __ffs(lanes) - 1;
+                lanes &= lanes - 1;
                 for (int k0 = 0; k0 < n_cand; k0 += 32) {
                     int flat;
-                    if (!band_member<KP>(pl, px[i], rc[i], L, row0, k0 + lane, n_cand, flat)) continue;
+                    if (!band_member<KP>(pl, px, rc, L, 0, k0 + lane, n_cand, flat)) continue;
                     if (!exact) {
                         ++n_loc;
                         one_loc = flat;
                     } else {
                         const int iw = flat / pl.n_phi, ip = flat - iw * pl.n_phi;
-                        am.feed(exact_cost_co(pl.wspd_grid[iw], pl.cos_phi[ip], pl.sin_phi[ip], slab64[flat], px[i].qa, px[i].qb,
-                                              px[i].s, pl.dsig_co), flat);
+                        am.feed(exact_cost_co(pl.wspd_grid[iw], pl.cos_phi[ip], pl.sin_phi[ip], slab64[flat], px.qa, px.qb, px.s,
+                                              pl.dsig_co), flat);
                     }
                 }
-            };
-            auto sweep = [&](unsigned cells, unsigned lanes, bool exact) {
-                while (cells) {
-                    const int L = __ffs(cells) - 1;
-                    cells &= cells - 1;
-                    visit(L, chunk_of(i, L) * kChunkRows, kCand, exact);
-                    if (!exact) ++n_cells;
-                }
-                while (lanes) {
-                    const int L = __ffs(lanes) - 1;
-                    lanes &= lanes - 1;
-                    visit(L, 0, pl.n_wspd * 2 * KP, exact);
-                    if (!exact) n_cells += n_chunks;
-                }
-            };
-            if (rest[i] | rc[i].wide) sweep(rest[i], rc[i].wide, false);
-            const int n_in = __reduce_add_sync(0xffffffffu, n_loc);
-            int result = __reduce_max_sync(0xffffffffu, one_loc);  // the member itself when n_in == 1
-            if (n_in > 1) {
-                sweep(rc[i].cont, rc[i].wide, true);
-                am.warp_reduce();
-                result = am.result();
-                ++n_fp64;
+                if (!exact) n_cells += n_chunks;
             }
-            if (lane == 0) {
-                if (n_in >= 1)
-                    write_co(pl, out, result, px[i].neg, px[i].px);
-                else  // cannot happen if the re-created costs equal the scan's; be safe
-                    ws.fallback[atomicAdd(&ws.counters[1], 1ull)] = px[i].px;
-            }
-            ++n_scanned;
+        };
+        sweep(false);
+        const int n_in = __reduce_add_sync(0xffffffffu, n_loc);
+        int result = __reduce_max_sync(0xffffffffu, one_loc);  // the member itself when n_in == 1
+        if (n_in > 1) {
+            sweep(true);
+            am.warp_reduce();
+            result = am.result();
+            ++n_fp64;
         }
+        if (lane == 0) {
+            if (n_in >= 1)
+                write_co(pl, out, result, px.neg, px.px);
+            else  // cannot happen if the re-created costs equal the scan's; be safe
+                ws.fallback[atomicAdd(&ws.counters[1], 1ull)] = px.px;
+        }
+        ++n_scanned;
     }
     if (lane == 0) {
         if (n_scanned) atomicAdd(&ws.counters[2], n_scanned);
@@ -659,16 +661,21 @@ int scan_tile_px(int kp) {
 }
 
 template <int KP, int P, int NW, int MB>
-static int launch_shape(const xs_plan *pl, const RasterArgs &ra, const Workspace &ws, const OutSpec &out, int64_t n_px,
-                        xs_timer *timer, cudaStream_t st) {
+static int launch_shape(const xs_plan *pl, const RasterArgs &ra, const Workspace &ws, const unsigned *sorted_px,
+                        const OutSpec &out, int64_t n_px, xs_timer *timer, cudaStream_t st) {
     constexpr int TP = P * NW;
-    static_assert(TP <= kTilePad && TP <= kSortRun, "tile size");
+    static_assert(TP <= kTilePad, "tile size");
     int sms = kNumSMs;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, pl->device);
-    const int64_t max_tiles = ceil_div(n_px, TP) + pl->n_inc;
-    XS_LAUNCH(k_list_prepare, (unsigned)ceil_div(max_tiles, kSortRun / TP), kSortRun, 0, st, *pl, ra, ws, TP);
+    XS_LAUNCH(k_list_prepare, sms * 16, 256, 0, st, *pl, ra, ws, sorted_px, TP);
 
     auto kern = k_scan_co<KP, P, NW, MB>;
+    // largest estimated 2 |sigma| Lam for which a warp scans in shared-sigma0 mode (XS_SHARE_BUDGET: development aid; 0 = never)
+    static float share_tau = -1.f;
+    if (share_tau < 0.f) {
+        const char *e = getenv("XS_SHARE_BUDGET");
+        share_tau = e ? (float)atof(e) : 0.02f;
+    }
     const size_t smem = sizeof(ScanSmem<KP, P, NW>) + sizeof(float2) * (size_t)pl->n_wspd_pad;
     if (smem > 200 * 1024) {
         set_error("xs_invert: wspd grid too long for the shared-memory row table");
@@ -680,10 +687,10 @@ static int launch_shape(const xs_plan *pl, const RasterArgs &ra, const Workspace
     XS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NW * 32, smem));
     if (per_sm < 1) per_sm = 1;
     if (timer) XS_CUDA(cudaEventRecord(timer->ev[0], st));
-    XS_LAUNCH(kern, sms * per_sm, NW * 32, smem, st, *pl, ws);
+    XS_LAUNCH(kern, sms * per_sm, NW * 32, smem, st, *pl, ws, share_tau);
     if (timer) XS_CUDA(cudaEventRecord(timer->ev[1], st));
     XS_LAUNCH(k_refine_easy<KP>, sms * 6, 256, 0, st, *pl, ws, out, TP);
-    XS_LAUNCH((k_refine_co<KP, 2>), sms * 6, 256, 0, st, *pl, ws, out);
+    XS_LAUNCH(k_refine_co<KP>, sms * 6, 256, 0, st, *pl, ws, out);
     if (timer) {
         XS_CUDA(cudaEventRecord(timer->ev[2], st));
         timer->recorded = 1;
@@ -691,11 +698,11 @@ static int launch_shape(const xs_plan *pl, const RasterArgs &ra, const Workspace
     return XS_OK;
 }
 
-int launch_scan_pipeline(const xs_plan *pl, const RasterArgs &ra, const Workspace &ws, const OutSpec &out, int64_t n_px,
-                         xs_timer *timer, cudaStream_t st) {
+int launch_scan_pipeline(const xs_plan *pl, const RasterArgs &ra, const Workspace &ws, const unsigned *sorted_px,
+                         const OutSpec &out, int64_t n_px, xs_timer *timer, cudaStream_t st) {
     const Shape s = scan_shape(pl->kp);
 #define XS_SHAPE(KP_, P_, MB_) \
-    if (pl->kp == KP_ && s.p == P_ && s.mb == MB_) return launch_shape<KP_, P_, 4, MB_>(pl, ra, ws, out, n_px, timer, st)
+    if (pl->kp == KP_ && s.p == P_ && s.mb == MB_) return launch_shape<KP_, P_, 4, MB_>(pl, ra, ws, sorted_px, out, n_px, timer, st)
     XS_SHAPE(1, 8, 4);
     XS_SHAPE(2, 8, 4);
     XS_SHAPE(3, 8, 4);
