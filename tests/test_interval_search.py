@@ -4,8 +4,9 @@ A statement-by-statement Python transcription of the device function (float64 ar
 involved) against the brute-force first-minimum argmin of the reference's cost (windspeed.py:254-269) on seeded
 adversarial rows: strictly increasing, plateaus (runs of equal LUT values -> runs of equal costs), two-valued rows,
 sigma0 on nodes and midpoints, |wind_co| on nodes and midpoints, dsig from 1e-8 to 1e4, sigma0 far outside the row.
-This pins the monotonicity argument (the candidate set is an index interval found by bisection) independently of the
-GPU; the GPU test `test_cross_pol_filter_adversarial` pins the implementation."""
+This pins the monotonicity argument (the candidate set is an index interval; its ends are found from guessed brackets --
+inverse index of the row, uniform-grid guess -- verified and widened when wrong, and by galloping outwards from the valley
+bottoms) independently of the GPU; the GPU test `test_cross_pol_filter_adversarial` pins the implementation."""
 import math
 
 import numpy as np
@@ -20,18 +21,53 @@ def cost(col, wg, s, dsig, mag, hc, w):
     return J
 
 
-def interval_search(col, wg, s, dsig, mag, hc):
+NB = 1024   # kCrInvBuckets
+
+
+def inverse_index(col):
+    """k_build_cr_tables: inv[b] = first w with col[w] >= vlo + b / scale (b < NB), inv[NB] = n."""
+    n = len(col)
+    vlo, vhi = col[0], col[-1]
+    usable = vhi > vlo and math.isfinite(vhi - vlo)
+    scale = NB / (vhi - vlo) if usable else 0.0
+    inv, w = [], 0
+    for b in range(NB):
+        if usable:
+            edge = vlo + b / scale
+            while w < n and col[w] < edge:
+                w += 1
+        inv.append(w if usable else 0)
+    inv.append(n)
+    return (vlo if usable else 0.0), scale, inv
+
+
+def interval_search(col, wg, s, dsig, mag, hc, tables=None, wspd_uniform=None):
     n = len(col)
     num = lambda w: col[w] - s
     tw_at = lambda w: (wg[w] - mag) * 0.5
-    lo, hi = 0, n
-    while lo < hi:
-        mid = (lo + hi) >> 1
-        if num(mid) < 0.0:
-            lo = mid + 1
-        else:
-            hi = mid
-    k = lo
+
+    def first_ge(lo, hi, ge):
+        lo0, hi0 = lo, hi
+        while lo < hi:
+            mid = (lo + hi) >> 1
+            if not ge(mid):
+                lo = mid + 1
+            else:
+                hi = mid
+        if (lo == lo0 and lo > 0 and ge(lo - 1)) or (lo == hi0 and lo < n and not ge(lo)):
+            lo, hi = 0, n
+            while lo < hi:
+                mid = (lo + hi) >> 1
+                if not ge(mid):
+                    lo = mid + 1
+                else:
+                    hi = mid
+        return lo
+
+    vlo, scale, inv = tables if tables is not None else inverse_index(col)
+    t = (s - vlo) * scale
+    b = int(min(t, NB - 1)) if t > 0.0 else 0
+    k = first_ge(inv[max(b - 1, 0)], inv[min(b + 2, NB)], lambda w: not (num(w) < 0.0))
     m0 = math.inf
     if k < n:
         m0 = cost(col, wg, s, dsig, mag, hc, k)
@@ -40,13 +76,12 @@ def interval_search(col, wg, s, dsig, mag, hc):
     j = 0
     if hc:
         lo, hi = 0, n
-        while lo < hi:
-            mid = (lo + hi) >> 1
-            if tw_at(mid) < 0.0:
-                lo = mid + 1
-            else:
-                hi = mid
-        j = lo
+        if wspd_uniform is not None:
+            g0, inv_step = wspd_uniform
+            t = (mag - g0) * inv_step
+            g = 0 if t <= 0.0 else (n if t >= n else int(t))
+            lo, hi = max(g - 1, 0), min(g + 2, n)
+        j = first_ge(lo, hi, lambda w: not (tw_at(w) < 0.0))
         if j < n:
             m0 = min(m0, cost(col, wg, s, dsig, mag, hc, j))
         if j > 0:
@@ -67,41 +102,50 @@ def interval_search(col, wg, s, dsig, mag, hc):
         t = v / dsig
         return t * t > m0
 
-    lo, hi = 0, k
-    while lo < hi:
-        mid = (lo + hi) >> 1
-        if a_gt_m0(mid):
-            lo = mid + 1
-        else:
-            hi = mid
-    first = lo
-    lo, hi = k, n
-    while lo < hi:
-        mid = (lo + hi) >> 1
-        if not a_gt_m0(mid):
-            lo = mid + 1
-        else:
-            hi = mid
-    last = lo
+    def b_gt_m0(w):
+        t = tw_at(w)
+        return t * t > m0
+
+    def left_end(c, gt):
+        ok, bad, step, pos = c, -1, 1, c - 1
+        while pos >= 0:
+            if gt(pos):
+                bad = pos
+                break
+            ok = pos
+            pos -= step
+            step <<= 1
+        lo, hi = bad + 1, ok
+        while lo < hi:
+            mid = (lo + hi) >> 1
+            if gt(mid):
+                lo = mid + 1
+            else:
+                hi = mid
+        return lo
+
+    def right_end(c, gt):
+        ok, bad, step, pos = c - 1, n, 1, c
+        while pos < n:
+            if gt(pos):
+                bad = pos
+                break
+            ok = pos
+            pos += step
+            step <<= 1
+        lo, hi = ok + 1, bad
+        while lo < hi:
+            mid = (lo + hi) >> 1
+            if not gt(mid):
+                lo = mid + 1
+            else:
+                hi = mid
+        return lo
+
+    first, last = left_end(k, a_gt_m0), right_end(k, a_gt_m0)
     if hc:
-        lo, hi = 0, j
-        while lo < hi:
-            mid = (lo + hi) >> 1
-            t = tw_at(mid)
-            if t * t > m0:
-                lo = mid + 1
-            else:
-                hi = mid
-        first = max(first, lo)
-        lo, hi = j, n
-        while lo < hi:
-            mid = (lo + hi) >> 1
-            t = tw_at(mid)
-            if t * t <= m0:
-                lo = mid + 1
-            else:
-                hi = mid
-        last = min(last, lo)
+        first = max(first, left_end(j, b_gt_m0))
+        last = min(last, right_end(j, b_gt_m0))
     best, res = math.inf, -1
     for w in range(first, last):
         J = cost(col, wg, s, dsig, mag, hc, w)
@@ -149,7 +193,8 @@ def test_interval_search_equals_brute_force():
                     tw = (wg - mag) * 0.5
                     J = J + tw * tw
             want = int(np.argmin(J))                                      # first minimum, like the reference
-            got = interval_search(col, wg, s, dsig, mag, hc)
+            hint = (float(wg[0]), 1.0 / ((wg[-1] - wg[0]) / (len(wg) - 1))) if trial % 4 < 2 else None   # the uniform-grid guess
+            got = interval_search(col, wg, s, dsig, mag, hc, wspd_uniform=hint)
             if got == -1:                                                 # every cost overflowed: the kernel falls back
                 assert not np.isfinite(J).any() or not np.isfinite(J.min())
                 continue

@@ -11,6 +11,7 @@
 namespace xs {
 
 void set_error(const char *fmt, ...);
+void keep_async_pool();
 extern std::atomic<int64_t> g_launches;  // concurrent host threads launch through the same library
 
 inline int check(cudaError_t e, const char *what) {

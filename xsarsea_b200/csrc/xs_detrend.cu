@@ -113,6 +113,7 @@ extern "C" int xs_detrend(const void *sigma0, const double *gmf_line, int64_t n_
     if (n_lines == 0) return XS_OK;
     cudaStream_t st = (cudaStream_t)stream;
     double *ratio = nullptr;
+    keep_async_pool();
     XS_CUDA(cudaMallocAsync(&ratio, 2 * sizeof(double) * (size_t)n_samples, st));
     double *rinv = ratio + n_samples;
     XS_LAUNCH(k_detrend_ratio, 1, 1024, 0, stream, gmf_line, n_samples, ratio, rinv);

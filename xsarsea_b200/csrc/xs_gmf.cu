@@ -235,6 +235,7 @@ extern "C" int xs_lut_build(int model_id, const double *inc_h, int n_inc, const 
     cudaStream_t st = (cudaStream_t)stream;
     double *grids = nullptr;
     const size_t ng = (size_t)n_inc + n_wspd + np;
+    keep_async_pool();
     XS_CUDA(cudaMallocAsync(&grids, ng * sizeof(double), st));
     XS_CUDA(cudaMemcpyAsync(grids, inc_h, n_inc * sizeof(double), cudaMemcpyHostToDevice, st));
     XS_CUDA(cudaMemcpyAsync(grids + n_inc, wspd_h, n_wspd * sizeof(double), cudaMemcpyHostToDevice, st));

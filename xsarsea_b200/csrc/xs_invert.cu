@@ -20,7 +20,7 @@
 namespace xs {
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
-size_t ws_layout(int n_inc, int64_t n_px, unsigned flags, char *base, Workspace *w) {
+size_t ws_layout(int n_inc, int64_t n_px, unsigned flags, size_t sort_bytes, char *base, Workspace *w) {
     size_t off = 0;
     auto take = [&](size_t bytes) {
         char *p = base ? base + off : nullptr;
@@ -39,7 +39,7 @@ size_t ws_layout(int n_inc, int64_t n_px, unsigned flags, char *base, Workspace 
     char *k1 = take(sizeof(unsigned) * (size_t)n_sort);
     char *v0 = take(sizeof(unsigned) * (size_t)n_sort);
     char *v1 = take(sizeof(unsigned) * (size_t)n_sort);
-    const size_t sort_bytes = n_inc > 0 ? kSortTempBytes : 0;
+    if (n_inc <= 0) sort_bytes = 0;
     char *st = take(sort_bytes);
     char *fb = take(sizeof(unsigned) * (size_t)n_sort);
     char *pr = take(sizeof(PixRec) * (size_t)n_list);
@@ -135,6 +135,21 @@ __global__ void k_build_cr_tables(xs_plan pl) {
         }
         pl.cr_finite[i] = ok | ((ok & mono) << 1);
         pl.cr_absmax[i] = amax;
+        // inverse index of a monotone row (see xs_plan::cr_inv)
+        const double *col = pl.cr_lut + (int64_t)i * pl.n_wspd_cr;
+        unsigned short *inv = pl.cr_inv + (int64_t)i * (kCrInvBuckets + 1);
+        const double vlo = col[0], vhi = col[pl.n_wspd_cr - 1];
+        const bool usable = ok && mono && vhi > vlo && isfinite(vhi - vlo);
+        const double scale = usable ? (double)kCrInvBuckets / (vhi - vlo) : 0.0;
+        pl.cr_vlo[i] = usable ? vlo : 0.0;
+        pl.cr_vscale[i] = scale;
+        int w = 0;
+        for (int b = 0; b < kCrInvBuckets; ++b) {
+            const double edge = vlo + (double)b / scale;
+            while (usable && w < pl.n_wspd_cr && col[w] < edge) ++w;
+            inv[b] = (unsigned short)(usable ? w : 0);
+        }
+        inv[kCrInvBuckets] = (unsigned short)pl.n_wspd_cr;
     }
 }
 __global__ void k_fix_first_nan(xs_plan pl) {
@@ -288,34 +303,56 @@ __device__ __forceinline__ double exact_cost_cr(double L, double s, double dsig,
 // that can be the argmin (J <= m0, ties included) has a <= m0 and b <= m0, and each of these sets is an index interval
 // whose ends are found by bisection.  The interval is then scanned in index order with the reference's operations
 // (first minimum wins, like np.argmin).  Returns -1 when no finite bound exists (caller falls back to the full scan).
-__device__ __forceinline__ int cross_interval_search(const double *__restrict__ col, const double *__restrict__ wg, int n,
-                                                     double s, double dsig, double mag, bool hc) {
+__device__ __forceinline__ int cross_interval_search(const xs_plan &pl, int bin, const double *__restrict__ col,
+                                                     const double *__restrict__ wg, int n, double s, double dsig, double mag,
+                                                     bool hc) {
     auto num_at = [=](int w) { return __dsub_rn(col[w], s); };  // ts = num/dsig has the sign of num (dsig > 0)
     auto tw_at = [=](int w) { return __dmul_rn(__dsub_rn(wg[w], mag), 0.5); };
     auto cost = [=](int w) { return exact_cost_cr(col[w], s, dsig, wg[w], mag, hc); };
-    int lo = 0, hi = n;  // k = first w with num(w) >= 0
-    while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (num_at(mid) < 0.0)
-            lo = mid + 1;
-        else
-            hi = mid;
-    }
-    const int k = lo;
-    double m0 = CUDART_INF;
-    if (k < n) m0 = cost(k);
-    if (k > 0) m0 = fmin(m0, cost(k - 1));
-    int j = 0;
-    if (hc) {
-        lo = 0, hi = n;  // j = first w with tw(w) >= 0
+    // first index of a non-decreasing sequence that satisfies `ge`, searched from a guessed bracket [lo, hi] that is widened
+    // by bisection over everything if the final check fails (so a wrong guess costs time, never correctness)
+    auto first_ge = [=](int lo, int hi, auto ge) {
+        const int lo0 = lo, hi0 = hi;
         while (lo < hi) {
             const int mid = (lo + hi) >> 1;
-            if (tw_at(mid) < 0.0)
+            if (!ge(mid))
                 lo = mid + 1;
             else
                 hi = mid;
         }
-        j = lo;
+        if ((lo == lo0 && lo > 0 && ge(lo - 1)) || (lo == hi0 && lo < n && !ge(lo))) {
+            lo = 0, hi = n;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (!ge(mid))
+                    lo = mid + 1;
+                else
+                    hi = mid;
+            }
+        }
+        return lo;
+    };
+    // k = first w with num(w) >= 0, i.e. col[w] >= s: bracket from the row's inverse index
+    int k;
+    {
+        const double t = (s - pl.cr_vlo[bin]) * pl.cr_vscale[bin];
+        const int b = t > 0.0 ? (int)fmin(t, (double)(kCrInvBuckets - 1)) : 0;
+        const unsigned short *inv = pl.cr_inv + (int64_t)bin * (kCrInvBuckets + 1);
+        k = first_ge(inv[max(b - 1, 0)], inv[min(b + 2, kCrInvBuckets)], [=](int w) { return !(num_at(w) < 0.0); });
+    }
+    double m0 = CUDART_INF;
+    if (k < n) m0 = cost(k);
+    if (k > 0) m0 = fmin(m0, cost(k - 1));
+    int j = 0;
+    if (hc) {  // j = first w with tw(w) >= 0, i.e. wg[w] >= mag
+        int lo = 0, hi = n;
+        if (pl.wspd_cr_uniform) {
+            const double t = (mag - pl.wspd_cr_g0) * pl.wspd_cr_inv_step;
+            const int g = t <= 0.0 ? 0 : (t >= (double)n ? n : (int)t);
+            lo = max(g - 1, 0);
+            hi = min(g + 2, n);
+        }
+        j = first_ge(lo, hi, [=](int w) { return !(tw_at(w) < 0.0); });
         if (j < n) m0 = fmin(m0, cost(j));
         if (j > 0) m0 = fmin(m0, cost(j - 1));
     }
@@ -334,46 +371,55 @@ __device__ __forceinline__ int cross_interval_search(const double *__restrict__ 
         const double t = __ddiv_rn(num, dsig);
         return __dmul_rn(t, t) > m0;
     };
-    // [first, last): candidates with a(w) <= m0 (a is non-increasing left of k, non-decreasing from k on)
-    lo = 0, hi = k;
-    while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (a_gt_m0(mid))
-            lo = mid + 1;
-        else
-            hi = mid;
-    }
-    int first = lo;
-    lo = k, hi = n;
-    while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (!a_gt_m0(mid))
-            lo = mid + 1;
-        else
-            hi = mid;
-    }
-    int last = lo;
+    auto b_gt_m0 = [=](int w) {
+        const double t = tw_at(w);
+        return __dmul_rn(t, t) > m0;
+    };
+    // Ends of {w : x(w) <= m0} around the valley bottom c (x non-increasing left of c, non-decreasing from c on): the set
+    // is a handful of nodes, so its ends are found by galloping outwards from c (1, 2, 4, ... nodes) and bisecting the last
+    // stride, instead of bisecting [0, c) and [c, n).
+    auto left_end = [=](int c, auto gt) {  // smallest w in [0, c] with !gt on [w, c)
+        int ok = c, bad = -1, step = 1;
+        for (int pos = c - 1; pos >= 0; pos -= step, step <<= 1) {
+            if (gt(pos)) {
+                bad = pos;
+                break;
+            }
+            ok = pos;
+        }
+        int lo = bad + 1, hi = ok;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (gt(mid))
+                lo = mid + 1;
+            else
+                hi = mid;
+        }
+        return lo;
+    };
+    auto right_end = [=](int c, auto gt) {  // smallest w in [c, n] with gt(w) (n if none)
+        int ok = c - 1, bad = n, step = 1;
+        for (int pos = c; pos < n; pos += step, step <<= 1) {
+            if (gt(pos)) {
+                bad = pos;
+                break;
+            }
+            ok = pos;
+        }
+        int lo = ok + 1, hi = bad;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (!gt(mid))
+                lo = mid + 1;
+            else
+                hi = mid;
+        }
+        return lo;
+    };
+    int first = left_end(k, a_gt_m0), last = right_end(k, a_gt_m0);
     if (hc) {  // intersect with the candidates with b(w) <= m0
-        lo = 0, hi = j;
-        while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            const double t = tw_at(mid);
-            if (__dmul_rn(t, t) > m0)
-                lo = mid + 1;
-            else
-                hi = mid;
-        }
-        first = max(first, lo);
-        lo = j, hi = n;
-        while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            const double t = tw_at(mid);
-            if (__dmul_rn(t, t) <= m0)
-                lo = mid + 1;
-            else
-                hi = mid;
-        }
-        last = min(last, lo);
+        first = max(first, left_end(j, b_gt_m0));
+        last = min(last, right_end(j, b_gt_m0));
     }
     double best = CUDART_INF;
     int res = -1;
@@ -409,7 +455,7 @@ __global__ void __launch_bounds__(256) k_cross(xs_plan pl, RasterArgs a, int64_t
         p.cls = 0;
         p.co = 0;
         p.s_cr = p.dsig_cr = p.inc = nan;
-        if (valid) p = load_pixel(pl, a, px);
+        if (valid) p = load_pixel(pl, a, px, false);
         double2 co = make_double2(nan, 0.0), dual = make_double2(nan, 0.0);
         bool scan = false, has_co = false, filter_ok = false;
         int bin = 0, ix = -1;
@@ -420,8 +466,9 @@ __global__ void __launch_bounds__(256) k_cross(xs_plan pl, RasterArgs a, int64_t
             dual = make_double2(nan, nan);
             if (!isnan(p.s_cr) && !isnan(p.dsig_cr) && pl.n_inc_cr > 0) {
                 scan = true;
-                bin = nearest_bin(pl.inc_cr_grid, pl.n_inc_cr, p.inc, pl.inc_cr_sorted);
-                mag = hypot(co.x, co.y);
+                bin = pl.inc_cr_uniform ? nearest_bin_uniform(pl.inc_cr_grid, pl.n_inc_cr, p.inc, pl.inc_cr_g0, pl.inc_cr_inv_step)
+                                        : nearest_bin(pl.inc_cr_grid, pl.n_inc_cr, p.inc, pl.inc_cr_sorted);
+                mag = p.co ? hypot(co.x, co.y) : nan;
                 has_co = !isnan(mag);
                 filter_ok = isfinite(p.s_cr) && isfinite(p.dsig_cr) && p.dsig_cr != 0.0 && (!has_co || isfinite(mag)) &&
                             pl.cr_finite[bin];
@@ -433,8 +480,8 @@ __global__ void __launch_bounds__(256) k_cross(xs_plan pl, RasterArgs a, int64_t
         bool settled_own = false;
         if (scan && filter_ok && p.dsig_cr > 0.0 && (pl.cr_finite[bin] & 2) && pl.wspd_cr_sorted &&
             !(a.flags & XS_FLAG_CR_FULL_SCAN)) {
-            const int r = cross_interval_search(pl.cr_lut + (int64_t)bin * pl.n_wspd_cr, pl.wspd_cr_grid, pl.n_wspd_cr, p.s_cr,
-                                                p.dsig_cr, mag, has_co);
+            const int r = cross_interval_search(pl, bin, pl.cr_lut + (int64_t)bin * pl.n_wspd_cr, pl.wspd_cr_grid, pl.n_wspd_cr,
+                                                p.s_cr, p.dsig_cr, mag, has_co);
             if (r >= 0) {
                 ix = r;
                 settled_own = true;
@@ -539,7 +586,7 @@ __global__ void __launch_bounds__(256) k_cross(xs_plan pl, RasterArgs a, int64_t
                 if (aco < 5.0 || adu < 5.0) o = co;
             }
             if (a.flags & XS_FLAG_CR_ABS)
-                reinterpret_cast<double *>(out_cr)[px] = hypot(o.x, o.y);
+                reinterpret_cast<double *>(out_cr)[px] = o.y == 0.0 ? fabs(o.x) : hypot(o.x, o.y);
             else
                 store_wind(out, out_cr, px, o);
         }
@@ -582,6 +629,9 @@ extern "C" void xs_plan_destroy(xs_plan *pl) {
     cudaFree(pl->cr_scan);
     cudaFree(pl->cr_absmax);
     cudaFree(pl->cr_finite);
+    cudaFree(pl->cr_inv);
+    cudaFree(pl->cr_vlo);
+    cudaFree(pl->cr_vscale);
     delete pl;
 }
 
@@ -667,6 +717,24 @@ extern "C" int xs_plan_create(const xs_plan_desc *d, void *stream, xs_plan **out
         for (int i = 0; i < d->n_wspd_cr; ++i) wcmax = fmax(wcmax, fabs(d->wspd_cr_grid_host[i]));
         pl->w_cr_absmax = wcmax;
         if ((rc = xs::check(cudaMalloc(&pl->cr_finite, sizeof(int) * (size_t)d->n_inc_cr), "cudaMalloc")) != XS_OK) return fail(rc);
+        if (d->n_wspd_cr >= 65535) {
+            set_error("xs_plan_create: cross-pol wspd grid too long");
+            return fail(XS_E_UNSUPPORTED);
+        }
+        if ((rc = xs::check(cudaMalloc(&pl->cr_inv, sizeof(unsigned short) * (size_t)d->n_inc_cr * (kCrInvBuckets + 1)), "cudaMalloc")) != XS_OK) return fail(rc);
+        if ((rc = xs::check(cudaMalloc(&pl->cr_vlo, sizeof(double) * (size_t)d->n_inc_cr), "cudaMalloc")) != XS_OK) return fail(rc);
+        if ((rc = xs::check(cudaMalloc(&pl->cr_vscale, sizeof(double) * (size_t)d->n_inc_cr), "cudaMalloc")) != XS_OK) return fail(rc);
+        auto uniform = [](const double *g, int n, double *g0, double *inv_step) {  // ascending and within 1 % of a constant step
+            if (n < 2 || !strictly_ascending(g, n)) return 0;
+            const double step = (g[n - 1] - g[0]) / (n - 1);
+            for (int i = 1; i < n; ++i)
+                if (fabs((g[i] - g[i - 1]) - step) > 0.01 * step) return 0;
+            *g0 = g[0];
+            *inv_step = 1.0 / step;
+            return 1;
+        };
+        pl->inc_cr_uniform = uniform(d->inc_cr_grid_host, d->n_inc_cr, &pl->inc_cr_g0, &pl->inc_cr_inv_step);
+        pl->wspd_cr_uniform = uniform(d->wspd_cr_grid_host, d->n_wspd_cr, &pl->wspd_cr_g0, &pl->wspd_cr_inv_step);
     }
     auto build = [&]() -> int {
         if (has_cr) {
@@ -694,7 +762,7 @@ extern "C" int xs_plan_create(const xs_plan_desc *d, void *stream, xs_plan **out
 
 extern "C" size_t xs_invert_workspace_bytes(const xs_plan *pl, int64_t n_px, uint32_t flags) {
     if (!pl || n_px < 0) return 0;
-    return ws_layout(pl->fast_ok ? pl->n_inc : 0, n_px, flags, nullptr, nullptr);
+    return ws_layout(pl->fast_ok ? pl->n_inc : 0, n_px, flags, pl->fast_ok ? sort_temp_bytes(n_px) : 0, nullptr, nullptr);
 }
 
 extern "C" int xs_timer_create(xs_timer **out) {
@@ -772,7 +840,8 @@ extern "C" int xs_invert(const xs_plan *pl, const xs_invert_args *ar, void *stre
     int sms = kNumSMs;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, pl->device);
 
-    const size_t need = ws_layout(pl->fast_ok ? pl->n_inc : 0, n, ar->flags, nullptr, nullptr);
+    const size_t sort_bytes = pl->fast_ok ? sort_temp_bytes(n) : 0;  // host-side query of CUB, no launch
+    const size_t need = ws_layout(pl->fast_ok ? pl->n_inc : 0, n, ar->flags, sort_bytes, nullptr, nullptr);
     if (!ar->workspace || ar->workspace_bytes < need) {
         set_error("xs_invert: workspace too small (%zu < %zu)", ar->workspace_bytes, need);
         return XS_E_WORKSPACE;
@@ -782,7 +851,7 @@ extern "C" int xs_invert(const xs_plan *pl, const xs_invert_args *ar, void *stre
         return XS_E_INVALID;
     }
     Workspace ws;
-    ws_layout(pl->fast_ok ? pl->n_inc : 0, n, ar->flags, (char *)ar->workspace, &ws);
+    ws_layout(pl->fast_ok ? pl->n_inc : 0, n, ar->flags, sort_bytes, (char *)ar->workspace, &ws);
     OutSpec out;
     out.co = ar->out_co;
     out.cr = ar->out_cr;

@@ -35,6 +35,13 @@ struct xs_plan {
                            // non-decreasing in wspd (the exact interval search of k_cross applies)
     int inc_cr_sorted;
     int wspd_cr_sorted;    // wspd_cr_grid strictly ascending
+    // inverse index of the monotone cross-pol rows: cr_inv[row][b] = first wspd index whose LUT value is >= cr_vlo[row] +
+    // b / cr_vscale[row], b = 0 .. kCrInvBuckets (the last entry is n_wspd_cr): one table look-up replaces most of a bisection
+    unsigned short *cr_inv;
+    double *cr_vlo, *cr_vscale;
+    // uniform grids (np.linspace): a direct index guess replaces the bisection of nearest_bin / of the wspd sign change
+    double inc_cr_g0, inc_cr_inv_step, wspd_cr_g0, wspd_cr_inv_step;
+    int inc_cr_uniform, wspd_cr_uniform;
     int device;
     // nothing mutable lives here: counters, timers and workspaces belong to the xs_invert call (ABI 2), so one plan
     // serves concurrent calls from several host threads / streams
@@ -50,6 +57,7 @@ namespace xs {
 constexpr int kChunkRows = 16;     // wspd rows per staged chunk = granularity of the argmin bookkeeping
 constexpr int kRowPad = 8;         // the scan image pads the wspd axis to a multiple of this (+inf rows)
 constexpr int kStages = 3;         // shared-memory ring depth of the scan
+constexpr int kCrInvBuckets = 1024;
 constexpr float kBandMargin = 0.5f;  // every accepted error band is narrower than this (2 E < kBandMargin)
 constexpr int kTilePad = 32;       // upper bound of the pixels per scan tile (the bin segments of the pixel list are padded to tiles)
 constexpr int kMaxIncBins = 6144;  // bins whose two shared-memory histograms (k_bin_scatter) fit the default 48 KB
@@ -93,6 +101,24 @@ __device__ __forceinline__ int nearest_bin(const double *__restrict__ grid, int 
     return (dl <= dr) ? lo - 1 : lo;
 }
 
+// the same with a direct first guess on a (nearly) uniform ascending grid: the guess is moved to the local minimum of
+// |grid - v|, which is the global one on a sorted grid; ties to the lower index like np.argmin
+__device__ __forceinline__ int nearest_bin_uniform(const double *__restrict__ grid, int n, double v, double g0, double inv_step) {
+    if (isinf(v)) return 0;
+    const double t = (v - g0) * inv_step;
+    int i = t <= 0.0 ? 0 : (t >= (double)(n - 1) ? n - 1 : (int)(t + 0.5));
+    double d = fabs(grid[i] - v);
+    while (i > 0 && fabs(grid[i - 1] - v) <= d) {
+        --i;
+        d = fabs(grid[i] - v);
+    }
+    while (i + 1 < n && fabs(grid[i + 1] - v) < d) {
+        ++i;
+        d = fabs(grid[i] - v);
+    }
+    return i;
+}
+
 // isnan(np.abs(z)) for complex z: np.abs is hypot, which is inf (not NaN) when either part is infinite.
 __device__ __forceinline__ bool cplx_abs_is_nan(double2 z) {
     return (isnan(z.x) || isnan(z.y)) && !(isinf(z.x) || isinf(z.y));
@@ -130,7 +156,8 @@ __device__ __forceinline__ bool pixel_co_bin(const xs_plan &pl, const RasterArgs
     return true;
 }
 
-__device__ __forceinline__ Pixel load_pixel(const xs_plan &pl, const RasterArgs &a, int64_t i) {
+// co_db = false: s_co only tells NaN (no co-pol inversion) from not-NaN, without the log10 (the cross-pol pass)
+__device__ __forceinline__ Pixel load_pixel(const xs_plan &pl, const RasterArgs &a, int64_t i, bool co_db = true) {
     Pixel p;
     p.inc = load_real(a.inc, i, a.dtype);
     const bool db = a.flags & XS_FLAG_SIGMA0_DB;
@@ -138,7 +165,10 @@ __device__ __forceinline__ Pixel load_pixel(const xs_plan &pl, const RasterArgs 
     p.s_cr = CUDART_NAN;
     if (a.s_co) {
         const double s = load_real(a.s_co, i, a.dtype);
-        p.s_co = db ? s : to_db(s);
+        if (co_db)
+            p.s_co = db ? s : to_db(s);
+        else  // log10(s + 1e-15) is NaN exactly for a NaN or negative argument
+            p.s_co = (isnan(s) || (!db && s + 1e-15 < 0.0)) ? CUDART_NAN : 0.0;
     }
     double s_cr_raw = CUDART_NAN;
     if (a.s_cr) {
@@ -323,7 +353,7 @@ struct Workspace {
     int *idx_tmp;          // [n_px] co-pol argmin when the caller gave no idx_co and the outputs are speed/direction planes
     int64_t n_list;        // n_px + kTilePad * n_inc rounded up to a sort run
 };
-size_t ws_layout(int n_inc, int64_t n_px, unsigned flags, char *base, Workspace *w);
+size_t ws_layout(int n_inc, int64_t n_px, unsigned flags, size_t sort_bytes, char *base, Workspace *w);
 
 // ---- outputs ---------------------------------------------------------------------------------------------------------
 // complex128 per pixel (the reference's return type), or -- XS_FLAG_OUT_SPEED_DIR -- two planes [speed | direction] of
@@ -381,7 +411,7 @@ __device__ __forceinline__ void write_co(const xs_plan &pl, const OutSpec &o, in
     if (!(o.flags & XS_FLAG_OUT_SPEED_DIR)) reinterpret_cast<double2 *>(o.co)[px] = co_from_idx(pl, idx, anc_im_neg);
 }
 
-constexpr size_t kSortTempBytes = 16u << 20;  // CUB radix sort scratch with double buffers: per-pass histograms only
+size_t sort_temp_bytes(int64_t n);  // CUB radix sort scratch for n (key, value) pairs with double buffers (host-side query)
 int sort_pairs_u32(unsigned *keys[2], unsigned *vals[2], int64_t n, void *temp, size_t temp_bytes, cudaStream_t st, int *which);
 int launch_scan_pipeline(const xs_plan *pl, const RasterArgs &ra, const Workspace &ws, const unsigned *sorted_px,
                          const OutSpec &out, int64_t n_px, xs_timer *timer, cudaStream_t st);

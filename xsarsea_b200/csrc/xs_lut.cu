@@ -13,6 +13,21 @@ namespace xs {
 static thread_local char g_err[512] = "";
 std::atomic<int64_t> g_launches{0};
 
+// The stream-ordered allocations of this library (small scratch buffers) stay in the device's default pool instead of going
+// back to the OS at every synchronisation: once per device.
+void keep_async_pool() {
+    static std::atomic<unsigned long long> done{0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev > 63) return;
+    if (done.load() & (1ull << dev)) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        unsigned long long thr = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    done.fetch_or(1ull << dev);
+}
+
 void set_error(const char *fmt, ...) {
     va_list ap;
     va_start(ap, fmt);
@@ -100,6 +115,7 @@ extern "C" int xs_lut_interp_axis(const double *src, int64_t outer, int n_src, i
     char *buf = nullptr;
     const size_t nb_i = sizeof(int) * n_dst, nb_d = sizeof(double) * n_dst;
     const size_t off_w = (nb_i + 15) / 16 * 16;
+    keep_async_pool();
     XS_CUDA(cudaMallocAsync(&buf, off_w + 2 * nb_d, st));
     XS_CUDA(cudaMemcpyAsync(buf, hi.data(), nb_i, cudaMemcpyHostToDevice, st));
     XS_CUDA(cudaMemcpyAsync(buf + off_w, wh.data(), nb_d, cudaMemcpyHostToDevice, st));

@@ -444,12 +444,23 @@ __global__ void __launch_bounds__(256, 3) k_refine_easy(xs_plan pl, Workspace ws
         // rarely as without sharing.
         const bool two_stage = rc.nq == 0.f;
         const float kfull = (float)(-2.0 * (px.s / pl.dsig_co - (double)rc.cs));
-        float thr2 = CUDART_INF_F, jmin = CUDART_INF_F;
-        int n_loc = 0, one_loc = -1;
-        double bj = CUDART_INF;  // FP64 pass: lexicographic (J, flat index) minimum of this lane's members
+        float thr2 = CUDART_INF_F;
+        // every lane keeps its two best members (second-filter cost, flat index) and the value of its third best: almost
+        // always that is all of them, and the pixel is settled without walking the cells again
+        float b1 = CUDART_INF_F, b2 = CUDART_INF_F, b3 = CUDART_INF_F;
+        int f1 = -1, f2 = -1, n_loc = 0, one_loc = -1;
+        double bj = CUDART_INF;  // FP64: lexicographic (J, flat index) minimum of this lane's members
         int bi = 0x7fffffff;
-        // walk the cont cells.  stage 0: count the band members (and note the smallest full cost); 1: count the members that
-        // pass the second filter; 2: evaluate them in FP64
+        auto fp64_feed = [&](int flat) {  // J is never NaN here: finite inputs, NaN-free slab
+            const int iw = flat / pl.n_phi, ip = flat - iw * pl.n_phi;
+            const double J = exact_cost_co(pl.wspd_grid[iw], pl.cos_phi[ip], pl.sin_phi[ip], slab64[flat], px.qa, px.qb, px.s, pl.dsig_co);
+            if (J < bj || (J == bj && flat < bi)) {
+                bj = J;
+                bi = flat;
+            }
+        };
+        // walk the recorded cells.  stage 0: collect the band members; 1: count the members that pass the second filter;
+        // 2: evaluate them in FP64 (stages 1 and 2 only when a lane holds more than two candidates)
         auto walk = [&](int stage) {
             unsigned lanes = rc.cont;
 #pragma unroll 1
@@ -475,68 +486,86 @@ __global__ void __launch_bounds__(256, 3) k_refine_easy(xs_plan pl, Workspace ws
                     }
                     if (sub == 0 && stage == 0) ++n_cells;
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
+                    for (int h = 0; h < 2; ++h) {
                         const int iw = c * kChunkRows + sub + 8 * h;
-                    if (iw >= pl.n_wspd) continue;
-                    const float2 rt = pl.rowtab[iw];
-                    const float2 *rowp = reinterpret_cast<const float2 *>(slab32 + (size_t)iw * pl.nph_pad) + L;
+                        if (iw >= pl.n_wspd) continue;
+                        const float2 rt = pl.rowtab[iw];
+                        const float2 *rowp = reinterpret_cast<const float2 *>(slab32 + (size_t)iw * pl.nph_pad) + L;
 #pragma unroll
-                    for (int j = 0; j < KP; ++j) {
-                        const float2 v = rowp[32 * j];
+                        for (int j = 0; j < KP; ++j) {
+                            const float2 v = rowp[32 * j];
 #pragma unroll
-                        for (int o = 0; o < 2; ++o) {  // exactly the scan's operations
-                            const int ip = 2 * (L + 32 * j) + o;
-                            const float lc = __fadd_rn(o ? v.y : v.x, -rc.cs);
-                            const float mm = __fmaf_rn(lc, lc, rt.y);
-                            const float aa = __fmaf_rn(rc.nq, lc, mm);
-                            if (ip >= pl.n_phi || !(__fmaf_rn(rt.x, gq[2 * j + o], aa) <= rc.thr)) continue;
-                            const int flat = iw * pl.n_phi + ip;
-                            if (two_stage) {
-                                const float jf = __fmaf_rn(rt.x, gq[2 * j + o], __fmaf_rn(kfull, lc, mm));
-                                if (stage == 0) jmin = fminf(jmin, jf);
-                                if (stage > 0 && !(jf <= thr2)) continue;
-                            }
-                            if (stage < 2) {
-                                ++n_loc;
-                                one_loc = flat;
-                            } else {  // J is never NaN here: finite inputs, NaN-free slab
-                                const double J = exact_cost_co(pl.wspd_grid[iw], pl.cos_phi[ip], pl.sin_phi[ip], slab64[flat], px.qa,
-                                                               px.qb, px.s, pl.dsig_co);
-                                if (J < bj || (J == bj && flat < bi)) {
-                                    bj = J;
-                                    bi = flat;
+                            for (int o = 0; o < 2; ++o) {  // exactly the scan's operations
+                                const int ip = 2 * (L + 32 * j) + o;
+                                const float lc = __fadd_rn(o ? v.y : v.x, -rc.cs);
+                                const float mm = __fmaf_rn(lc, lc, rt.y);
+                                const float J = __fmaf_rn(rt.x, gq[2 * j + o], __fmaf_rn(rc.nq, lc, mm));
+                                if (ip >= pl.n_phi || !(J <= rc.thr)) continue;
+                                const int flat = iw * pl.n_phi + ip;
+                                const float jf = two_stage ? __fmaf_rn(rt.x, gq[2 * j + o], __fmaf_rn(kfull, lc, mm)) : J;
+                                if (stage == 0) {
+                                    if (jf < b1) {
+                                        b3 = b2;
+                                        b2 = b1;
+                                        f2 = f1;
+                                        b1 = jf;
+                                        f1 = flat;
+                                    } else if (jf < b2) {
+                                        b3 = b2;
+                                        b2 = jf;
+                                        f2 = flat;
+                                    } else
+                                        b3 = fminf(b3, jf);
+                                } else if (jf <= thr2) {
+                                    if (stage == 1) {
+                                        ++n_loc;
+                                        one_loc = flat;
+                                    } else
+                                        fp64_feed(flat);
                                 }
                             }
                         }
-                    }
                     }
                     ++c;
                 }
             }
         };
-        auto group_count = [&](int &n_in, int &result) {
-            n_in = n_loc;
-            result = one_loc;
+        auto group_sum = [&](int v) {
 #pragma unroll
-            for (int o = 4; o > 0; o >>= 1) {
-                n_in += __shfl_xor_sync(gmask, n_in, o);
-                result = max(result, __shfl_xor_sync(gmask, result, o));  // the member itself when there is exactly one
-            }
+            for (int o = 4; o > 0; o >>= 1) v += __shfl_xor_sync(gmask, v, o);
+            return v;
         };
-        int n_in, result;
+        auto group_max = [&](int v) {
+#pragma unroll
+            for (int o = 4; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(gmask, v, o));
+            return v;
+        };
         walk(0);
-        group_count(n_in, result);
-        if (n_in > 1 && two_stage) {
+        if (two_stage) {
+            float jmin = b1;
 #pragma unroll
             for (int o = 4; o > 0; o >>= 1) jmin = fminf(jmin, __shfl_xor_sync(gmask, jmin, o));
             thr2 = jmin + 2.f * rc.efp;
-            n_loc = 0;
-            one_loc = -1;
-            walk(1);
-            group_count(n_in, result);
         }
-        if (n_in > 1) {  // FP64 with the reference's operation order over the remaining members, first minimum wins
-            walk(2);
+        else
+            thr2 = rc.thr;  // exact-k records: the members are the candidates
+        const bool in1 = f1 >= 0 && b1 <= thr2, in2 = f2 >= 0 && b2 <= thr2;
+        const bool overflow = group_max((b3 < CUDART_INF_F && b3 <= thr2) ? 1 : 0) != 0;  // a lane with more than two candidates
+        int n_in, result;
+        if (!overflow) {
+            n_in = group_sum((in1 ? 1 : 0) + (in2 ? 1 : 0));
+            result = group_max(in1 ? f1 : -1);  // the candidate itself when there is exactly one
+            if (n_in > 1) {
+                if (in1) fp64_feed(f1);
+                if (in2) fp64_feed(f2);
+            }
+        } else {
+            walk(1);
+            n_in = group_sum(n_loc);
+            result = group_max(one_loc);
+            if (n_in > 1) walk(2);
+        }
+        if (n_in > 1) {  // FP64 with the reference's operation order over the candidates, first minimum wins
 #pragma unroll
             for (int o = 4; o > 0; o >>= 1) {
                 const double oj = __shfl_xor_sync(gmask, bj, o);

@@ -11,11 +11,12 @@ namespace xs {
 size_t sort_temp_bytes(int64_t n) {
     size_t bytes = 0;
     cub::DoubleBuffer<unsigned> k(nullptr, nullptr), v(nullptr, nullptr);
+    if (n <= 0) return 0;
     if (cub::DeviceRadixSort::SortPairs(nullptr, bytes, k, v, n, 0, 32, (cudaStream_t)0) != cudaSuccess) {
         cudaGetLastError();
         return 0;
     }
-    return bytes;
+    return bytes + 256;
 }
 
 // sorts (keys[0], vals[0]) using (keys[1], vals[1]) as the alternate buffers; *which = index of the buffers holding the result

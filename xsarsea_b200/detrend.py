@@ -37,26 +37,29 @@ def sigma0_detrend(sigma0, inc_angle, wind_speed_gmf=np.array([10.0]), wind_dir_
     if resident:
         # device-resident extension: CUDA tensors in ([..., line, sample] sigma0, [line, sample] incidence), CUDA tensor out
         inc_t = inc_angle if type(inc_angle).__module__.split(".")[0] == "torch" else torch.as_tensor(np.asarray(inc_angle))
-        inc_line = inc_t.reshape(-1, inc_t.shape[-1])[0].detach().cpu().numpy().astype(np.float64)
+        t_inc = inc_t.reshape(-1, inc_t.shape[-1])[0].detach().cuda().to(torch.float64).contiguous()   # stays on the device: no sync
+        inc_line = None
     else:
         inc_line = np.asarray(inc_angle.isel(line=0).data, dtype=np.float64).reshape(-1)  # needs a labelled array, like the reference
+        t_inc = dev.to_device(inc_line)
     wspd = float(np.asarray(wind_speed_gmf).reshape(-1)[0])
     phi = float(np.asarray(wind_dir_gmf).reshape(-1)[0])
 
-    t_inc = dev.to_device(inc_line)
     if getattr(model, "_device_id", None) is not None:
         t_w = torch.full_like(t_inc, wspd)
         t_p = torch.full_like(t_inc, phi) if model.phi_range is not None else None
         profile = dev.gmf_eval(model._device_id, t_inc, t_w, t_p)
     else:
         # LUT-backed or host-defined model: evaluate the profile through the model's own call
+        if inc_line is None:
+            inc_line = t_inc.cpu().numpy()
         if model.phi_range is not None:
             vals = model(inc_line, np.array([wspd]), np.array([phi]))
         else:
             vals = model(inc_line, np.array([wspd]))
         profile = dev.to_device(np.asarray(vals, dtype=np.float64).reshape(-1))
 
-    w = inc_line.size
+    w = int(t_inc.numel())
     if resident:
         if sigma0.shape[-1] != w:
             raise ValueError(f"sigma0 sample axis ({sigma0.shape[-1]}) does not match inc_angle ({w})")
