@@ -439,6 +439,7 @@ def run_aux(args, plan, model, peak_tflops, hbm_gbs, hbm_src):
         res[name] = dict(value=Hh * args.samples / (best * 1e-3), unit="px/s", ms=best, co_pixels=n_co,
                          co_px_per_s=n_co / (best * 1e-3), refined_cells_per_px=st["fp64_chunks"] / n_co,
                          fp64_pixels_frac=st["fp64_pixels"] / n_co, exhaustive_pixels=st["exhaustive_pixels"],
+                         many_lane_pixels_frac=st["many_lane_pixels"] / n_co, shared_mode_frac=st["shared_mode_positions"] / n_co,
                          scan_ms=sm, refine_ms=rm)
         del inc, s_co, s_cr, anc
     res["hostile_over_friendly_px_rate"] = res["hostile"]["value"] / res["friendly"]["value"]

@@ -177,7 +177,7 @@ typedef struct xs_invert_args {
     /* per-call bookkeeping (ABI 2; all optional): nothing mutable lives on the plan, so one plan may serve any number
      * of concurrent xs_invert calls (different host threads and streams), each with its own workspace */
     uint64_t *counters_dev;   /* device, XS_N_COUNTERS words: the call's counters, copied on the stream at the end */
-    xs_timer *scan_timer;     /* recorded around the co-pol scan (k_scan_co + k_refine_co) of this call */
+    xs_timer *scan_timer;     /* recorded around the co-pol scan (k_scan_co + k_refine_easy) of this call */
     /* F2 epilogue (XS_FLAG_OUT_SPEED_DIR): planes instead of complex128 */
     const void *ground_heading; /* device, n_px of `dtype`, degrees; NULL = directions stay in the antenna convention */
     double ground_heading_scalar; /* used when ground_heading is NULL and XS_FLAG_DIR_METEO is set */
@@ -198,7 +198,7 @@ int xs_invert(const xs_plan *plan, const xs_invert_args *args, void *stream);
  * [2] co-pol pixels settled by the FP32 scan (+ refinement), [3] (lane, chunk) cells re-examined by the refinement,
  * [4..7], [9], [10] clock64 sums per phase when an instrumented scan variant is selected (development aid), else 0,
  * [8] tile hand-out cursor, [11] pixels the refinement settled in FP64 (more than one candidate inside the band),
- * [12] pixels left to the second refinement pass, [13] record positions scanned in shared-sigma0 mode. */
+ * [12] pixels with more than two contending lanes, [13] record positions scanned in shared-sigma0 mode. */
 
 /* ---- detrend -------------------------------------------------------------------------------- */
 

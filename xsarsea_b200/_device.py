@@ -180,7 +180,7 @@ class ScanTimer:
         nat.check(nat.load().xs_timer_create(ctypes.byref(self._h)), "xs_timer_create")
 
     def elapsed_ms(self):
-        """(k_scan_co, k_refine_co) device times in ms; waits for the kernels to finish."""
+        """(k_scan_co, k_refine_easy) device times in ms; waits for the kernels to finish."""
         ms = (ctypes.c_float * 2)()
         nat.check(nat.load().xs_timer_elapsed_ms(self._h, ms), "xs_timer_elapsed_ms")
         return float(ms[0]), float(ms[1])
@@ -370,7 +370,7 @@ class InversionPlan:
         return out_co, out_cr, idx_co, idx_cr
 
     def last_scan_ms(self):
-        """Device times (k_scan_co, k_refine_co) in ms of this thread's last `invert(..., timed=True)`."""
+        """Device times (k_scan_co, k_refine_easy) in ms of this thread's last `invert(..., timed=True)`."""
         timer = getattr(self._tls, "timer", None)
         if timer is None:
             raise nat.NativeError("no timed invert() call on this thread")
@@ -385,5 +385,5 @@ class InversionPlan:
 
     def last_stats(self):
         c = self.debug_counters()
-        return dict(scan_pixels=c[2], fp64_chunks=c[3], exhaustive_pixels=c[1], tiles=c[0], fp64_pixels=c[11], hard_pixels=c[12],
+        return dict(scan_pixels=c[2], fp64_chunks=c[3], exhaustive_pixels=c[1], tiles=c[0], fp64_pixels=c[11], many_lane_pixels=c[12],
                     shared_mode_positions=c[13])

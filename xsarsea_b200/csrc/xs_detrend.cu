@@ -92,6 +92,45 @@ __global__ void __launch_bounds__(256) k_detrend_vec(const V *__restrict__ s0, c
     }
 }
 
+// Column-stationary variant: a thread owns VEC adjacent samples (one 16-byte word of a line), keeps their ratio and
+// reciprocal in registers and walks down the lines of its CTA's row block with UNROLL independent loads in flight.  The
+// [W] vectors are read once per thread instead of once per pixel (16 B of L1 traffic per pixel before, which is what
+// bounded the float32 case at half the HBM rate).
+template <typename T, typename V, int VEC, int UNROLL>
+__global__ void __launch_bounds__(256) k_detrend_cols(const V *__restrict__ s0, const double *__restrict__ ratio,
+                                                      const double *__restrict__ rinv, int64_t n_lines, int64_t wv,
+                                                      int64_t lines_per_cta, V *__restrict__ out) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= wv) return;
+    double r[VEC], ri[VEC];
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+        r[k] = ratio[c * VEC + k];
+        ri[k] = rinv[c * VEC + k];
+    }
+    const int64_t l0 = (int64_t)blockIdx.y * lines_per_cta, l1 = min(l0 + lines_per_cta, n_lines);
+    for (int64_t l = l0; l < l1; l += UNROLL) {
+        V v[UNROLL];
+#pragma unroll
+        for (int q = 0; q < UNROLL; ++q)
+            if (l + q < l1) v[q] = __ldcs(&s0[(l + q) * wv + c]);  // streaming: read once
+#pragma unroll
+        for (int q = 0; q < UNROLL; ++q)
+            if (l + q < l1) {
+                T *e = reinterpret_cast<T *>(&v[q]);
+#pragma unroll
+                for (int k = 0; k < VEC; ++k) {
+                    const double x = (double)e[k];
+                    const double q0 = x * ri[k];
+                    const double res = fma(-q0, r[k], x);
+                    // non-finite operands (NaN/inf sigma0, zero or NaN ratio) take the plain division
+                    e[k] = (T)((isfinite(q0) && isfinite(ri[k])) ? fma(res, ri[k], q0) : x / r[k]);
+                }
+                __stcs(&out[(l + q) * wv + c], v[q]);
+            }
+    }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) k_detrend_scalar(const T *__restrict__ s0, const double *__restrict__ ratio, int64_t h,
                                                         int64_t w, T *__restrict__ out) {
@@ -124,15 +163,35 @@ extern "C" int xs_detrend(const void *sigma0, const double *gmf_line, int64_t n_
         const int64_t cap = (int64_t)kNumSMs * 32;
         return (int)(g < 1 ? 1 : (g > cap ? cap : g));
     };
+    // column-stationary launch shape: enough CTAs for ~16 per SM, at least 64 lines per CTA
+    auto rows_shape = [&](int64_t wv, dim3 *grid, int64_t *lines_per_cta) {
+        const int64_t gx = ceil_div(wv, 256);
+        int64_t gy = ceil_div((int64_t)kNumSMs * 16, gx);
+        if (gy > ceil_div(n_lines, 64)) gy = ceil_div(n_lines, 64);
+        if (gy < 1) gy = 1;
+        if (gy > 65535) gy = 65535;
+        *lines_per_cta = ceil_div(n_lines, gy);
+        *grid = dim3((unsigned)gx, (unsigned)ceil_div(n_lines, *lines_per_cta));
+    };
+    dim3 grid2;
+    int64_t lpc = 0;
     if (dtype == XS_F64) {
-        if (aligned && n_samples % 2 == 0)
+        if (aligned && n_samples % 2 == 0 && n_lines >= 256) {
+            rows_shape(n_samples / 2, &grid2, &lpc);
+            XS_LAUNCH((k_detrend_cols<double, double2, 2, 4>), grid2, 256, 0, stream, (const double2 *)sigma0, ratio, rinv, n_lines,
+                      n_samples / 2, lpc, (double2 *)out);
+        } else if (aligned && n_samples % 2 == 0)
             XS_LAUNCH((k_detrend_vec<double, double2, 2, 4>), grid_for(n / 2 / 4), 256, 0, stream, (const double2 *)sigma0,
                       ratio, rinv, n / 2, n_samples / 2, (double2 *)out);
         else
             XS_LAUNCH(k_detrend_scalar<double>, grid_for(n), 256, 0, stream, (const double *)sigma0, ratio, n_lines, n_samples,
                       (double *)out);
     } else {
-        if (aligned && n_samples % 4 == 0)
+        if (aligned && n_samples % 4 == 0 && n_lines >= 256) {
+            rows_shape(n_samples / 4, &grid2, &lpc);
+            XS_LAUNCH((k_detrend_cols<float, float4, 4, 4>), grid2, 256, 0, stream, (const float4 *)sigma0, ratio, rinv, n_lines,
+                      n_samples / 4, lpc, (float4 *)out);
+        } else if (aligned && n_samples % 4 == 0)
             XS_LAUNCH((k_detrend_vec<float, float4, 4, 4>), grid_for(n / 4 / 4), 256, 0, stream, (const float4 *)sigma0,
                       ratio, rinv, n / 4, n_samples / 4, (float4 *)out);
         else

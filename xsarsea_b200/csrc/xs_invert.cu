@@ -4,7 +4,7 @@
 // workspace, counters, timer -- belongs to the call, so one plan serves concurrent calls):
 //   k_bin_count / k_bin_offsets / k_bin_scatter   counting sort of the co-pol pixels by incidence bin; every bin's segment
 //                  of the list is padded to whole scan tiles
-//   k_list_prepare / k_scan_co / k_refine_co      the co-pol argmin: FP32 FFMA2 scan + exact refinement (xs_scan.cu)
+//   k_list_prepare / k_scan_co / k_refine_easy    the co-pol argmin: FP32 FFMA2 scan + exact refinement (xs_scan.cu)
 //   k_exact        exhaustive FP64 scan (warp per pixel) of the pixels the fast path cannot handle (non-finite
 //                  inputs, magnitudes outside the error bound's range) and of XS_MODE_FP64
 //   k_cross        cross-pol / dual-pol pass (windspeed.py:252-279), merge (:426-428), NaN classes, and the output
@@ -44,7 +44,6 @@ size_t ws_layout(int n_inc, int64_t n_px, unsigned flags, size_t sort_bytes, cha
     char *fb = take(sizeof(unsigned) * (size_t)n_sort);
     char *pr = take(sizeof(PixRec) * (size_t)n_list);
     char *rr = take(sizeof(RefRec) * (size_t)n_list);
-    char *hd = take(sizeof(unsigned) * (size_t)n_list);
     char *it = take((flags & XS_FLAG_OUT_SPEED_DIR) ? sizeof(int) * (size_t)n_px : 0);
     if (w) {
         w->counters = (u64 *)c;
@@ -61,7 +60,6 @@ size_t ws_layout(int n_inc, int64_t n_px, unsigned flags, size_t sort_bytes, cha
         w->fallback = (unsigned *)fb;
         w->pix = (PixRec *)pr;
         w->rec = (RefRec *)rr;
-        w->hard = (unsigned *)hd;
         w->idx_tmp = (int *)it;
         w->n_list = n_list;
     }

@@ -48,7 +48,7 @@ struct xs_plan {
 };
 
 struct xs_timer {
-    cudaEvent_t ev[3];  // before k_scan_co, after k_scan_co, after k_refine_co
+    cudaEvent_t ev[3];  // before k_scan_co, after k_scan_co, after k_refine_easy
     int recorded;
 };
 
@@ -331,7 +331,7 @@ struct __align__(16) RefRec {  // 32 B
                                // re-creates the scanned FP32 costs
     float efp;                 // bound of the full centred form's FP32 error (second filter of shared-sigma0 records)
     unsigned cont;             // lanes holding band members (0: the scan could not bound its error -> exhaustive FP64)
-    unsigned mask[3];          // chunk masks (bit = chunk >> mask_sh) of the first three cont lanes
+    unsigned mask[3];          // chunk masks (bit = chunk >> mask_sh) of the first two cont lanes and the union of the others'
 };
 static_assert(sizeof(PixRec) == 32 && sizeof(RefRec) == 32, "record layout");
 
@@ -349,7 +349,6 @@ struct Workspace {
     unsigned *fallback;    // [n_px] pixels for the exhaustive kernel
     PixRec *pix;           // [n_list]
     RefRec *rec;           // [n_list]
-    unsigned *hard;        // [n_list] list positions k_refine_easy leaves to k_refine_co (counters[12])
     int *idx_tmp;          // [n_px] co-pol argmin when the caller gave no idx_co and the outputs are speed/direction planes
     int64_t n_list;        // n_px + kTilePad * n_inc rounded up to a sort run
 };

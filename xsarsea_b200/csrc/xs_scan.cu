@@ -27,7 +27,6 @@
 //   k_refine_easy   eight lanes per pixel: re-creates the FP32 costs (bit-identical operations) of the recorded (lane,
 //                   chunk) cells; a single band member settles the pixel, several are evaluated in FP64 with the
 //                   reference's operation order, lexicographic (J, index) minimum = numpy's first minimum
-//   k_refine_co     a warp per pixel for the rare records with more than three contending lanes
 #include <stdio.h>
 #include <stdlib.h>
 
@@ -324,7 +323,7 @@ __global__ void __launch_bounds__(NW * 32, MB) k_scan_co(xs_plan pl, Workspace w
         // ---- band of every pixel -> RefRec ---------------------------------------------------------------------------
         // m32 = warp-shuffle min of the FP32 costs; E bounds |J''_fp32 - J''_exact| for every candidate that can still
         // win (derivation: DESIGN.md 4.1, checked on the CPU by tests/test_error_bound.py), so the reference's FP64 argmin
-        // lies in S = {c : J''_fp32(c) <= m32 + 2E}; k_refine_co collects S from the cells recorded here.
+        // lies in S = {c : J''_fp32(c) <= m32 + 2E}; k_refine_easy collects S from the cells recorded here.
         const float lmax = pl.slab_absmax[bin];
         const float W = (float)pl.w_absmax * 1.0000002f;
 #pragma unroll
@@ -354,13 +353,13 @@ __global__ void __launch_bounds__(NW * 32, MB) k_scan_co(xs_plan pl, Workspace w
             // bound was derived for
             const bool sane = (E < 0.5f * kBandMargin) && (m32 < CUDART_INF_F);
             const unsigned cont = __ballot_sync(0xffffffffu, sane && best[p] <= thr);  // lanes holding band members
-            // the record carries the chunk masks of the first three contending lanes (one or two in 99 % of the pixels);
-            // with more, k_refine_co looks at the lanes whole
+            // the record carries the chunk masks of the first two contending lanes (one or two in 99 % of the pixels) and
+            // the union of the masks of all further ones (a superset for each of them)
             const bool mine_c = (cont >> lane) & 1u;
             const int rank = __popc(cont & ((1u << lane) - 1u));
             const unsigned m0 = __reduce_or_sync(0xffffffffu, (mine_c && rank == 0) ? cmask[p] : 0u);
             const unsigned m1 = __reduce_or_sync(0xffffffffu, (mine_c && rank == 1) ? cmask[p] : 0u);
-            const unsigned m2 = __reduce_or_sync(0xffffffffu, (mine_c && rank == 2) ? cmask[p] : 0u);
+            const unsigned m2 = __reduce_or_sync(0xffffffffu, (mine_c && rank >= 2) ? cmask[p] : 0u);
             if (lane == 0) {
                 RefRec rr;
                 rr.thr = thr;
@@ -379,31 +378,13 @@ __global__ void __launch_bounds__(NW * 32, MB) k_scan_co(xs_plan pl, Workspace w
 }
 
 // ---- exact refinement ---------------------------------------------------------------------------------------------------
-// FP32 cost of candidate k of cell (lane L, rows row0...) of a pixel, exactly as the scan computed it; true if it is inside
-// the pixel's band.  flat = w * n_phi + phi index of the candidate.
-template <int KP>
-__device__ __forceinline__ bool band_member(const xs_plan &pl, const PixRec &px, const RefRec &rc, int L, int row0, int k,
-                                            int n_cand, int &flat) {
-    const int iw = row0 + k / (2 * KP);
-    const int slot = k % (2 * KP);
-    const int ip = 2 * (L + 32 * (slot >> 1)) + (slot & 1);
-    flat = iw * pl.n_phi + ip;
-    if (k >= n_cand || iw >= pl.n_wspd || ip >= pl.n_phi) return false;
-    const float2 rt = pl.rowtab[iw];
-    const float *slab32 = pl.scan + (size_t)px.bin * pl.n_wspd_pad * pl.nph_pad;
-    const float lc = __fadd_rn(slab32[(size_t)iw * pl.nph_pad + ip], -rc.cs);
-    const float mm = __fmaf_rn(lc, lc, rt.y);
-    const float aa = __fmaf_rn(rc.nq, lc, mm);
-    return __fmaf_rn(rt.x, g32(px.qa, px.qb, pl.cos_phi[ip], pl.sin_phi[ip]), aa) <= rc.thr;
-}
-
-// Pass 1: eight lanes per list position (four positions per warp at a time, so four times as many pixels are in flight
+// Eight lanes per record position (four positions per warp at a time, so four times as many pixels are in flight
 // as with a warp per pixel -- this pass is bound by the latency of its dependent loads and by instruction issue, not by
 // arithmetic).  Settles padding, NaN slabs (answer = first NaN), pixels for the exhaustive kernel, and every pixel whose
 // band touches only "cont" cells (one 16-row chunk of one lane each, at most 8): lane `sub` of the group owns rows sub and
 // sub + 8 of a cell and all 2 KP phi slots, so g(phi) is evaluated once per slot; a single band member settles the pixel,
 // several are evaluated in FP64 with the reference's operation order and reduced to the lexicographic (J, flat index)
-// minimum = numpy's first minimum.  Pixels with "wide" lanes (several chunks of one lane in the band) go to pass 2.
+// minimum = numpy's first minimum.
 template <int KP>
 __global__ void __launch_bounds__(256, 3) k_refine_easy(xs_plan pl, Workspace ws, OutSpec out, int tile_px) {
     const int lane = threadIdx.x & 31, sub = lane & 7, grp = lane >> 3;
@@ -415,7 +396,7 @@ __global__ void __launch_bounds__(256, 3) k_refine_easy(xs_plan pl, Workspace ws
     const int n_chunks = (pl.n_wspd_pad + kChunkRows - 1) / kChunkRows;
     int mask_sh = 0;
     while ((n_chunks + (1 << mask_sh) - 1) >> mask_sh > 32) ++mask_sh;
-    unsigned n_settled = 0, n_cells = 0, n_fp64 = 0;
+    unsigned n_settled = 0, n_cells = 0, n_fp64 = 0, n_many = 0;
     for (int64_t e0 = warp * 4; e0 < n_pos; e0 += n_warps * 4) {
         const int64_t e = e0 + grp;
         if (e >= n_pos) continue;
@@ -431,10 +412,7 @@ __global__ void __launch_bounds__(256, 3) k_refine_easy(xs_plan pl, Workspace ws
             }
             continue;
         }
-        if (__popc(rc.cont) > 3) {  // more contending lanes than the record has chunk masks for
-            if (sub == 0) ws.hard[atomicAdd(&ws.counters[12], 1ull)] = (unsigned)e;
-            continue;
-        }
+        if (sub == 0 && __popc(rc.cont) > 2) ++n_many;
         const float *slab32 = pl.scan + (size_t)px.bin * pl.n_wspd_pad * pl.nph_pad;
         const double *slab64 = pl.co_lut + (size_t)px.bin * pl.n_wspd * pl.n_phi;
         // Shared-sigma0 records (nq == 0): the scanned cost left k lambda out and the band is wider by 2 |sigma| Lam.  The
@@ -589,75 +567,12 @@ __global__ void __launch_bounds__(256, 3) k_refine_easy(xs_plan pl, Workspace ws
     n_settled = __reduce_add_sync(0xffffffffu, n_settled);
     n_cells = __reduce_add_sync(0xffffffffu, n_cells);
     n_fp64 = __reduce_add_sync(0xffffffffu, n_fp64);
+    n_many = __reduce_add_sync(0xffffffffu, n_many);
     if (lane == 0) {
+        if (n_many) atomicAdd(&ws.counters[12], (u64)n_many);
         if (n_settled) atomicAdd(&ws.counters[2], (u64)n_settled);
         if (n_cells) atomicAdd(&ws.counters[3], (u64)n_cells);
         if (n_fp64) atomicAdd(&ws.counters[11], (u64)n_fp64);
-    }
-}
-
-// Pass 2: a warp per record with more than three contending lanes (rare: flat cost surfaces, equal-cost plateaus).  The
-// contending lanes are looked at whole: every candidate of the lane is re-created in FP32; a single band member settles the
-// pixel, several are evaluated in FP64 with the reference's operation order and reduced by a warp-shuffle lexicographic
-// (J, flat index) argmin = numpy's first minimum.
-template <int KP>
-__global__ void __launch_bounds__(256, 3) k_refine_co(xs_plan pl, Workspace ws, OutSpec out) {
-    const int lane = threadIdx.x & 31;
-    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    const int64_t n_hard = (int64_t)ws.counters[12];
-    const int n_chunks = (pl.n_wspd_pad + kChunkRows - 1) / kChunkRows;
-    u64 n_scanned = 0, n_cells = 0, n_fp64 = 0;
-    for (int64_t h = warp; h < n_hard; h += n_warps) {
-        const unsigned e = ws.hard[h];
-        const PixRec px = ws.pix[e];
-        const RefRec rc = ws.rec[e];
-        const double *slab64 = pl.co_lut + (size_t)px.bin * pl.n_wspd * pl.n_phi;
-        const int n_cand = pl.n_wspd * 2 * KP;
-        int n_loc = 0, one_loc = -1;
-        ArgMin am;
-        am.init();
-        auto sweep = [&](bool exact) {
-            unsigned lanes = rc.cont;
-            while (lanes) {
-                const int L = __ffs(lanes) - 1;
-                lanes &= lanes - 1;
-                for (int k0 = 0; k0 < n_cand; k0 += 32) {
-                    int flat;
-                    if (!band_member<KP>(pl, px, rc, L, 0, k0 + lane, n_cand, flat)) continue;
-                    if (!exact) {
-                        ++n_loc;
-                        one_loc = flat;
-                    } else {
-                        const int iw = flat / pl.n_phi, ip = flat - iw * pl.n_phi;
-                        am.feed(exact_cost_co(pl.wspd_grid[iw], pl.cos_phi[ip], pl.sin_phi[ip], slab64[flat], px.qa, px.qb, px.s,
-                                              pl.dsig_co), flat);
-                    }
-                }
-                if (!exact) n_cells += n_chunks;
-            }
-        };
-        sweep(false);
-        const int n_in = __reduce_add_sync(0xffffffffu, n_loc);
-        int result = __reduce_max_sync(0xffffffffu, one_loc);  // the member itself when n_in == 1
-        if (n_in > 1) {
-            sweep(true);
-            am.warp_reduce();
-            result = am.result();
-            ++n_fp64;
-        }
-        if (lane == 0) {
-            if (n_in >= 1)
-                write_co(pl, out, result, px.neg, px.px);
-            else  // cannot happen if the re-created costs equal the scan's; be safe
-                ws.fallback[atomicAdd(&ws.counters[1], 1ull)] = px.px;
-        }
-        ++n_scanned;
-    }
-    if (lane == 0) {
-        if (n_scanned) atomicAdd(&ws.counters[2], n_scanned);
-        if (n_cells) atomicAdd(&ws.counters[3], n_cells);
-        if (n_fp64) atomicAdd(&ws.counters[11], n_fp64);
     }
 }
 
@@ -719,7 +634,6 @@ static int launch_shape(const xs_plan *pl, const RasterArgs &ra, const Workspace
     XS_LAUNCH(kern, sms * per_sm, NW * 32, smem, st, *pl, ws, share_tau);
     if (timer) XS_CUDA(cudaEventRecord(timer->ev[1], st));
     XS_LAUNCH(k_refine_easy<KP>, sms * 6, 256, 0, st, *pl, ws, out, TP);
-    XS_LAUNCH(k_refine_co<KP>, sms * 6, 256, 0, st, *pl, ws, out);
     if (timer) {
         XS_CUDA(cudaEventRecord(timer->ev[2], st));
         timer->recorded = 1;

@@ -26,7 +26,8 @@ logger = logging.getLogger("xsarsea.windspeed")
 _PLAN_CACHE: "OrderedDict[tuple, dev.InversionPlan]" = OrderedDict()
 _PLAN_CACHE_MAX = 4
 _PLAN_LOCK = threading.RLock()
-BLOCK_PIXELS = 1 << 24  # pixels per streamed block (16 Mi px: 0.67 GB of f64 inputs, 0.5 GB of outputs)
+BLOCK_PIXELS = 1 << 26  # pixels per compute block of the host path (64 Mi px: 2.7 GB of f64 inputs, 2.1 GB of outputs, 5.6 GB of workspace)
+STAGE_PIXELS = 1 << 24  # pixels per pinned staging chunk (16 Mi px: 0.27 GB per complex128 raster)
 
 
 def _get_plan(model_co, model_cr, dsig_co, kwargs):
@@ -134,12 +135,31 @@ class _PinnedPool:
 _POOL = _PinnedPool()
 
 
+def _block_edges(n):
+    """Compute blocks of the host path: BLOCK_PIXELS each, with a short first and last one (STAGE_PIXELS) so that the
+    upload that cannot overlap anything (the first) and the download that cannot (the last) are small."""
+    if n <= BLOCK_PIXELS:
+        return [0, n]
+    short = min(STAGE_PIXELS, BLOCK_PIXELS)
+    edges = [0, short]
+    while n - edges[-1] > BLOCK_PIXELS + short:
+        edges.append(edges[-1] + BLOCK_PIXELS)
+    if n - edges[-1] > short:
+        edges.append(n - short)
+    edges.append(n)
+    return edges
+
+
 def _run_device(plan, inc, s_co, s_cr, dsig_cr, anc, *, sigma0_db, merge_dual, cr_abs, mode=nat.MODE_FAST,
                 need_co=False, speed_dir=False, ground_heading=None, out_f32=False):
-    """Host arrays in, host arrays out.  Row blocks are streamed: H2D on one side stream, xs_invert on the current
-    stream, D2H on another side stream, two device slots so block k+1 uploads while block k is scanned.  Host memory that
-    is not page-locked is staged through block-sized pinned buffers (inputs by this thread, results by a helper thread
-    that copies each finished block into the pageable output while the GPU works on the next ones)."""
+    """Host arrays in, host arrays out.
+
+    The raster is inverted in compute blocks of BLOCK_PIXELS (large, because the co-pol scan shares work between pixels of
+    equal incidence bin and sigma0: the more pixels a call sees, the more of it runs in the fast mode) held in two device
+    slots: while block b is scanned, block b + 1 is uploaded (H2D on a side stream) and block b - 1 downloaded (D2H on
+    another).  Host memory that is not page-locked is staged through STAGE_PIXELS-sized pinned buffers -- inputs by this
+    thread, results by a helper thread that copies every finished chunk into the ordinary (pageable) output arrays while
+    the GPU works on."""
     torch = nat.torch_cuda()
     shape = inc.shape
     rasters = (inc, s_co, s_cr, anc, ground_heading if isinstance(ground_heading, np.ndarray) else None)
@@ -158,18 +178,22 @@ def _run_device(plan, inc, s_co, s_cr, dsig_cr, anc, *, sigma0_db, merge_dual, c
     n = h_in[0].size
     want_co = plan.co_grids is not None and h_in[1] is not None
     pdt = np.float32 if out_f32 else np.float64
-    wind_shape, wind_dt = ((2, n), pdt) if speed_dir else ((n,), np.complex128)
-    out_co = np.empty(wind_shape, dtype=wind_dt) if (want_co or need_co) else None
-    out_cr = np.empty((n,), dtype=np.float64) if cr_abs else np.empty(wind_shape, dtype=wind_dt)
+    planes = 2 if speed_dir else 1
+    wind_dt = pdt if speed_dir else np.complex128
+    out_co = np.empty((planes, n), dtype=wind_dt) if (want_co or need_co) else None
+    out_cr = np.empty((1, n), dtype=np.float64) if cr_abs else np.empty((planes, n), dtype=wind_dt)
 
     def finish(o):
-        return None if o is None else o.reshape(((2,) if o.ndim == 2 else ()) + tuple(shape))
+        return None if o is None else o.reshape(((2,) if o.shape[0] == 2 else ()) + tuple(shape))
 
     if n == 0:
         return finish(out_co), finish(out_cr)
 
-    blk = min(n, BLOCK_PIXELS)
-    nslots = 1 if n <= blk else 2
+    edges = _block_edges(n)
+    nb = len(edges) - 1
+    blk = max(b - a for a, b in zip(edges, edges[1:]))
+    stg = min(blk, STAGE_PIXELS)
+    nslots = 1 if nb == 1 else 2
     t_of = {np.dtype(np.float32): torch.float32, np.dtype(np.float64): torch.float64,
             np.dtype(np.complex64): torch.complex64, np.dtype(np.complex128): torch.complex128}
     cur = torch.cuda.current_stream()
@@ -179,11 +203,9 @@ def _run_device(plan, inc, s_co, s_cr, dsig_cr, anc, *, sigma0_db, merge_dual, c
     s_in.wait_stream(cur)
     s_out.wait_stream(cur)
     d_in = [None if h is None else [torch.empty(blk, dtype=t_of[h.dtype], device="cuda") for _ in range(nslots)] for h in h_in]
-    d_oco = None if out_co is None else [torch.empty(wind_shape[:-1] + (blk,), dtype=t_of[np.dtype(wind_dt)], device="cuda")
-                                         for _ in range(nslots)]
-    d_ocr = [torch.empty(((blk,) if cr_abs else wind_shape[:-1] + (blk,)), dtype=t_of[out_cr.dtype], device="cuda")
-             for _ in range(nslots)]
-    # pinned staging: inputs that are not page-locked already, and both outputs
+    d_oco = None if out_co is None else [torch.empty(out_co.shape[0] * blk, dtype=t_of[out_co.dtype], device="cuda") for _ in range(nslots)]
+    d_ocr = [torch.empty(out_cr.shape[0] * blk, dtype=t_of[out_cr.dtype], device="cuda") for _ in range(nslots)]
+    # pinned staging rings (2 chunks each): inputs that are not page-locked already, and both outputs
     taken = []
 
     def pinned(nelem, np_dt):
@@ -191,99 +213,130 @@ def _run_device(plan, inc, s_co, s_cr, dsig_cr, anc, *, sigma0_db, merge_dual, c
         taken.append(buf)
         return buf.numpy().view(np_dt)
 
-    in_stage = [None if (h is None or torch.from_numpy(h).is_pinned()) else [pinned(blk, h.dtype) for _ in range(nslots)]
-                for h in h_in]
-    oco_stage = None if out_co is None else [pinned(out_co.size // n * blk, out_co.dtype).reshape(wind_shape[:-1] + (blk,))
-                                             for _ in range(nslots)]
-    ocr_stage = [pinned(out_cr.size // n * blk, out_cr.dtype).reshape(out_cr.shape[:-1] + (blk,)) for _ in range(nslots)]
-
-    def front(bufs, slot, m):
-        """Contiguous view of the first m pixels' worth of a slot buffer: [m] or -- planes -- [2][m]."""
-        if bufs is None:
-            return None
-        b = bufs[slot]
-        return b[:m] if b.ndim == 1 else b.reshape(-1)[:2 * m].reshape(2, m)
-
-    ev_h2d = [None] * nslots    # upload of the block that last used the slot's input staging
-    ev_scan = [None] * nslots   # scan of the block that last used the slot's device inputs
-    slot_free = [threading.Semaphore(1) for _ in range(nslots)]  # output staging of the slot has been drained
+    in_stage = [None if (h is None or torch.from_numpy(h).is_pinned()) else [pinned(stg, h.dtype) for _ in range(2)] for h in h_in]
+    oco_stage = None if out_co is None else [pinned(out_co.shape[0] * stg, out_co.dtype) for _ in range(2)]
+    ocr_stage = [pinned(out_cr.shape[0] * stg, out_cr.dtype) for _ in range(2)]
+    ev_stage_in = [None, None]            # H2D that last read the input staging chunk
+    stage_free = [threading.Semaphore(1), threading.Semaphore(1)]   # output staging chunk has been drained
+    ev_scan = [None] * nslots             # scan of the block that last used the device slot
+    ev_d2h = [None] * nslots              # last download out of the device slot's outputs
     jobs: "queue.Queue" = queue.Queue()
     errors = []
+    counters = dict(in_chunk=0, out_chunk=0)
 
     def drain():
-        # the outputs are fresh pageable memory: the copy out of the staging block also takes the first-touch page faults
-        # (~6 GB/s per thread), so every finished block is split between a few helper threads (numpy releases the GIL)
-        def part(slot, lo, m, k, parts):
+        # the outputs are fresh pageable memory: the copy out of the staging chunk also takes the first-touch page faults
+        # (~6 GB/s per thread), so every finished chunk is split between a few helper threads (numpy releases the GIL)
+        def part(r, lo, m, k, parts):
             a, b = m * k // parts, m * (k + 1) // parts
             if out_co is not None:
-                out_co[..., lo + a:lo + b] = front(oco_stage, slot, m)[..., a:b]
-            out_cr[..., lo + a:lo + b] = front(ocr_stage, slot, m)[..., a:b]
+                out_co[:, lo + a:lo + b] = oco_stage[r][:out_co.shape[0] * m].reshape(out_co.shape[0], m)[:, a:b]
+            out_cr[:, lo + a:lo + b] = ocr_stage[r][:out_cr.shape[0] * m].reshape(out_cr.shape[0], m)[:, a:b]
 
         while True:
             job = jobs.get()
             if job is None:
                 return
-            ev, slot, lo, hi = job
+            ev, r, lo, m = job
             try:
                 ev.synchronize()
-                m = hi - lo
                 parts = 4 if m >= (1 << 20) else 1
-                helpers = [threading.Thread(target=part, args=(slot, lo, m, k, parts)) for k in range(1, parts)]
+                helpers = [threading.Thread(target=part, args=(r, lo, m, k, parts)) for k in range(1, parts)]
                 for t in helpers:
                     t.start()
-                part(slot, lo, m, 0, parts)
+                part(r, lo, m, 0, parts)
                 for t in helpers:
                     t.join()
             except Exception as e:  # pragma: no cover
                 errors.append(e)
             finally:
-                slot_free[slot].release()
+                stage_free[r].release()
+
+    def upload(b):
+        lo, hi = edges[b], edges[b + 1]
+        slot = b % nslots
+        with torch.cuda.stream(s_in):
+            if ev_scan[slot] is not None:
+                s_in.wait_event(ev_scan[slot])   # the slot's inputs are read by the scan of block b - 2 until then
+            for d, h, st in zip(d_in, h_in, in_stage):
+                if d is None:
+                    continue
+                if st is None:   # page-locked already: one direct copy
+                    d[slot][:hi - lo].copy_(torch.from_numpy(h[lo:hi]), non_blocking=True)
+                    continue
+                for a in range(lo, hi, stg):
+                    m = min(stg, hi - a)
+                    r = counters["in_chunk"] % 2
+                    counters["in_chunk"] += 1
+                    if ev_stage_in[r] is not None:
+                        ev_stage_in[r].synchronize()
+                    np.copyto(st[r][:m], h[a:a + m])
+                    d[slot][a - lo:a - lo + m].copy_(torch.from_numpy(st[r][:m]), non_blocking=True)
+                    ev_stage_in[r] = torch.cuda.Event()
+                    ev_stage_in[r].record(s_in)
+            ev = torch.cuda.Event()
+            ev.record(s_in)
+        return ev
+
+    def outs(b):
+        """Contiguous views [planes * m] of the slot's output buffers for block b (planes are [planes][m])."""
+        m = edges[b + 1] - edges[b]
+        slot = b % nslots
+        oc = None if d_oco is None else d_oco[slot][:out_co.shape[0] * m]
+        return oc, d_ocr[slot][:out_cr.shape[0] * m]
+
+    def invert(b, ev_in):
+        m = edges[b + 1] - edges[b]
+        slot = b % nslots
+        cur.wait_event(ev_in)
+        if ev_d2h[slot] is not None:
+            cur.wait_event(ev_d2h[slot])         # results of block b - 2 have left the slot
+        sl = lambda d: None if d is None else d[slot][:m]
+        oc, ox = outs(b)
+        shp = (lambda t, k: t if k == 1 else t.reshape(k, m))
+        plan.invert(sl(d_in[0]), sl(d_in[1]), sl(d_in[2]), sl(d_in[3]) if d_in[3] is not None else dsig_scalar,
+                    sl(d_in[4]), sigma0_db=sigma0_db, merge_dual=merge_dual, cr_abs=cr_abs, mode=mode,
+                    out_co=None if oc is None else shp(oc, out_co.shape[0]), out_cr=shp(ox, out_cr.shape[0]),
+                    speed_dir=speed_dir, out_f32=out_f32,
+                    ground_heading=sl(d_in[5]) if d_in[5] is not None else gh_scalar)
+        ev_scan[slot] = torch.cuda.Event()
+        ev_scan[slot].record(cur)
+
+    def download(b):
+        lo, hi = edges[b], edges[b + 1]
+        mb = hi - lo
+        slot = b % nslots
+        oc, ox = outs(b)
+        for a in range(lo, hi, stg):
+            m = min(stg, hi - a)
+            r = counters["out_chunk"] % 2
+            counters["out_chunk"] += 1
+            stage_free[r].acquire()              # the chunk that last used the staging buffers is on the host
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(ev_scan[slot])
+                for dev_o, stage, host_o in ((oc, oco_stage, out_co), (ox, ocr_stage, out_cr)):
+                    if dev_o is None:
+                        continue
+                    k = host_o.shape[0]
+                    src = dev_o.reshape(k, mb)[:, a - lo:a - lo + m]
+                    dst = torch.from_numpy(stage[r][:k * m]).reshape(k, m)
+                    dst.copy_(src, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(s_out)
+            jobs.put((ev, r, a, m))
+        ev_d2h[slot] = ev
 
     worker = threading.Thread(target=drain, name="xs-d2h", daemon=True)
     worker.start()
     try:
-        for k, lo in enumerate(range(0, n, blk)):
-            hi = min(lo + blk, n)
-            m = hi - lo
-            slot = k % nslots
-            if ev_h2d[slot] is not None:
-                ev_h2d[slot].synchronize()  # the slot's input staging is read by the previous upload until then
-            srcs = []
-            for h, st in zip(h_in, in_stage):
-                if h is None:
-                    srcs.append(None)
-                elif st is None:
-                    srcs.append(torch.from_numpy(h[lo:hi]))
-                else:
-                    np.copyto(st[slot][:m], h[lo:hi])
-                    srcs.append(torch.from_numpy(st[slot][:m]))
-            with torch.cuda.stream(s_in):
-                if ev_scan[slot] is not None:
-                    s_in.wait_event(ev_scan[slot])
-                for d, src in zip(d_in, srcs):
-                    if d is not None:
-                        d[slot][:m].copy_(src, non_blocking=True)
-                ev_in = torch.cuda.Event()
-                ev_in.record(s_in)
-            ev_h2d[slot] = ev_in
-            cur.wait_event(ev_in)
-            slot_free[slot].acquire()  # results of the block that last used the slot are on the host
-            sl = lambda d: None if d is None else d[slot][:m]
-            o_co, o_cr = front(d_oco, slot, m), front(d_ocr, slot, m)
-            plan.invert(sl(d_in[0]), sl(d_in[1]), sl(d_in[2]), sl(d_in[3]) if d_in[3] is not None else dsig_scalar,
-                        sl(d_in[4]), sigma0_db=sigma0_db, merge_dual=merge_dual, cr_abs=cr_abs, mode=mode,
-                        out_co=o_co, out_cr=o_cr, speed_dir=speed_dir, out_f32=out_f32,
-                        ground_heading=sl(d_in[5]) if d_in[5] is not None else gh_scalar)
-            ev_scan[slot] = torch.cuda.Event()
-            ev_scan[slot].record(cur)
-            with torch.cuda.stream(s_out):
-                s_out.wait_event(ev_scan[slot])
-                if out_co is not None:
-                    torch.from_numpy(front(oco_stage, slot, m)).copy_(o_co, non_blocking=True)
-                torch.from_numpy(front(ocr_stage, slot, m)).copy_(o_cr, non_blocking=True)
-                ev_out = torch.cuda.Event()
-                ev_out.record(s_out)
-            jobs.put((ev_out, slot, lo, hi))
+        invert(0, upload(0))
+        nxt = upload(1) if nb > 1 else None
+        for b in range(nb):
+            if b + 1 < nb:
+                invert(b + 1, nxt)                # queued behind the scan of block b
+            if b + 2 < nb:
+                nxt = upload(b + 2)               # host-side staging overlaps the scans
+            download(b)                           # blocks on the staging ring; the GPU is busy with block b + 1
     finally:
         jobs.put(None)
         worker.join()
