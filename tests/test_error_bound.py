@@ -36,12 +36,13 @@ def slabs():
     return lut_db, gw, gp
 
 
-def kernel_E(m32, sc_abs, amag, lmax, wmax):
+def kernel_E(m32, sc_abs, amag, lmax, wmax, shared=False):
     """Mirror of the band section of k_scan_co (float arithmetic there, float64 here): bound of the full centred form."""
     A, W = amag, wmax * 1.0000002
     T = W * A + 0.25 * W * W
     SC = sc_abs
-    D = np.sqrt(np.maximum(m32 + SC * SC * 1.0000002, 0.0) + 0.25 * A * A + 1.0)
+    R0 = np.sqrt(np.maximum(m32, 0.0) + 0.25 * A * A + 1.0)
+    D = np.sqrt(np.maximum(m32 + SC * SC * 1.0000002, 0.0) + 0.25 * A * A + 1.0 + (2.0 * SC * R0 * 1.000001 if shared else 0.0))
     Lam = D + SC
     E = 5.9604645e-8 * 1.5 * (2 * Lam * lmax + 2 * SC * lmax + 4 * Lam * Lam + 6 * SC * Lam + SC * SC + D * D + 4 * T)
     return E, D
@@ -114,7 +115,7 @@ def test_shared_sigma0_mode_band_and_second_filter(slabs):
     rng = np.random.default_rng(21)
     cphi, sphi = np.cos(np.radians(gp)), np.sin(np.radians(gp))
     nwh32, w2q32 = f32(-0.5 * gw), f32(0.25 * gw * gw)
-    n_checked = 0
+    n_checked = n_outside = 0
     for b in range(lut_db.shape[0]):
         Ls = lut_db[b] / dsig
         L32 = f32(Ls)
@@ -124,7 +125,7 @@ def test_shared_sigma0_mode_band_and_second_filter(slabs):
             iw, ip = rng.integers(0, gw.size), rng.integers(0, gp.size)
             s = lut_db[b, iw, ip] if kind == 0 else rng.uniform(-35.0, 5.0)
             if kind == 4:
-                s = rng.uniform(-45.0, 12.0)                                  # outside the LUT range: large lambda at the minimum
+                s = rng.choice([rng.uniform(-60.0, -40.0), rng.uniform(8.0, 25.0)])   # outside the LUT range: large lambda, small spread
             a_w, a_p = (gw[iw], np.radians(gp[ip])) if kind == 0 else (rng.uniform(0.0, 40.0), rng.uniform(0.0, np.pi))
             qa, qb = a_w * np.cos(a_p), a_w * np.sin(a_p)
             sc = rng.uniform(-1.0, 1.0) * 10.0 ** rng.uniform(-4, -1.5)       # |sigma| of a sorted list: 1e-4 .. 3e-2
@@ -143,9 +144,13 @@ def test_shared_sigma0_mode_band_and_second_filter(slabs):
             m32 = Ja.min()
             amag = float(F32(np.hypot(qa, qb))) * 1.000001
             SC = abs(sc) * 1.0000002
-            efp, D = kernel_E(m32, SC, amag, lmax, gw.max())
+            efp, D = kernel_E(m32, SC, amag, lmax, gw.max(), shared=True)
             Lam = D + SC
-            E = efp + 2.0 * SC * Lam * 1.000001
+            sp = float(F32(s / dsig))
+            dist = max(float(L32.min()) - sp, sp - float(L32.max()))      # sigma0 outside the slab's value range?
+            dmin = max(dist * 0.999999 - 1e-6 * lmax - 1e-6 * abs(sp), 0.0)
+            dl = max(Lam - dmin, 0.0) if dmin > 0.0 else 2.0 * Lam
+            E = efp + SC * dl * 1.000001
             if not (E < 0.25):      # the kernel sends such pixels to the exhaustive FP64 kernel
                 continue
             band = Ja <= m32 + 2 * E
@@ -157,4 +162,5 @@ def test_shared_sigma0_mode_band_and_second_filter(slabs):
             ties = Jx == Jx[ix]                                               # every exact tie must survive too
             assert (band & (Jf <= Jf[band].min() + 2 * efp))[ties].all()
             n_checked += 1
-    assert n_checked > 100
+            n_outside += dmin > 0.0
+    assert n_checked > 100 and n_outside > 15

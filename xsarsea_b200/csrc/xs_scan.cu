@@ -184,22 +184,21 @@ __global__ void __launch_bounds__(NW * 32, MB) k_scan_co(xs_plan pl, Workspace w
             if (any) cs = (float)(0.5 * (smin + smax));
         }
         // Shared-sigma0 mode: the list is in sigma0 order, so the warp's pixels usually differ from the centre by a tiny
-        // |sigma|; then k lambda (|k lambda| <= 2 |sigma| Lam) is left out of the scanned cost altogether -- one FFMA2 per
-        // pixel and candidate pair instead of two -- and added to the error band instead (see the band section below).
-        // The omitted term is bounded by 2 |sigma| Lam, and Lam grows with the distance of sigma0 from the slab's value
-        // range (a pixel far outside the LUT has a large lambda at its minimum): the mode is chosen from an estimate of
-        // that product (performance only -- the band below uses the rigorous bound).
+        // |sigma|; then k lambda = -2 sigma lambda is left out of the scanned cost altogether -- one FFMA2 per pixel and
+        // candidate pair instead of two -- and the band is widened by what the omission can change BETWEEN two candidates
+        // that can win, 2 |sigma| |lambda(c1) - lambda(c2)| (see the band section below).  The mode is chosen from an
+        // estimate of that quantity (performance only -- the band uses the rigorous bound).
+        const float slab_lo = float_from_order_key(pl.slab_range[2 * bin]), slab_hi = float_from_order_key(pl.slab_range[2 * bin + 1]);
         float budget_need = 0.f;
-        {
-            const float lo = float_from_order_key(pl.slab_range[2 * bin]), hi = float_from_order_key(pl.slab_range[2 * bin + 1]);
 #pragma unroll
-            for (int p = 0; p < P; ++p)
-                if (mine[p].state == 1) {
-                    const float sp = (float)(mine[p].s / pl.dsig_co);
-                    const float dmin = fmaxf(fmaxf(lo - sp, sp - hi), 0.f);
-                    budget_need = fmaxf(budget_need, 2.f * fabsf(sp - cs) * (dmin + 2.5f));
-                }
-        }
+        for (int p = 0; p < P; ++p)
+            if (mine[p].state == 1) {
+                const float sp = (float)(mine[p].s / pl.dsig_co);
+                const float dmin = fmaxf(fmaxf(slab_lo - sp, sp - slab_hi), 0.f);
+                // |d| of a winning candidate lies in [dmin, ~sqrt(dmin^2 + 6)]: outside the slab's range the spread is small
+                const float spread = dmin > 0.f ? sqrtf(dmin * dmin + 6.f) - dmin : 5.f;
+                budget_need = fmaxf(budget_need, fabsf(sp - cs) * spread);
+            }
         const bool shared = any && budget_need <= share_tau;  // warp-uniform
         float nqs[P];   // k_p = -2 (s_p/dsig - cs); 0 in shared mode
         u64 g[P][KP];   // {g(phi_even), g(phi_odd)} as packed FP32
@@ -340,14 +339,26 @@ __global__ void __launch_bounds__(NW * 32, MB) k_scan_co(xs_plan pl, Workspace w
             // Error terms (u = 2^-24): image value and lambda roundings 2 Lam (lmax + Lam) through lambda^2 and
             // 2 |sc| (lmax + 2 Lam) through k lambda; M, a and J roundings Lam^2 + W^2/4, Lam^2 + W^2/4 + 2 |sc| Lam and
             // D^2 + sc^2 + T; row-table and g roundings W^2/4 + W A; the W terms add up to W^2 + 2 W A <= 4 T.
-            const float D = sqrtf(fmaxf(m32 + SC * SC * 1.0000002f, 0.f) + 0.25f * A * A + 1.0f);
+            // Shared mode scans J_a = J'' - k lambda.  With c^ the scanned minimum and c* the true argmin: lambda(c^)^2 <=
+            // J_a(c^) + A^2/4 <= m32 + A^2/4 + 1 =: R0^2 (the "+ 1" covers the FP32 error, below 0.25), J''(c*) <= J''(c^) <=
+            // m32 + E_fp + 2 |sc| R0, hence |d(c*)| <= D with the extra 2 |sc| R0 under the root.
+            const float R0 = sqrtf(fmaxf(m32, 0.f) + 0.25f * A * A + 1.0f);
+            const float D = sqrtf(fmaxf(m32 + SC * SC * 1.0000002f, 0.f) + 0.25f * A * A + 1.0f + (shared ? 2.f * SC * R0 * 1.000001f : 0.f));
             const float Lam = D + SC;
             float E = 5.9604645e-8f * 1.5f * (2.f * Lam * lmax + 2.f * SC * lmax + 4.f * Lam * Lam + 6.f * SC * Lam + SC * SC + D * D + 4.f * T);
-            // shared mode: the scanned cost lacks k lambda = -2 sigma lambda.  Both the scanned minimum's candidate and the
-            // true argmin have |lambda| <= Lam (the "+ 1" under D's root covers the shift of the minimum as long as the total
-            // bound stays below 1, which `sane` checks), so the omission moves their costs by at most 2 |sigma| Lam.
             const float efp = E;  // bound of the full centred form's FP32 error (the refinement's second filter in shared mode)
-            if (shared) E += 2.f * SC * Lam * 1.000001f;
+            if (shared) {
+                // J32_a(c*) <= J_a(c*) + E_fp = J''(c*) - k lambda(c*) + E_fp <= J''(c^) - k lambda(c*) + E_fp
+                //           <= J32_a(c^) + 2 E_fp + |k| |lambda(c^) - lambda(c*)|,   lambda(c^) - lambda(c*) = d(c^) - d(c*).
+                // Both |d| are at most Lam; when sigma0 lies outside the slab's value range by dmin, every d has the same
+                // sign and magnitude >= dmin, so the difference is at most Lam - dmin (a pixel far outside the LUT has a
+                // large lambda but a small spread); otherwise it is at most 2 Lam.
+                const float sp = (float)(mine[p].s / pl.dsig_co);
+                const float dist = fmaxf(slab_lo - sp, sp - slab_hi);  // scan-image values; the exact L/dsig differ by <= 1 ulp
+                const float dmin = fmaxf(dist * 0.999999f - 1e-6f * lmax - 1e-6f * fabsf(sp), 0.f);
+                const float dl = dmin > 0.f ? fmaxf(Lam - dmin, 0.f) : 2.f * Lam;
+                E += SC * dl * 1.000001f;  // half of |k| dl: the band is m32 + 2E
+            }
             const float thr = m32 + 2.f * E;
             // 2 E < kBandMargin keeps the chunk masks complete; a larger bound means magnitudes outside the range the
             // bound was derived for
@@ -618,7 +629,7 @@ static int launch_shape(const xs_plan *pl, const RasterArgs &ra, const Workspace
     static float share_tau = -1.f;
     if (share_tau < 0.f) {
         const char *e = getenv("XS_SHARE_BUDGET");
-        share_tau = e ? (float)atof(e) : 0.02f;
+        share_tau = e ? (float)atof(e) : 0.03f;
     }
     const size_t smem = sizeof(ScanSmem<KP, P, NW>) + sizeof(float2) * (size_t)pl->n_wspd_pad;
     if (smem > 200 * 1024) {
