@@ -56,7 +56,7 @@ namespace xs {
 
 constexpr int kChunkRows = 16;     // wspd rows per staged chunk = granularity of the argmin bookkeeping
 constexpr int kRowPad = 8;         // the scan image pads the wspd axis to a multiple of this (+inf rows)
-constexpr int kStages = 3;         // shared-memory ring depth of the scan
+constexpr int kStages = 4;         // shared-memory ring depth of the scan (4 x 12 KB per CTA at 192 phi slots; 4 CTAs per SM)
 constexpr int kCrInvBuckets = 1024;
 constexpr float kBandMargin = 0.5f;  // every accepted error band is narrower than this (2 E < kBandMargin)
 constexpr int kTilePad = 32;       // upper bound of the pixels per scan tile (the bin segments of the pixel list are padded to tiles)
@@ -293,10 +293,10 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
                  "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
-// shared-memory arrival counter with acquire/release ordering inside the CTA
-__device__ __forceinline__ unsigned atom_add_acq_rel_shared(unsigned *p, unsigned v) {
+// shared-memory arrival counter (relaxed: the one thread that acts on the count fences before it does)
+__device__ __forceinline__ unsigned atom_add_shared(unsigned *p, unsigned v) {
     unsigned old;
-    asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(smem_u32(p)), "r"(v) : "memory");
+    asm volatile("atom.relaxed.cta.shared::cta.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(smem_u32(p)), "r"(v) : "memory");
     return old;
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }

@@ -18,7 +18,7 @@
 //   k_list_prepare  one 32-byte PixRec per record position from the sorted pixel indices (bins padded to whole tiles)
 //   k_scan_co       persistent CTAs (4 per SM, 4 warps, 128 registers): a tile = 32 record positions of one bin; the tile's
 //                   PixRecs and the bin's slab of the FP32 scan image arrive by bulk-async (TMA) copies -- records
-//                   double-buffered one tile ahead, slab chunks of 16 wspd rows through a 3-stage ring that keeps
+//                   double-buffered one tile ahead, slab chunks of 16 wspd rows through a 4-stage ring that keeps
 //                   streaming across tile boundaries; there is no producer thread and no CTA barrier: the warp that is
 //                   the last to finish a chunk refills its stage (shared-memory arrival counter), so no warp ever waits
 //                   for another one to release a stage.  Lane l owns the phi pairs {2(l+32j), 2(l+32j)+1}; per lane and
@@ -83,7 +83,6 @@ struct ScanSmem {
     static constexpr int kRowFloats = 64 * KP;
     alignas(128) float ring[kStages][kChunkRows * kRowFloats];
     alignas(16) PixRec pix[2][NW * P];
-    alignas(16) double2 cs_phi[64 * KP];  // (cos, sin) of the phi node, (0, 0) in the padding
     alignas(8) uint64_t full[kStages];    // a chunk has landed in the stage
     uint64_t pix_full[2];                 // the tile's records (or the end-of-work mark) have landed
     unsigned done[kStages];               // warps that have finished with the stage's chunk (monotonic)
@@ -145,8 +144,6 @@ __global__ void __launch_bounds__(NW * 32, MB) k_scan_co(xs_plan pl, Workspace w
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int i = threadIdx.x; i < pl.n_wspd_pad; i += blockDim.x) rowtab_s[i] = pl.rowtab[i];
-    for (int i = threadIdx.x; i < 64 * KP; i += blockDim.x)
-        sm.cs_phi[i] = i < pl.n_phi ? make_double2(pl.cos_phi[i], pl.sin_phi[i]) : make_double2(0.0, 0.0);
     __syncthreads();
     if (threadIdx.x == 0) {  // first tile and the first NS chunks of its slab
         fetch_tile(0);
@@ -209,8 +206,11 @@ __global__ void __launch_bounds__(NW * 32, MB) k_scan_co(xs_plan pl, Workspace w
             const double qa = mine[p].qa, qb = mine[p].qb;
 #pragma unroll
             for (int j = 0; j < KP; ++j) {
-                const double2 c0 = sm.cs_phi[2 * (lane + 32 * j)], c1 = sm.cs_phi[2 * (lane + 32 * j) + 1];
-                g[p][j] = on ? pack2(g32(qa, qb, c0.x, c0.y), g32(qa, qb, c1.x, c1.y)) : 0ull;
+                // (cos, sin) of the lane's phi nodes: 12 L1-resident loads per tile; 0 in the padding (+inf image values there)
+                const int ip = 2 * (lane + 32 * j);
+                const double c0x = ip < pl.n_phi ? pl.cos_phi[ip] : 0.0, c0y = ip < pl.n_phi ? pl.sin_phi[ip] : 0.0;
+                const double c1x = ip + 1 < pl.n_phi ? pl.cos_phi[ip + 1] : 0.0, c1y = ip + 1 < pl.n_phi ? pl.sin_phi[ip + 1] : 0.0;
+                g[p][j] = on ? pack2(g32(qa, qb, c0x, c0y), g32(qa, qb, c1x, c1y)) : 0ull;
             }
         }
         // per lane and pixel: the running minimum and the set of chunks (bit c >> mask_sh) whose minimum came within
@@ -284,8 +284,10 @@ __global__ void __launch_bounds__(NW * 32, MB) k_scan_co(xs_plan pl, Workspace w
                 // the warp that is the last to finish with a stage refills it (stream chunk + NS); at a tile's first
                 // chunk it also fetches the CTA's next tile: every warp has left the previous tile by then, so the
                 // other record buffer is free
-                const unsigned old = atom_add_acq_rel_shared(&sm.done[stage], 1u);
+                // (the warp's reads of the stage are complete: their values have been consumed; the arrival itself is relaxed)
+                const unsigned old = atom_add_shared(&sm.done[stage], 1u);
                 if (old % NW == NW - 1) {
+                    __threadfence_block();  // the other warps' arrivals (and what they wrote before them) are visible
                     if (c == 0) fetch_tile(b ^ 1);
                     int c2 = c + NS, bin2 = bin;
                     bool ok = true;
@@ -305,10 +307,10 @@ __global__ void __launch_bounds__(NW * 32, MB) k_scan_co(xs_plan pl, Workspace w
             const unsigned cbit = 1u << (c >> mask_sh);
 #pragma unroll
             for (int p = 0; p < P; ++p) {
-                const float mp = m[p];
-                cmask[p] = (mp < best[p] - kBandMargin) ? 0u : cmask[p];
-                cmask[p] |= (mp <= best[p] + kBandMargin) ? cbit : 0u;
-                best[p] = fminf(best[p], mp);
+                const float dm = m[p] - best[p];  // -inf while best is still +inf; NaN (no bit) when the chunk is all padding too
+                cmask[p] = (dm < -kBandMargin) ? 0u : cmask[p];
+                cmask[p] |= (dm <= kBandMargin) ? cbit : 0u;
+                best[p] = fminf(best[p], m[p]);
                 m[p] = CUDART_INF_F;
             }
             if (++stage == NS) {
@@ -411,6 +413,10 @@ __global__ void __launch_bounds__(256, 3) k_refine_easy(xs_plan pl, Workspace ws
     for (int64_t e0 = warp * 4; e0 < n_pos; e0 += n_warps * 4) {
         const int64_t e = e0 + grp;
         if (e >= n_pos) continue;
+        if (sub < 2 && e + n_warps * 4 < n_pos) {  // the next iteration's records: into L2 while this one computes
+            const void *nxt = sub == 0 ? (const void *)&ws.pix[e + n_warps * 4] : (const void *)&ws.rec[e + n_warps * 4];
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt));
+        }
         const PixRec px = ws.pix[e];
         const RefRec rc = ws.rec[e];  // loaded together with the pixel (only meaningful for state 1)
         if (px.state == 0) continue;  // uniform within the group; no warp-wide synchronisation below
