@@ -67,7 +67,19 @@ def interval_search(col, wg, s, dsig, mag, hc, tables=None, wspd_uniform=None):
     vlo, scale, inv = tables if tables is not None else inverse_index(col)
     t = (s - vlo) * scale
     b = int(min(t, NB - 1)) if t > 0.0 else 0
-    k = first_ge(inv[max(b - 1, 0)], inv[min(b + 2, NB)], lambda w: not (num(w) < 0.0))
+    k = first_ge(inv[b], inv[b + 1], lambda w: not (num(w) < 0.0))
+    if not hc:   # cross-pol only: decided on |L - s| of the nodes around the sign change (no division)
+        xa = abs(num(k - 1)) if k > 0 else math.inf
+        xb = abs(num(k)) if k < n else math.inf
+        xm = min(xa, xb)
+        if 1e-100 <= dsig <= 1e100 and 1e-100 * dsig <= xm <= 1e100 * dsig:
+            if xa > xb * (1.0 + 4e-16):
+                return k, 1
+            if xa <= xb:
+                if k - 1 == 0:
+                    return 0, 1
+                if abs(num(k - 2)) > xa * (1.0 + 4e-16):
+                    return k - 1, 1
     m0 = math.inf
     if k < n:
         m0 = cost(col, wg, s, dsig, mag, hc, k)

@@ -301,9 +301,42 @@ __device__ __forceinline__ double exact_cost_cr(double L, double s, double dsig,
 // that can be the argmin (J <= m0, ties included) has a <= m0 and b <= m0, and each of these sets is an index interval
 // whose ends are found by bisection.  The interval is then scanned in index order with the reference's operations
 // (first minimum wins, like np.argmin).  Returns -1 when no finite bound exists (caller falls back to the full scan).
-__device__ __forceinline__ int cross_interval_search(const xs_plan &pl, int bin, const double *__restrict__ col,
-                                                     const double *__restrict__ wg, int n, double s, double dsig, double mag,
-                                                     bool hc) {
+// Cross-pol only (no co-pol solution), monotone finite row, dsig > 0: the argmin from the nodes around the sign change of
+// L[w] - s, found through the row's inverse index; -2 when a comparison falls into a rounding sliver or the magnitudes
+// leave the normal range (the caller then runs the general search).  Derivation: see the `!hc` block of
+// cross_interval_search, which repeats these decisions.
+__device__ __forceinline__ int cross_only_fast(const xs_plan &pl, int bin, const double *__restrict__ col, int n, double s,
+                                               double dsig) {
+    const double t = (s - pl.cr_vlo[bin]) * pl.cr_vscale[bin];
+    const int b = t > 0.0 ? (int)fmin(t, (double)(kCrInvBuckets - 1)) : 0;
+    const unsigned short *inv = pl.cr_inv + (int64_t)bin * (kCrInvBuckets + 1);
+    int lo = inv[b], hi = inv[b + 1];
+    const int lo0 = lo, hi0 = hi;
+    while (lo < hi) {  // first w in the bracket with L[w] >= s
+        const int mid = (lo + hi) >> 1;
+        if (col[mid] < s)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    const int k = lo;
+    const double lm1 = k > 0 ? col[k - 1] : -CUDART_INF, l0 = k < n ? col[k] : CUDART_INF;
+    if ((k == lo0 && !(lm1 < s)) || (k == hi0 && l0 < s)) return -2;  // the bracket missed: general search
+    const double xa = k > 0 ? fabs(__dsub_rn(lm1, s)) : CUDART_INF, xb = k < n ? fabs(__dsub_rn(l0, s)) : CUDART_INF;
+    const double xm = fmin(xa, xb);
+    if (!(dsig >= 1e-100 && dsig <= 1e100 && xm >= 1e-100 * dsig && xm <= 1e100 * dsig)) return -2;
+    if (xa > xb * (1.0 + 4e-16)) return k;
+    if (xa <= xb) {
+        if (k - 1 == 0) return 0;
+        if (fabs(__dsub_rn(col[k - 2], s)) > xa * (1.0 + 4e-16)) return k - 1;
+    }
+    return -2;
+}
+
+// (not inlined: the hot path of the cross-pol-only pass is `cross_only_fast`, which keeps the kernel's register count low)
+__device__ __noinline__ int cross_interval_search(const xs_plan &pl, int bin, const double *__restrict__ col,
+                                                  const double *__restrict__ wg, int n, double s, double dsig, double mag,
+                                                  bool hc) {
     auto num_at = [=](int w) { return __dsub_rn(col[w], s); };  // ts = num/dsig has the sign of num (dsig > 0)
     auto tw_at = [=](int w) { return __dmul_rn(__dsub_rn(wg[w], mag), 0.5); };
     auto cost = [=](int w) { return exact_cost_cr(col[w], s, dsig, wg[w], mag, hc); };
@@ -336,7 +369,25 @@ __device__ __forceinline__ int cross_interval_search(const xs_plan &pl, int bin,
         const double t = (s - pl.cr_vlo[bin]) * pl.cr_vscale[bin];
         const int b = t > 0.0 ? (int)fmin(t, (double)(kCrInvBuckets - 1)) : 0;
         const unsigned short *inv = pl.cr_inv + (int64_t)bin * (kCrInvBuckets + 1);
-        k = first_ge(inv[max(b - 1, 0)], inv[min(b + 2, kCrInvBuckets)], [=](int w) { return !(num_at(w) < 0.0); });
+        k = first_ge(inv[b], inv[b + 1], [=](int w) { return !(num_at(w) < 0.0); });
+    }
+    if (!hc) {
+        // Cross-pol only: J(w) = g(|x_w|), x_w = fl(L[w] - s), with g(x) = fl(fl(x/dsig)^2) non-decreasing (IEEE rounding is
+        // monotone).  |x_w| falls up to k - 1 and rises from k on, so the minimum is J(k-1) or J(k); np.argmin's first
+        // minimum is k if J(k) < J(k-1), else the start of the run of costs equal to J(k-1) that ends at k - 1.  Whether two
+        // costs are equal is decided on the |x| themselves: g(xa) > g(xb) whenever xa > xb (1 + 4e-16) (relative error of
+        // g below 3.4e-16 in the normal range).  The slivers in between, and magnitudes outside the normal range, take the
+        // general search below.
+        const double xa = k > 0 ? fabs(num_at(k - 1)) : CUDART_INF, xb = k < n ? fabs(num_at(k)) : CUDART_INF;
+        const double xm = fmin(xa, xb);
+        const bool normal = dsig >= 1e-100 && dsig <= 1e100 && xm >= 1e-100 * dsig && xm <= 1e100 * dsig;
+        if (normal) {
+            if (xa > xb * (1.0 + 4e-16)) return k;  // J(k) < J(k-1) (also k == 0)
+            if (xa <= xb) {                         // J(k-1) <= J(k): the left run
+                if (k - 1 == 0) return 0;
+                if (fabs(num_at(k - 2)) > xa * (1.0 + 4e-16)) return k - 1;
+            }
+        }
     }
     double m0 = CUDART_INF;
     if (k < n) m0 = cost(k);
@@ -431,12 +482,84 @@ __device__ __forceinline__ int cross_interval_search(const xs_plan &pl, int bin,
     return res;
 }
 
+// Cooperative scan of one pixel's cross-pol candidates by the whole warp (all lanes call it with the same arguments): the
+// path of non-monotone or non-finite LUT rows, dsig <= 0, costs that overflow, and XS_FLAG_CR_FULL_SCAN.  Not inlined: it
+// is rare, and its registers would otherwise be charged to every pixel of the pass.
+__device__ __noinline__ int cross_coop_scan(const xs_plan &pl, double s_cr, double dsig, double mg, int b, bool hc, bool fok,
+                                            int lane) {
+    const unsigned full = 0xffffffffu;
+    const double *col = pl.cr_lut + (int64_t)b * pl.n_wspd_cr;
+    int res = -1;
+    bool settled = false;
+    if (fok) {
+        // FP32 filter pass: J32 = ((L32 - s32) * r32)^2 + (w32/2 - mag32/2)^2.  E bounds |J32 - J| (J = the
+        // reference's FP64 cost) for every candidate whose cost is within the band of the minimum, so the true
+        // argmin has J32 <= m + 2E: a single candidate in the band is the argmin, several are re-evaluated in
+        // FP64 with the reference's operation order.
+        const float *colf = pl.cr_scan + (int64_t)b * pl.n_wspd_cr;
+        const float s32 = (float)s_cr, r32 = (float)(1.0 / dsig), mg2 = hc ? (float)(0.5 * mg) : 0.f;
+        float best = CUDART_INF_F, second = CUDART_INF_F;
+        int bidx = -1;
+        for (int w = lane; w < pl.n_wspd_cr; w += 32) {
+            const float ts = (colf[w] - s32) * r32;
+            float J = ts * ts;
+            if (hc) {
+                const float tw = pl.wspd_cr_half[w] - mg2;
+                J = fmaf(tw, tw, J);
+            }
+            second = fminf(second, fmaxf(best, J));
+            if (J < best) {
+                best = J;
+                bidx = w;
+            }
+        }
+        float m = best;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(full, m, o));
+        const float u = 5.9604645e-8f;
+        const float R2 = 1.01f * m + 1.0f, Rp = sqrtf(R2);
+        const float E = 1.5f * u * (2.f * Rp * fabsf(r32) * (pl.cr_absmax[b] + fabsf(s32)) * 1.0000002f +
+                                    2.f * Rp * ((float)(0.5 * pl.w_cr_absmax) + fabsf(mg2)) * 1.0000002f + 8.f * R2 + 2.f * m);
+        const float thr = m + 2.f * E;
+        const bool sane = isfinite(m) && isfinite(E) && (2.f * E <= 0.01f * m + 1.0f) && isfinite(r32);
+        const unsigned cont = __ballot_sync(full, best <= thr);
+        const unsigned wide = __ballot_sync(full, second <= thr);
+        if (!sane) {
+            // magnitudes outside the range of the bound: leave it to the exhaustive pass
+        } else if (wide == 0 && __popc(cont) == 1) {
+            res = __shfl_sync(full, bidx, __ffs(cont) - 1);
+            settled = true;
+        } else if (cont != 0) {
+            ArgMin am;
+            am.init();
+            if (second <= thr) {  // several contenders in this lane: all of the lane's candidates
+                for (int w = lane; w < pl.n_wspd_cr; w += 32)
+                    am.feed(exact_cost_cr(col[w], s_cr, dsig, pl.wspd_cr_grid[w], mg, hc), w);
+            } else if (best <= thr && bidx >= 0) {
+                am.feed(exact_cost_cr(col[bidx], s_cr, dsig, pl.wspd_cr_grid[bidx], mg, hc), bidx);
+            }
+            am.warp_reduce();
+            res = am.result();
+            settled = true;
+        }
+    }
+    if (!settled) {  // exhaustive, reference order (non-finite inputs, flat or tied costs)
+        ArgMin am;
+        am.init();
+        for (int w = lane; w < pl.n_wspd_cr; w += 32)
+            am.feed(exact_cost_cr(col[w], s_cr, dsig, pl.wspd_cr_grid[w], mg, hc), w);
+        am.warp_reduce();
+        res = am.result();
+    }
+    return res;
+}
+
 // ---- cross-pol / dual-pol pass + NaN classes + merge --------------------------------------------------------
 // windspeed.py:198-207 (NaN classes), :250 (no co-pol), :252-279 (cross-pol argmin), :422-428 (abs / merge).
 // A warp takes 32 consecutive pixels: every lane does the per-pixel scalar work of its own pixel (dB prologue,
 // incidence bin, |wind_co|), then the warp scans the wspd grid of one pixel after the other cooperatively
 // (parameters broadcast by shuffle), and finally every lane writes its own pixel (coalesced).
-__global__ void __launch_bounds__(256) k_cross(xs_plan pl, RasterArgs a, int64_t n_px, OutSpec out) {
+__global__ void __launch_bounds__(256, 3) k_cross(const __grid_constant__ xs_plan pl, RasterArgs a, int64_t n_px, OutSpec out) {
     double2 *const out_co = reinterpret_cast<double2 *>(out.co);
     void *const out_cr = out.cr;
     int *const idx_co = out.idx_co, *const idx_cr = out.idx_cr;
@@ -478,84 +601,21 @@ __global__ void __launch_bounds__(256) k_cross(xs_plan pl, RasterArgs a, int64_t
         bool settled_own = false;
         if (scan && filter_ok && p.dsig_cr > 0.0 && (pl.cr_finite[bin] & 2) && pl.wspd_cr_sorted &&
             !(a.flags & XS_FLAG_CR_FULL_SCAN)) {
-            const int r = cross_interval_search(pl, bin, pl.cr_lut + (int64_t)bin * pl.n_wspd_cr, pl.wspd_cr_grid, pl.n_wspd_cr,
-                                                p.s_cr, p.dsig_cr, mag, has_co);
+            const double *col = pl.cr_lut + (int64_t)bin * pl.n_wspd_cr;
+            int r = has_co ? -2 : cross_only_fast(pl, bin, col, pl.n_wspd_cr, p.s_cr, p.dsig_cr);
+            if (r == -2) r = cross_interval_search(pl, bin, col, pl.wspd_cr_grid, pl.n_wspd_cr, p.s_cr, p.dsig_cr, mag, has_co);
             if (r >= 0) {
                 ix = r;
                 settled_own = true;
             }
         }
         unsigned todo = __ballot_sync(full, scan && !settled_own);
-        while (todo) {
+        while (todo) {  // rare: the warp scans these pixels' wspd grids cooperatively
             const int src = __ffs(todo) - 1;
             todo &= todo - 1;
-            const double s_cr = __shfl_sync(full, p.s_cr, src), dsig = __shfl_sync(full, p.dsig_cr, src);
-            const double mg = __shfl_sync(full, mag, src);
-            const int b = __shfl_sync(full, bin, src);
-            const bool hc = __shfl_sync(full, (int)has_co, src), fok = __shfl_sync(full, (int)filter_ok, src);
-            const double *col = pl.cr_lut + (int64_t)b * pl.n_wspd_cr;
-            int res = -1;
-            bool settled = false;
-            if (fok) {
-                // FP32 filter pass: J32 = ((L32 - s32) * r32)^2 + (w32/2 - mag32/2)^2.  E bounds |J32 - J| (J = the
-                // reference's FP64 cost) for every candidate whose cost is within the band of the minimum, so the true
-                // argmin has J32 <= m + 2E: a single candidate in the band is the argmin, several are re-evaluated in
-                // FP64 with the reference's operation order.
-                const float *colf = pl.cr_scan + (int64_t)b * pl.n_wspd_cr;
-                const float s32 = (float)s_cr, r32 = (float)(1.0 / dsig), mg2 = hc ? (float)(0.5 * mg) : 0.f;
-                float best = CUDART_INF_F, second = CUDART_INF_F;
-                int bidx = -1;
-                for (int w = lane; w < pl.n_wspd_cr; w += 32) {
-                    const float ts = (colf[w] - s32) * r32;
-                    float J = ts * ts;
-                    if (hc) {
-                        const float tw = pl.wspd_cr_half[w] - mg2;
-                        J = fmaf(tw, tw, J);
-                    }
-                    second = fminf(second, fmaxf(best, J));
-                    if (J < best) {
-                        best = J;
-                        bidx = w;
-                    }
-                }
-                float m = best;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(full, m, o));
-                const float u = 5.9604645e-8f;
-                const float R2 = 1.01f * m + 1.0f, Rp = sqrtf(R2);
-                const float E = 1.5f * u * (2.f * Rp * fabsf(r32) * (pl.cr_absmax[b] + fabsf(s32)) * 1.0000002f +
-                                            2.f * Rp * ((float)(0.5 * pl.w_cr_absmax) + fabsf(mg2)) * 1.0000002f + 8.f * R2 + 2.f * m);
-                const float thr = m + 2.f * E;
-                const bool sane = isfinite(m) && isfinite(E) && (2.f * E <= 0.01f * m + 1.0f) && isfinite(r32);
-                const unsigned cont = __ballot_sync(full, best <= thr);
-                const unsigned wide = __ballot_sync(full, second <= thr);
-                if (!sane) {
-                    // magnitudes outside the range of the bound: leave it to the exhaustive pass
-                } else if (wide == 0 && __popc(cont) == 1) {
-                    res = __shfl_sync(full, bidx, __ffs(cont) - 1);
-                    settled = true;
-                } else if (cont != 0) {
-                    ArgMin am;
-                    am.init();
-                    if (second <= thr) {  // several contenders in this lane: all of the lane's candidates
-                        for (int w = lane; w < pl.n_wspd_cr; w += 32)
-                            am.feed(exact_cost_cr(col[w], s_cr, dsig, pl.wspd_cr_grid[w], mg, hc), w);
-                    } else if (best <= thr && bidx >= 0) {
-                        am.feed(exact_cost_cr(col[bidx], s_cr, dsig, pl.wspd_cr_grid[bidx], mg, hc), bidx);
-                    }
-                    am.warp_reduce();
-                    res = am.result();
-                    settled = true;
-                }
-            }
-            if (!settled) {  // exhaustive, reference order (non-finite inputs, flat or tied costs)
-                ArgMin am;
-                am.init();
-                for (int w = lane; w < pl.n_wspd_cr; w += 32)
-                    am.feed(exact_cost_cr(col[w], s_cr, dsig, pl.wspd_cr_grid[w], mg, hc), w);
-                am.warp_reduce();
-                res = am.result();
-            }
+            const int res = cross_coop_scan(pl, __shfl_sync(full, p.s_cr, src), __shfl_sync(full, p.dsig_cr, src),
+                                            __shfl_sync(full, mag, src), __shfl_sync(full, bin, src),
+                                            __shfl_sync(full, (int)has_co, src), __shfl_sync(full, (int)filter_ok, src), lane);
             if (lane == src) ix = res;
         }
         if (!valid) continue;

@@ -59,7 +59,7 @@ constexpr int kRowPad = 8;         // the scan image pads the wspd axis to a mul
 constexpr int kStages = 4;         // shared-memory ring depth of the scan (4 x 12 KB per CTA at 192 phi slots; 4 CTAs per SM)
 constexpr int kCrInvBuckets = 1024;
 constexpr float kBandMargin = 0.5f;  // every accepted error band is narrower than this (2 E < kBandMargin)
-constexpr int kTilePad = 32;       // upper bound of the pixels per scan tile (the bin segments of the pixel list are padded to tiles)
+constexpr int kTilePad = 64;       // upper bound of the pixels per scan tile (the bin segments of the pixel list are padded to tiles)
 constexpr int kMaxIncBins = 6144;  // bins whose two shared-memory histograms (k_bin_scatter) fit the default 48 KB
 
 // raster element access: XS_F64 / XS_F32, promoted to double on load

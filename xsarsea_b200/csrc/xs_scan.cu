@@ -612,7 +612,6 @@ static Shape scan_shape(int kp) {
         if (ep == 8 && em == 3) s = {8, 4, 3};
         if (ep == 7 && em == 4) s = {7, 4, 4};
         if (ep == 6 && em == 4) s = {6, 4, 4};
-        if (ep == 6 && em == 5) s = {6, 4, 5};
     }
     return s;
 }
@@ -669,7 +668,6 @@ int launch_scan_pipeline(const xs_plan *pl, const RasterArgs &ra, const Workspac
     XS_SHAPE(3, 8, 3);
     XS_SHAPE(3, 7, 4);
     XS_SHAPE(3, 6, 4);
-    XS_SHAPE(3, 6, 5);
     XS_SHAPE(4, 4, 3);
     XS_SHAPE(6, 4, 2);
 #undef XS_SHAPE
