@@ -612,6 +612,7 @@ static Shape scan_shape(int kp) {
         if (ep == 8 && em == 3) s = {8, 4, 3};
         if (ep == 7 && em == 4) s = {7, 4, 4};
         if (ep == 6 && em == 4) s = {6, 4, 4};
+        if (ep == 8 && em == 2) s = {8, 8, 2};  // 8 warps per CTA: a tile of 64 pixels shares one ring (half the L2 -> SM traffic)
     }
     return s;
 }
@@ -660,17 +661,21 @@ static int launch_shape(const xs_plan *pl, const RasterArgs &ra, const Workspace
 int launch_scan_pipeline(const xs_plan *pl, const RasterArgs &ra, const Workspace &ws, const unsigned *sorted_px,
                          const OutSpec &out, int64_t n_px, xs_timer *timer, cudaStream_t st) {
     const Shape s = scan_shape(pl->kp);
-#define XS_SHAPE(KP_, P_, MB_) \
-    if (pl->kp == KP_ && s.p == P_ && s.mb == MB_) return launch_shape<KP_, P_, 4, MB_>(pl, ra, ws, sorted_px, out, n_px, timer, st)
+#define XS_SHAPE_NW(KP_, P_, NW_, MB_) \
+    if (pl->kp == KP_ && s.p == P_ && s.nw == NW_ && s.mb == MB_) \
+    return launch_shape<KP_, P_, NW_, MB_>(pl, ra, ws, sorted_px, out, n_px, timer, st)
+#define XS_SHAPE(KP_, P_, MB_) XS_SHAPE_NW(KP_, P_, 4, MB_)
     XS_SHAPE(1, 8, 4);
     XS_SHAPE(2, 8, 4);
     XS_SHAPE(3, 8, 4);
     XS_SHAPE(3, 8, 3);
     XS_SHAPE(3, 7, 4);
     XS_SHAPE(3, 6, 4);
+    XS_SHAPE_NW(3, 8, 8, 2);
     XS_SHAPE(4, 4, 3);
     XS_SHAPE(6, 4, 2);
 #undef XS_SHAPE
+#undef XS_SHAPE_NW
     set_error("xs_invert: no scan instantiation for kp=%d", pl->kp);
     return XS_E_UNSUPPORTED;
 }
