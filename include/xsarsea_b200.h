@@ -150,7 +150,7 @@ void xs_plan_destroy(xs_plan *plan);
 #define XS_FLAG_OUT_F32 64u     /* with OUT_SPEED_DIR: float32 planes */
 
 /* scan modes */
-#define XS_MODE_FAST 0  /* FP32 FFMA2 scan (k_scan_co) + exact refinement of every candidate inside the error band (k_refine_co) */
+#define XS_MODE_FAST 0  /* FP32 FFMA2 scan (k_scan_co) + exact refinement of every candidate inside the error band (k_refine_easy) */
 #define XS_MODE_FP64 1  /* exhaustive FP64 evaluation of every candidate (verification / fallback) */
 
 typedef struct xs_invert_args {
