@@ -604,8 +604,11 @@ def main():
                 rlo, rhi = parallel.row_shard(args.lines, world, r)
                 ok = ok and bool(torch.isfinite(torch.view_as_real(co_full[rlo:rhi])).any())
         per_gpu = value / world
-        strong = {"what": "one scene row-partitioned over N GPUs, results gathered on the device into rank 0",
-                  "ms_total": t_all, "ms_invert": t_inv, "ms_gather": t_gat, "px_per_s": n_px / (t_all * 1e-3),
+        strong = {"what": "one scene row-partitioned over N GPUs, results gathered on the device into rank 0; every rank inverts "
+                          "its rows in sub-blocks and sub-block j travels on a side stream while j + 1 is inverted",
+                  "pieces_per_rank": parallel.n_pieces(args.lines, args.samples, world),
+                  "ms_total": t_all, "ms_invert": t_inv, "ms_gather": t_gat, "ms_gather_note": "exposed: after the last inversion ended",
+                  "px_per_s": n_px / (t_all * 1e-3),
                   "efficiency_vs_n1": n_px / (t_all * 1e-3) / (world * per_gpu), "gather_share_of_step": t_gat / t_all,
                   "efficiency_note": "against N x the per-GPU rate of the weak leg of this run",
                   "collective": "ncclSend/ncclRecv (torch.distributed batch_isend_irecv) into row slices of rank 0's result",

@@ -263,11 +263,15 @@ def _nccl_worker(rank, world, port, q):
         full = bench.synth_scene_device(lines, 700, 7, 20.0, 45.0)          # same seed on every rank: the same scene
         lo, hi = parallel.row_shard(lines, world, rank)
         res = parallel.invert_rows_resident(plan, [t[lo:hi] for t in full], lines, lo, hi, dst=0, merge_dual=True)
+        # ... and with the rows inverted in three sub-blocks whose transfers overlap the next inversion (side stream)
+        res3 = parallel.invert_rows_resident(plan, [t[lo:hi] for t in full], lines, lo, hi, dst=0, merge_dual=True, pieces=3)
+        torch.cuda.synchronize()
         ok = True
         if rank == 0:
             single = plan.invert(*full[:3], 0.1, full[3], merge_dual=True)
             bits = lambda z: torch.view_as_real(z).contiguous().view(torch.int64)
             ok = torch.equal(bits(res[0]), bits(single[0])) and torch.equal(bits(res[1]), bits(single[1]))
+            ok = ok and torch.equal(bits(res3[0]), bits(single[0])) and torch.equal(bits(res3[1]), bits(single[1]))
         else:
             ok = res == (None, None)
         # the host-array API on top of it

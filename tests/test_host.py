@@ -217,6 +217,13 @@ def _gloo_worker(rank, world, port, q):
             ok &= np.array_equal(co_f.numpy(), want_co) and np.array_equal(cr_f.numpy(), want_co * 0.5 + s1)
         else:
             ok &= co_f is None and cr_f is None
+        # the same with the rows of every rank inverted and sent in three sub-blocks (the pipelined form), gathered on rank 1
+        co_f, cr_f = invert_rows_resident(None, (t(inc), t(s0), t(s1), t(anc)), 11, lo, hi, dst=1, dsig_cr=0.5, pieces=3,
+                                          _invert=stub_rows)
+        if rank == 1:
+            ok &= np.array_equal(co_f.numpy(), want_co) and np.array_equal(cr_f.numpy(), want_co * 0.5 + s1)
+        else:
+            ok &= co_f is None and cr_f is None
         q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()

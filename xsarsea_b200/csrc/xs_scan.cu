@@ -398,23 +398,24 @@ __global__ void __launch_bounds__(NW * 32, MB) k_scan_co(xs_plan pl, Workspace w
 // sub + 8 of a cell and all 2 KP phi slots, so g(phi) is evaluated once per slot; a single band member settles the pixel,
 // several are evaluated in FP64 with the reference's operation order and reduced to the lexicographic (J, flat index)
 // minimum = numpy's first minimum.
-template <int KP>
+template <int KP, int G>  // G lanes per record position (32 / G positions per warp in flight)
 __global__ void __launch_bounds__(256, 3) k_refine_easy(xs_plan pl, Workspace ws, OutSpec out, int tile_px) {
-    const int lane = threadIdx.x & 31, sub = lane & 7, grp = lane >> 3;
-    const unsigned gmask = 0xffu << (8 * grp);
+    constexpr int PW = 32 / G;  // positions per warp
+    const int lane = threadIdx.x & 31, sub = lane & (G - 1), grp = lane / G;
+    const unsigned gmask = (G == 32 ? 0xffffffffu : ((1u << G) - 1u)) << (G * grp);
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int64_t n_pos = (int64_t)ws.counters[0] * tile_px;
-    static_assert(kChunkRows == 16, "two rows per lane of a group");
+    static_assert(kChunkRows % G == 0, "whole rows per lane of a group");
     const int n_chunks = (pl.n_wspd_pad + kChunkRows - 1) / kChunkRows;
     int mask_sh = 0;
     while ((n_chunks + (1 << mask_sh) - 1) >> mask_sh > 32) ++mask_sh;
     unsigned n_settled = 0, n_cells = 0, n_fp64 = 0, n_many = 0;
-    for (int64_t e0 = warp * 4; e0 < n_pos; e0 += n_warps * 4) {
+    for (int64_t e0 = warp * PW; e0 < n_pos; e0 += n_warps * PW) {
         const int64_t e = e0 + grp;
         if (e >= n_pos) continue;
-        if (sub < 2 && e + n_warps * 4 < n_pos) {  // the next iteration's records: into L2 while this one computes
-            const void *nxt = sub == 0 ? (const void *)&ws.pix[e + n_warps * 4] : (const void *)&ws.rec[e + n_warps * 4];
+        if (sub < 2 && e + n_warps * PW < n_pos) {  // the next iteration's records: into L2 while this one computes
+            const void *nxt = sub == 0 ? (const void *)&ws.pix[e + n_warps * PW] : (const void *)&ws.rec[e + n_warps * PW];
             asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt));
         }
         const PixRec px = ws.pix[e];
@@ -481,8 +482,8 @@ __global__ void __launch_bounds__(256, 3) k_refine_easy(xs_plan pl, Workspace ws
                     }
                     if (sub == 0 && stage == 0) ++n_cells;
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const int iw = c * kChunkRows + sub + 8 * h;
+                    for (int h = 0; h < kChunkRows / G; ++h) {
+                        const int iw = c * kChunkRows + sub + G * h;
                         if (iw >= pl.n_wspd) continue;
                         const float2 rt = pl.rowtab[iw];
                         const float2 *rowp = reinterpret_cast<const float2 *>(slab32 + (size_t)iw * pl.nph_pad) + L;
@@ -527,19 +528,19 @@ __global__ void __launch_bounds__(256, 3) k_refine_easy(xs_plan pl, Workspace ws
         };
         auto group_sum = [&](int v) {
 #pragma unroll
-            for (int o = 4; o > 0; o >>= 1) v += __shfl_xor_sync(gmask, v, o);
+            for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(gmask, v, o);
             return v;
         };
         auto group_max = [&](int v) {
 #pragma unroll
-            for (int o = 4; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(gmask, v, o));
+            for (int o = G / 2; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(gmask, v, o));
             return v;
         };
         walk(0);
         if (two_stage) {
             float jmin = b1;
 #pragma unroll
-            for (int o = 4; o > 0; o >>= 1) jmin = fminf(jmin, __shfl_xor_sync(gmask, jmin, o));
+            for (int o = G / 2; o > 0; o >>= 1) jmin = fminf(jmin, __shfl_xor_sync(gmask, jmin, o));
             thr2 = jmin + 2.f * rc.efp;
         }
         else
@@ -562,7 +563,7 @@ __global__ void __launch_bounds__(256, 3) k_refine_easy(xs_plan pl, Workspace ws
         }
         if (n_in > 1) {  // FP64 with the reference's operation order over the candidates, first minimum wins
 #pragma unroll
-            for (int o = 4; o > 0; o >>= 1) {
+            for (int o = G / 2; o > 0; o >>= 1) {
                 const double oj = __shfl_xor_sync(gmask, bj, o);
                 const int oi = __shfl_xor_sync(gmask, bi, o);
                 if (oj < bj || (oj == bj && oi < bi)) {
@@ -650,7 +651,17 @@ static int launch_shape(const xs_plan *pl, const RasterArgs &ra, const Workspace
     if (timer) XS_CUDA(cudaEventRecord(timer->ev[0], st));
     XS_LAUNCH(kern, sms * per_sm, NW * 32, smem, st, *pl, ws, share_tau);
     if (timer) XS_CUDA(cudaEventRecord(timer->ev[1], st));
-    XS_LAUNCH(k_refine_easy<KP>, sms * 6, 256, 0, st, *pl, ws, out, TP);
+    static int refine_g = -1;  // lanes per record position in k_refine_easy (XS_REFINE_G: development aid)
+    if (refine_g < 0) {
+        const char *e = getenv("XS_REFINE_G");
+        refine_g = e ? atoi(e) : 8;
+    }
+    if (refine_g == 4)
+        XS_LAUNCH((k_refine_easy<KP, 4>), sms * 6, 256, 0, st, *pl, ws, out, TP);
+    else if (refine_g == 16)
+        XS_LAUNCH((k_refine_easy<KP, 16>), sms * 6, 256, 0, st, *pl, ws, out, TP);
+    else
+        XS_LAUNCH((k_refine_easy<KP, 8>), sms * 6, 256, 0, st, *pl, ws, out, TP);
     if (timer) {
         XS_CUDA(cudaEventRecord(timer->ev[2], st));
         timer->recorded = 1;

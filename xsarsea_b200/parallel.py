@@ -5,9 +5,10 @@ blocks, each rank inverts its block with no communication, and NCCL is used only
 (the reference's analogue is the dask row-block fan-out of windspeed.py:356-364).
 
 The gather is device-resident and moves every result byte exactly once: the destination rank inverts its own rows
-straight into its slice of the full result and posts one receive per peer into that peer's row slice; the peers send
-their block from where the kernel wrote it (ncclSend / ncclRecv through `batch_isend_irecv`).  No padding, no staging
-through the host, no replication to ranks that did not ask for the result.  The same code runs on the gloo backend
+straight into its slice of the full result and posts receives into the peers' row slices; the peers send their rows
+from where the kernel wrote them (ncclSend / ncclRecv through `batch_isend_irecv`).  No padding, no staging through
+the host, no replication to ranks that did not ask for the result.  A rank's rows are inverted in a few sub-blocks and
+each sub-block's results travel on a side stream while the next one is inverted, so only the last transfer is exposed.  The same code runs on the gloo backend
 with CPU tensors (the CPU tests use it with a stub compute function).
 """
 from __future__ import annotations
@@ -50,12 +51,41 @@ def gather_rows(local, full, n_lines: int, dst: int, group=None):
             w.wait()
 
 
+_COMM_STREAMS = {}
+
+
+def _comm_stream(device):
+    """One side stream per device for the gather, so that it overlaps the inversion of the following rows."""
+    import torch
+
+    key = str(device)
+    if key not in _COMM_STREAMS:
+        _COMM_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _COMM_STREAMS[key]
+
+
+def piece_edges(lo: int, hi: int, pieces: int):
+    """Row edges of the `pieces` contiguous sub-blocks of [lo, hi) (the remainder goes to the first ones)."""
+    return [lo + row_shard(hi - lo, pieces, k)[0] for k in range(pieces)] + [hi]
+
+
+def n_pieces(n_lines: int, width: int, world: int, target_px: int = 24 << 20) -> int:
+    """Sub-blocks per rank: as many as keep ~24 Mpx each (enough pixels per incidence bin for the scan's fast mode),
+    at most 4; the same number on every rank."""
+    per_rank = (n_lines // max(world, 1)) * max(width, 1)
+    return int(max(1, min(4, per_rank // target_px)))
+
+
 def invert_rows_resident(plan, blk, n_lines: int, lo: int, hi: int, *, dst=0, dsig_cr=0.1, merge_dual=False, cr_abs=False,
-                         group=None, events=None, _invert=None):
+                         group=None, events=None, pieces=None, _invert=None):
     """This rank's rows [lo, hi) of one scene, device-resident: blk = (inc, sigma0_co, sigma0_cr, ancillary) tensors of
     those rows (None for an absent raster).  Inverts them with `plan` and gathers both results on the device into rank
     `dst`: returns (wind_co, wind_cr) of the whole scene there and (None, None) elsewhere; dst=None keeps every rank's
-    own block.  `events` = two CUDA events recorded after the inversion and after the gather (bench.py)."""
+    own block.
+
+    The block is inverted in `pieces` row sub-blocks (default `n_pieces`): the results of sub-block j travel on a side
+    stream while sub-block j + 1 is inverted, so only the last sub-block's transfer is exposed.
+    `events` = two CUDA events recorded on the current stream after the last inversion and after the gather (bench.py)."""
     import torch
     import torch.distributed as dist
 
@@ -67,22 +97,61 @@ def invert_rows_resident(plan, blk, n_lines: int, lo: int, hi: int, *, dst=0, ds
     run = _invert if _invert is not None else (lambda i, a, b, d, c, oc, ox: plan.invert(
         i, a, b, d, c, merge_dual=merge_dual, cr_abs=cr_abs, out_co=oc, out_cr=ox))
     gather = dst is not None and world > 1
+    if pieces is None:
+        pieces = n_pieces(n_lines, int(np.prod(width)) if width else 1, world) if gather else 1
     if gather and rank == dst:
         full_co = torch.empty((n_lines,) + width, dtype=cdt, device=dev)
         full_cr = torch.empty((n_lines,) + width, dtype=cr_dt, device=dev)
         o_co, o_cr = full_co[lo:hi], full_cr[lo:hi]   # own rows are written in place
     else:
+        full_co = full_cr = None
         o_co = torch.empty((hi - lo,) + width, dtype=cdt, device=dev)
         o_cr = torch.empty((hi - lo,) + width, dtype=cr_dt, device=dev)
-    if hi > lo:
-        cont = lambda t: None if t is None else t.contiguous()
-        run(cont(inc), cont(s_co), cont(s_cr), dsig_cr if np.isscalar(dsig_cr) else cont(dsig_cr), cont(anc), o_co, o_cr)
-    if events is not None:
-        events[0].record()
-    if gather:
-        mine = rank == dst
-        gather_rows(None if mine else o_co, full_co if mine else None, n_lines, dst, group)
-        gather_rows(None if mine else o_cr, full_cr if mine else None, n_lines, dst, group)
+    on_gpu = inc.is_cuda
+    cur = torch.cuda.current_stream(dev) if on_gpu else None
+    comm = _comm_stream(dev) if (on_gpu and gather and pieces > 1) else None
+    if comm is not None:
+        comm.wait_stream(cur)   # the output buffers were allocated on `cur`
+    cont = lambda t, a, b: None if t is None else t[a - lo:b - lo].contiguous()
+    mine = piece_edges(lo, hi, pieces)
+    for k in range(pieces):
+        a, b = mine[k], mine[k + 1]
+        if b > a:
+            run(cont(inc, a, b), cont(s_co, a, b), cont(s_cr, a, b), dsig_cr if np.isscalar(dsig_cr) else cont(dsig_cr, a, b),
+                cont(anc, a, b), o_co[a - lo:b - lo], o_cr[a - lo:b - lo])
+        if events is not None and k == pieces - 1:
+            events[0].record()
+        if not gather:
+            continue
+        # sub-block k of every rank -> rank dst (every rank computes the same edges)
+        ops = []
+        for r in range(world):
+            if r == dst:
+                continue
+            rlo, rhi = row_shard(n_lines, world, r)
+            e = piece_edges(rlo, rhi, pieces)
+            if e[k + 1] <= e[k]:
+                continue
+            if rank == dst:
+                ops.append(dist.P2POp(dist.irecv, _as_real(full_co[e[k]:e[k + 1]]), r, group))
+                ops.append(dist.P2POp(dist.irecv, _as_real(full_cr[e[k]:e[k + 1]]), r, group))
+            elif rank == r:
+                ops.append(dist.P2POp(dist.isend, _as_real(o_co[a - lo:b - lo]), dst, group))
+                ops.append(dist.P2POp(dist.isend, _as_real(o_cr[a - lo:b - lo]), dst, group))
+        if not ops:
+            continue
+        if comm is None:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        else:
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            with torch.cuda.stream(comm):
+                comm.wait_event(ev)   # the transfer starts when this sub-block's results exist; `cur` goes on inverting
+                for w in dist.batch_isend_irecv(ops):
+                    w.wait()
+    if comm is not None:
+        cur.wait_stream(comm)
     if events is not None:
         events[1].record()
     if not gather:
