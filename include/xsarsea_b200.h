@@ -196,7 +196,8 @@ int xs_invert(const xs_plan *plan, const xs_invert_args *args, void *stream);
 /* Layout of the counters an xs_invert call leaves in args.counters_dev (read them with any device->host copy after
  * the stream has reached the end of the call): [0] co-pol tiles, [1] pixels sent to the exhaustive FP64 scan,
  * [2] co-pol pixels settled by the FP32 scan (+ refinement), [3] (lane, chunk) cells re-examined by the refinement,
- * [4..7], [9], [10] clock64 sums per phase when an instrumented scan variant is selected (development aid), else 0,
+ * [4] pixels of a cross-pol-only call that the step-function kernel (k_cross_only) left to the general cross-pol pass,
+ * [5..7], [9], [10] unused (0),
  * [8] tile hand-out cursor, [11] pixels the refinement settled in FP64 (more than one candidate inside the band),
  * [12] pixels with more than two contending lanes, [13] record positions scanned in shared-sigma0 mode. */
 

@@ -311,3 +311,72 @@ def test_row_sharded_gather_nccl_world2(env):
     for p in procs:
         p.join(60)
     assert res == [(0, True), (1, True)]
+
+
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+def test_cross_pol_only_step_function_kernel(env, dtype):
+    """Config 4's fast path (k_cross_only: the argmin as a step function of LINEAR sigma0, no log10 per pixel) against the
+    general cross-pol pass (`cr_full_scan`: cooperative scan of all 771 candidates with the reference's operations) on
+    sigma0 on and next to the midpoints between LUT nodes, on the nodes, outside the LUT's range, zero / negative / NaN /
+    infinite sigma0, NaN incidence, and raster as well as scalar dsig; plus an oracle sample.  The two must agree bit for
+    bit (both take the dB value from the same device log10 when they need one)."""
+    torch, D, nat, ws, impl = env
+    gi, gwc = np.linspace(16, 66, 501), np.linspace(3, 80, 771)
+    cr = D.lut_to_db(D.lut_build(nat.GMF_IDS["gmf_s1_v2"], gi, gwc, None))
+    plan = D.InversionPlan(cr=(cr, gi, gwc))
+    crh = cr.cpu().numpy()
+    rng = np.random.default_rng(77)
+    n = 400_000
+    b = rng.integers(0, gi.size, n)
+    inc = gi[b] + rng.uniform(-0.04, 0.04, n)
+    k = rng.integers(0, gwc.size - 1, n)
+    kind = rng.integers(0, 8, n)
+    s_db = rng.uniform(-50, 0, n)
+    mid = 0.5 * crh[b, k] + 0.5 * crh[b, k + 1]
+    s_db = np.where(kind == 0, crh[b, k], s_db)
+    s_db = np.where(kind == 1, mid, s_db)
+    x = 10.0 ** (s_db / 10.0) - 1e-15
+    rel = rng.choice([0.0, 1e-16, -1e-16, 2e-16, 1e-14, -1e-14, 1e-12, -1e-12, 1e-10, -1e-10], n)
+    x = np.where(kind <= 2, x * (1.0 + rel), x)
+    x[3::1001] = 0.0
+    x[4::1001] = -1e-15
+    x[5::1001] = -1e-3
+    x[6::1001] = np.nan
+    x[7::1001] = np.inf
+    x[8::1001] = 1e-300
+    inc[9::1001] = np.nan
+    dsig = 10.0 ** rng.uniform(-6, 3, n)
+    dsig[10::1001] = 0.0
+    dsig[11::1001] = np.nan
+    dsig[12::1001] = -0.2
+    if dtype == "f32":
+        inc, x, dsig = (a.astype(np.float32) for a in (inc, x, dsig))
+    d_inc, d_x, d_dsig = D.to_device(inc), D.to_device(x), D.to_device(dsig)
+    for dsig_arg in (d_dsig, 0.1):
+        for kw in (dict(), dict(cr_abs=True), dict(speed_dir=True)):
+            _, fast, _, ifast = plan.invert(d_inc, None, d_x, dsig_arg, None, want_idx=True, **kw)
+            st = plan.last_stats()
+            _, slow, _, islow = plan.invert(d_inc, None, d_x, dsig_arg, None, want_idx=True, cr_full_scan=True, **kw)
+            assert torch.equal(ifast, islow), (dtype, kw, torch.nonzero(ifast != islow)[:5])
+            fr = torch.view_as_real(fast) if fast.is_complex() else fast
+            sr = torch.view_as_real(slow) if slow.is_complex() else slow
+            assert torch.equal(fr.view(torch.int64) if fr.dtype == torch.float64 else fr.view(torch.int32),
+                               sr.view(torch.int64) if sr.dtype == torch.float64 else sr.view(torch.int32)), (dtype, kw)
+            # the step-function kernel settled the bulk: what it leaves are the deliberately degenerate pixels and the guard hits
+            assert 0 < st["cross_listed_pixels"] < 0.2 * n, st   # one pixel in eight sits on a midpoint here
+    # an oracle sample (numpy's log10 may differ from the device's by an ulp: exact midpoints are excluded)
+    sel = np.flatnonzero((kind > 1) | ((kind == 0) & (rel != 0)))[:30000]
+    with np.errstate(all="ignore"):
+        s_ref = 10 * np.log10(x[sel].astype(np.float64) + 1e-15)
+        _, o_du, _, o_ix = oracle.invert(inc[sel].astype(np.float64), np.nan, s_ref, dsig[sel].astype(np.float64), np.nan + 0j,
+                                         cr_lut=crh, inc_cr_grid=gi, wspd_cr_grid=gwc)
+    _, _, _, ix = plan.invert(d_inc, None, d_x, d_dsig, None, want_idx=True)
+    got = ix.cpu().numpy()[sel]
+    assert (got != o_ix).mean() < 1e-4, np.flatnonzero(got != o_ix)[:10]
+    # dB input takes the same kernel with the dB midpoint table
+    s_in = np.where(np.isfinite(x) & (x + 1e-15 > 0), 10 * np.log10(np.abs(x.astype(np.float64)) + 1e-15), -30.0)
+    d_s = D.to_device(s_in.astype(inc.dtype))
+    _, _, _, i1 = plan.invert(d_inc, None, d_s, d_dsig, None, want_idx=True, sigma0_db=True)
+    assert plan.last_stats()["cross_listed_pixels"] < 0.2 * n
+    _, _, _, i2 = plan.invert(d_inc, None, d_s, d_dsig, None, want_idx=True, sigma0_db=True, cr_full_scan=True)
+    assert torch.equal(i1, i2)

@@ -215,3 +215,118 @@ def test_interval_search_equals_brute_force():
             checked += 1
     assert checked > 7000
     assert np.median(widths) <= 8          # a handful of candidates are evaluated instead of 771
+
+
+# ---- k_cross_only: the cross-pol-only argmin as a step function of sigma0 (linear domain, no log10 per pixel) ----------
+PROBE = 6   # kStepProbe
+
+
+def step_tables(col):
+    """k_build_cr_tables: midpoints in dB and in the linear domain, and whether the row is eligible (cr_finite bit 2)."""
+    n = len(col)
+    ok = bool(np.all(np.isfinite(col)))
+    sdb, slin = [0.0], [0.0]
+    for w in range(1, n):
+        a, b = col[w - 1], col[w]
+        ok = ok and (b - a > 1e-9 * (abs(a) + abs(b) + 1.0))
+        mid = 0.5 * a + 0.5 * b
+        lin = 10.0 ** (mid * 0.1)
+        ok = ok and abs(mid) < 3000.0 and 1e-290 < lin < 1e290
+        sdb.append(mid)
+        slin.append(lin)
+    return ok, sdb, slin
+
+
+def step_search(col, x, dsig, db, tables, steps):
+    """Transcription of k_cross_only's per-pixel decision; -1 = left to k_cross."""
+    n = len(col)
+    vlo, vscale, inv = tables
+    ok_row, sdb_t, slin_t = steps
+    y = x if db else x + 1e-15
+    if not (math.isfinite(y) and (db or y > 0.0) and 1e-100 <= dsig <= 1e100) or not ok_row:
+        return -1
+    row = sdb_t if db else slin_t
+    if db:
+        sdb = y
+    else:
+        yf = float(np.float32(y))
+        # __log2f: float log2 with ~2^-22 absolute error; denormal / zero input -> -inf
+        sdb = float(np.float32(3.0102999566) * np.float32(math.log2(yf))) if yf >= 1.18e-38 and math.isfinite(yf) else \
+            (-math.inf if yf < 1.18e-38 else math.inf)
+    t = (sdb - vlo) * vscale
+    b = int(min(t, NB - 1)) if t > 0.0 else 0
+    k_lo, k_hi = max(inv[b] - 1, 0), min(inv[b + 1], n - 1)
+    w0, w1 = max(k_lo, 1), min(k_hi + 1, n - 1)
+    if not (w1 - w0 < PROBE):
+        return -1
+    c_hi = c_lo = 0
+    first_below, last_below = True, False
+    for q in range(PROBE):
+        on = w0 + q <= w1
+        v = row[w0 + q] if on else math.inf
+        below_hi = ((v + 1e-10) if db else v * (1.0 + 1e-11)) < y
+        below_lo = ((v - 1e-10) if db else v * (1.0 - 1e-11)) < y
+        c_hi += below_hi
+        c_lo += below_lo
+        if q == 0:
+            first_below = below_hi
+        if on and w0 + q == w1:
+            last_below = below_lo
+    ok_lo = w0 == 1 or first_below
+    ok_hi = (k_hi == n - 1 or not last_below) if w1 == n - 1 else (not last_below)
+    if w1 < w0:
+        return 0
+    if c_hi == c_lo and ok_lo and ok_hi:
+        return w0 - 1 + c_hi
+    return -1
+
+
+def test_cross_only_step_function_equals_brute_force():
+    """Whenever the step-function kernel settles a pixel, its index is np.argmin of the reference cost evaluated the
+    reference's way (dB conversion included); sigma0 on / next to midpoints and nodes must either agree or be declined."""
+    rng = np.random.default_rng(20261018)
+    n_settled = n_declined = n_random = n_random_declined = 0
+    for case in range(60):
+        n = int(rng.choice([1, 2, 3, 17, 200, 771]))
+        kind = case % 4
+        if kind == 0:      # GMF-like: dB of a power law
+            w = np.linspace(3, 80, n) if n > 1 else np.array([3.0])
+            col = 10 * np.log10(1e-4 * (w / 10.0) ** rng.uniform(1.0, 2.5))
+        elif kind == 1:    # irregular steps, some tiny
+            col = np.cumsum(rng.choice([1e-7, 1e-3, 0.05, 2.0], n)) - 40.0
+        elif kind == 2:    # a plateau: the row is not eligible at all
+            col = np.sort(rng.uniform(-40, -10, n))
+            if n > 2:
+                col[n // 2] = col[n // 2 - 1]
+        else:              # clustered nodes: many nodes in one bucket of the inverse index
+            col = np.sort(np.concatenate([rng.uniform(-30.0, -29.99, n // 2), rng.uniform(-45, -5, n - n // 2)]))
+        col = np.asarray(col, dtype=np.float64)
+        tables = inverse_index(col)
+        steps = step_tables(col)
+        for db in (False, True):
+            mids = 0.5 * col[:-1] + 0.5 * col[1:] if n > 1 else np.array([col[0]])
+            base = np.concatenate([mids, col, rng.uniform(col[0] - 15, col[-1] + 15, 40)])
+            is_random = np.concatenate([np.zeros(len(mids) + len(col), bool), np.ones(40, bool)])
+            for s_t, rnd in zip(base, is_random):
+                for rel in (0.0, 1e-16, -1e-16, 3e-13, -3e-13, 1e-9, -1e-9):
+                    dsig = float(rng.choice([1e-8, 0.1, 1.0, 37.5, 1e4]))
+                    if db:
+                        x = float(s_t + rel * max(abs(s_t), 1.0))
+                        s = x
+                    else:
+                        x = float(10.0 ** (s_t / 10.0) * (1.0 + rel) - 1e-15)
+                        with np.errstate(invalid="ignore", divide="ignore"):
+                            s = float(10.0 * np.log10(np.float64(x) + 1e-15))
+                    got = step_search(col, x, dsig, db, tables, steps)
+                    n_random += rnd and rel == 0.0
+                    if got < 0:
+                        n_declined += 1
+                        n_random_declined += rnd and rel == 0.0
+                        continue
+                    ts = (col - s) / dsig
+                    want = int(np.argmin(ts * ts))
+                    assert got == want, (case, db, x, dsig, got, want)
+                    n_settled += 1
+    assert n_settled > 20000
+    # pixels away from midpoints are settled (only rows that are not eligible, or clustered beyond the probe, decline)
+    assert n_random_declined < 0.45 * n_random, (n_random_declined, n_random)

@@ -20,7 +20,7 @@
 namespace xs {
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
-size_t ws_layout(int n_inc, int64_t n_px, unsigned flags, size_t sort_bytes, char *base, Workspace *w) {
+size_t ws_layout(int n_inc, int64_t n_px, unsigned flags, size_t sort_bytes, bool cr_list, char *base, Workspace *w) {
     size_t off = 0;
     auto take = [&](size_t bytes) {
         char *p = base ? base + off : nullptr;
@@ -41,7 +41,7 @@ size_t ws_layout(int n_inc, int64_t n_px, unsigned flags, size_t sort_bytes, cha
     char *v1 = take(sizeof(unsigned) * (size_t)n_sort);
     if (n_inc <= 0) sort_bytes = 0;
     char *st = take(sort_bytes);
-    char *fb = take(sizeof(unsigned) * (size_t)n_sort);
+    char *fb = take(sizeof(unsigned) * (size_t)((n_inc > 0 || cr_list) ? n_px : 0));  // also k_cross_only's slow list
     char *pr = take(sizeof(PixRec) * (size_t)n_list);
     char *rr = take(sizeof(RefRec) * (size_t)n_list);
     char *it = take((flags & XS_FLAG_OUT_SPEED_DIR) ? sizeof(int) * (size_t)n_px : 0);
@@ -116,7 +116,7 @@ __global__ void k_find_first_nan(xs_plan pl) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
         if (isnan(pl.co_lut[i])) atomicMin(&pl.first_nan[i / per_slab], (int)(i % per_slab));
 }
-__global__ void k_build_cr_tables(xs_plan pl) {
+__global__ void k_build_cr_tables(xs_plan pl, int *n_step_rows) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < pl.n_wspd_cr) pl.wspd_cr_half[i] = (float)(0.5 * pl.wspd_cr_grid[i]);
     if (i < pl.n_inc_cr) {
@@ -131,8 +131,25 @@ __global__ void k_build_cr_tables(xs_plan pl) {
             pl.cr_scan[(int64_t)i * pl.n_wspd_cr + w] = (float)v;
             if (isfinite(v)) amax = fmaxf(amax, (float)fabs(v) * 1.0000002f);
         }
-        pl.cr_finite[i] = ok | ((ok & mono) << 1);
         pl.cr_absmax[i] = amax;
+        // step function of the cross-pol-only argmin (xs_plan::cr_step_db): rows whose neighbouring values are clearly apart
+        int step = ok & mono;
+        {
+            const double *row = pl.cr_lut + (int64_t)i * pl.n_wspd_cr;
+            double *sdb = pl.cr_step_db + (int64_t)i * pl.n_wspd_cr, *slin = pl.cr_step_lin + (int64_t)i * pl.n_wspd_cr;
+            sdb[0] = slin[0] = 0.0;
+            for (int w = 1; w < pl.n_wspd_cr; ++w) {
+                const double a = row[w - 1], b = row[w];
+                step &= (b - a > 1e-9 * (fabs(a) + fabs(b) + 1.0)) ? 1 : 0;
+                const double mid = 0.5 * a + 0.5 * b;
+                const double lin = exp10(mid * 0.1);
+                step &= (fabs(mid) < 3000.0 && lin > 1e-290 && lin < 1e290) ? 1 : 0;
+                sdb[w] = mid;
+                slin[w] = lin;
+            }
+        }
+        if (step) atomicAdd(n_step_rows, 1);
+        pl.cr_finite[i] = ok | ((ok & mono) << 1) | (step << 2);
         // inverse index of a monotone row (see xs_plan::cr_inv)
         const double *col = pl.cr_lut + (int64_t)i * pl.n_wspd_cr;
         unsigned short *inv = pl.cr_inv + (int64_t)i * (kCrInvBuckets + 1);
@@ -554,24 +571,52 @@ __device__ __noinline__ int cross_coop_scan(const xs_plan &pl, double s_cr, doub
     return res;
 }
 
+// What the cross-pol pass leaves for one pixel: the co-pol result where the scan did not write it (no co-pol inversion:
+// NaN, :250), the cross-pol index, and the dual / merged / abs() result (:422-428).
+__device__ __forceinline__ void emit_cross(const OutSpec &out, unsigned flags, int64_t px, bool has_co_solution, double2 co,
+                                           double2 dual, int ix) {
+    double2 *const out_co = reinterpret_cast<double2 *>(out.co);
+    if (out.flags & XS_FLAG_OUT_SPEED_DIR) {
+        if (out_co) store_wind(out, out_co, px, co);
+        if (!has_co_solution && out.idx_co) out.idx_co[px] = -1;
+    } else if (!has_co_solution && out_co) {
+        out_co[px] = co;
+        if (out.idx_co) out.idx_co[px] = -1;
+    }
+    if (out.idx_cr) out.idx_cr[px] = ix;
+    if (out.cr) {
+        double2 o = dual;
+        if (flags & XS_FLAG_MERGE_DUAL) {
+            const double aco = hypot(co.x, co.y), adu = hypot(dual.x, dual.y);
+            if (aco < 5.0 || adu < 5.0) o = co;
+        }
+        if (flags & XS_FLAG_CR_ABS)
+            reinterpret_cast<double *>(out.cr)[px] = o.y == 0.0 ? fabs(o.x) : hypot(o.x, o.y);
+        else
+            store_wind(out, out.cr, px, o);
+    }
+}
+
 // ---- cross-pol / dual-pol pass + NaN classes + merge --------------------------------------------------------
 // windspeed.py:198-207 (NaN classes), :250 (no co-pol), :252-279 (cross-pol argmin), :422-428 (abs / merge).
 // A warp takes 32 consecutive pixels: every lane does the per-pixel scalar work of its own pixel (dB prologue,
 // incidence bin, |wind_co|), then the warp scans the wspd grid of one pixel after the other cooperatively
 // (parameters broadcast by shuffle), and finally every lane writes its own pixel (coalesced).
-__global__ void __launch_bounds__(256, 3) k_cross(const __grid_constant__ xs_plan pl, RasterArgs a, int64_t n_px, OutSpec out) {
+// `list` / `n_list` (optional): the pass covers only the listed pixels (what k_cross_only left over).
+__global__ void __launch_bounds__(256, 3) k_cross(const __grid_constant__ xs_plan pl, RasterArgs a, int64_t n_px, OutSpec out,
+                                                  const unsigned *__restrict__ list, const u64 *__restrict__ n_list) {
     double2 *const out_co = reinterpret_cast<double2 *>(out.co);
-    void *const out_cr = out.cr;
-    int *const idx_co = out.idx_co, *const idx_cr = out.idx_cr;
+    int *const idx_co = out.idx_co;
     const bool planes = out.flags & XS_FLAG_OUT_SPEED_DIR;
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const double nan = CUDART_NAN;
     const unsigned full = 0xffffffffu;
-    for (int64_t base = warp * 32; base < n_px; base += n_warps * 32) {
-        const int64_t px = base + lane;
-        const bool valid = px < n_px;
+    const int64_t n_items = list ? (int64_t)*n_list : n_px;
+    for (int64_t base = warp * 32; base < n_items; base += n_warps * 32) {
+        const bool valid = base + lane < n_items;
+        const int64_t px = !valid ? 0 : (list ? (int64_t)list[base + lane] : base + lane);
         Pixel p;
         p.cls = 0;
         p.co = 0;
@@ -629,28 +674,82 @@ __global__ void __launch_bounds__(256, 3) k_cross(const __grid_constant__ xs_pla
             } else
                 dual = make_double2(wd, 0.0);  // angle(0) = 0, and phi_dual = 0 without co-pol
         }
-        if (planes) {
-            if (out_co) store_wind(out, out_co, px, co);
-            if (!p.co && idx_co) idx_co[px] = -1;
-        } else if (!p.co && out_co) {
-            out_co[px] = co;
-            if (idx_co) idx_co[px] = -1;
-        }
-        if (idx_cr) idx_cr[px] = ix;
-        if (out_cr) {
-            double2 o = dual;
-            if (a.flags & XS_FLAG_MERGE_DUAL) {
-                const double aco = hypot(co.x, co.y), adu = hypot(dual.x, dual.y);
-                if (aco < 5.0 || adu < 5.0) o = co;
-            }
-            if (a.flags & XS_FLAG_CR_ABS)
-                reinterpret_cast<double *>(out_cr)[px] = o.y == 0.0 ? fabs(o.x) : hypot(o.x, o.y);
-            else
-                store_wind(out, out_cr, px, o);
-        }
+        emit_cross(out, a.flags, px, p.co, co, dual, ix);
     }
 }
 
+
+// ---- cross-pol only (config 4): the argmin as a step function of sigma0 ------------------------------------------------
+// Without a co-pol solution the cost is J(w) = fl(fl(fl(L[w] - s)/dsig)^2) (windspeed.py:252-279 with the wind term absent):
+// a monotone function of |L[w] - s|.  On a strictly increasing LUT row np.argmin is therefore the number of midpoints
+// t_w = (L[w-1] + L[w])/2, w >= 1, below s -- unless s lies within rounding distance of a midpoint, where the rounded costs
+// decide and may tie.  This kernel counts the midpoints below sigma0 in the LINEAR domain (10^(t_w/10) against sigma0 +
+// 1e-15: no log10 per pixel) inside the bracket the row's inverse index gives, and settles every pixel that is clear of
+// the midpoints by a relative guard of 1e-11 (the dB value the reference computes is within 3 ulp, < 1e-13 dB, of the
+// exact one; the midpoint table within 1e-14 dB; the guard is 4e-11 dB wide -- and the neighbouring |L - s| then differ by
+// far more than the 4e-16 relative sliver in which rounded costs can tie, see cross_only_fast).  Everything else -- guard
+// hits, bracket misses, NaN / non-finite / non-positive inputs, NaN incidence, rows that are not strictly increasing --
+// goes onto a list for k_cross.  One pixel per thread and iteration; all table loads of a pixel are independent.
+constexpr int kStepProbe = 6;  // midpoints inspected per pixel (a bracket of the 1024-bucket inverse index holds 0 - 2)
+
+__global__ void __launch_bounds__(256) k_cross_only(const __grid_constant__ xs_plan pl, RasterArgs a, int64_t n_px, OutSpec out,
+                                                    unsigned *__restrict__ slow, u64 *__restrict__ n_slow) {
+    const bool db = a.flags & XS_FLAG_SIGMA0_DB;
+    const double *const steps = db ? pl.cr_step_db : pl.cr_step_lin;
+    const int n = pl.n_wspd_cr;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t px = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; px < n_px; px += stride) {
+        const double inc = load_real(a.inc, px, a.dtype);
+        const double x = load_real(a.s_cr, px, a.dtype);
+        const double dsig = a.dsig_cr ? load_real(a.dsig_cr, px, a.dtype) : a.dsig_cr_scalar;
+        const double y = db ? x : x + 1e-15;  // the argument of the reference's log10
+        int kk = -1;
+        if (!isnan(inc) && isfinite(y) && (db || y > 0.0) && dsig >= 1e-100 && dsig <= 1e100) {
+            const int bin = pl.inc_cr_uniform ? nearest_bin_uniform(pl.inc_cr_grid, pl.n_inc_cr, inc, pl.inc_cr_g0, pl.inc_cr_inv_step)
+                                              : nearest_bin(pl.inc_cr_grid, pl.n_inc_cr, inc, pl.inc_cr_sorted);
+            if (pl.cr_finite[bin] & 4) {
+                // bucket of the inverse index from a float estimate of the dB value (a wrong bucket is caught below)
+                const double sdb = db ? y : (double)(3.0102999566f * __log2f((float)y));
+                const double t = (sdb - pl.cr_vlo[bin]) * pl.cr_vscale[bin];
+                const int b = t > 0.0 ? (int)fmin(t, (double)(kCrInvBuckets - 1)) : 0;
+                const unsigned short *inv = pl.cr_inv + (int64_t)bin * (kCrInvBuckets + 1);
+                // first node with L >= s is in [inv[b], inv[b + 1]]; the count of midpoints below s is that node or the one before
+                const int k_lo = max((int)inv[b] - 1, 0), k_hi = min((int)inv[b + 1], n - 1);
+                const int w0 = max(k_lo, 1), w1 = min(k_hi + 1, n - 1);  // midpoints w0 .. w1 are inspected
+                const double *row = steps + (int64_t)bin * n;
+                if (w1 - w0 < kStepProbe) {
+                    int c_hi = 0, c_lo = 0;
+                    bool first_below = true, last_below = false;
+#pragma unroll
+                    for (int q = 0; q < kStepProbe; ++q) {
+                        const bool on = w0 + q <= w1;
+                        const double v = on ? row[w0 + q] : CUDART_INF;
+                        // guard band of the midpoint: relative in the linear domain, absolute in dB
+                        const bool below_hi = (db ? v + 1e-10 : v * (1.0 + 1e-11)) < y;  // certainly below sigma0
+                        const bool below_lo = (db ? v - 1e-10 : v * (1.0 - 1e-11)) < y;  // possibly below sigma0
+                        c_hi += below_hi ? 1 : 0;
+                        c_lo += below_lo ? 1 : 0;
+                        if (q == 0) first_below = below_hi;
+                        if (on && w0 + q == w1) last_below = below_lo;
+                    }
+                    // the bracket is confirmed when the midpoint below it is below sigma0 and the one above it is not
+                    const bool ok_lo = w0 == 1 || first_below;
+                    const bool ok_hi = w1 == n - 1 ? (k_hi == n - 1 || !last_below) : !last_below;
+                    if (w1 < w0)
+                        kk = 0;  // a single-node row
+                    else if (c_hi == c_lo && ok_lo && ok_hi)
+                        kk = w0 - 1 + c_hi;
+                }
+            }
+        }
+        if (kk < 0) {
+            slow[atomicAdd(n_slow, 1ull)] = (unsigned)px;
+            continue;
+        }
+        // cls 1, no co-pol inversion: wind_co = NaN + NaN j (:250), wind_dual = wspd + 0 j (phi_dual = 0 without co-pol)
+        emit_cross(out, a.flags, px, false, make_double2(CUDART_NAN, CUDART_NAN), make_double2(pl.wspd_cr_grid[kk], 0.0), kk);
+    }
+}
 }  // namespace xs
 
 using namespace xs;
@@ -690,6 +789,8 @@ extern "C" void xs_plan_destroy(xs_plan *pl) {
     cudaFree(pl->cr_inv);
     cudaFree(pl->cr_vlo);
     cudaFree(pl->cr_vscale);
+    cudaFree(pl->cr_step_db);
+    cudaFree(pl->cr_step_lin);
     delete pl;
 }
 
@@ -782,6 +883,8 @@ extern "C" int xs_plan_create(const xs_plan_desc *d, void *stream, xs_plan **out
         if ((rc = xs::check(cudaMalloc(&pl->cr_inv, sizeof(unsigned short) * (size_t)d->n_inc_cr * (kCrInvBuckets + 1)), "cudaMalloc")) != XS_OK) return fail(rc);
         if ((rc = xs::check(cudaMalloc(&pl->cr_vlo, sizeof(double) * (size_t)d->n_inc_cr), "cudaMalloc")) != XS_OK) return fail(rc);
         if ((rc = xs::check(cudaMalloc(&pl->cr_vscale, sizeof(double) * (size_t)d->n_inc_cr), "cudaMalloc")) != XS_OK) return fail(rc);
+        if ((rc = xs::check(cudaMalloc(&pl->cr_step_db, sizeof(double) * (size_t)d->n_inc_cr * d->n_wspd_cr), "cudaMalloc")) != XS_OK) return fail(rc);
+        if ((rc = xs::check(cudaMalloc(&pl->cr_step_lin, sizeof(double) * (size_t)d->n_inc_cr * d->n_wspd_cr), "cudaMalloc")) != XS_OK) return fail(rc);
         auto uniform = [](const double *g, int n, double *g0, double *inv_step) {  // ascending and within 1 % of a constant step
             if (n < 2 || !strictly_ascending(g, n)) return 0;
             const double step = (g[n - 1] - g[0]) / (n - 1);
@@ -794,10 +897,14 @@ extern "C" int xs_plan_create(const xs_plan_desc *d, void *stream, xs_plan **out
         pl->inc_cr_uniform = uniform(d->inc_cr_grid_host, d->n_inc_cr, &pl->inc_cr_g0, &pl->inc_cr_inv_step);
         pl->wspd_cr_uniform = uniform(d->wspd_cr_grid_host, d->n_wspd_cr, &pl->wspd_cr_g0, &pl->wspd_cr_inv_step);
     }
+    int *n_step_rows_dev = nullptr;
+    if (has_cr && (rc = xs::check(cudaMalloc(&n_step_rows_dev, sizeof(int)), "cudaMalloc")) != XS_OK) return fail(rc);
     auto build = [&]() -> int {
         if (has_cr) {
             const int nmax = pl->n_wspd_cr > pl->n_inc_cr ? pl->n_wspd_cr : pl->n_inc_cr;
-            XS_LAUNCH(k_build_cr_tables, (int)ceil_div(nmax, 128), 128, 0, st, *pl);
+            XS_CUDA(cudaMemsetAsync(n_step_rows_dev, 0, sizeof(int), st));
+            XS_LAUNCH(k_build_cr_tables, (int)ceil_div(nmax, 128), 128, 0, st, *pl, n_step_rows_dev);
+            XS_CUDA(cudaMemcpyAsync(&pl->cr_step_rows, n_step_rows_dev, sizeof(int), cudaMemcpyDeviceToHost, st));
         }
         if (!has_co) return XS_OK;
         XS_CUDA(cudaMemsetAsync(pl->first_nan, 0x7f, sizeof(int) * (size_t)pl->n_inc, st));  // 0x7f7f7f7f > any index
@@ -812,15 +919,17 @@ extern "C" int xs_plan_create(const xs_plan_desc *d, void *stream, xs_plan **out
         XS_LAUNCH(k_fix_first_nan, (int)ceil_div(pl->n_inc, 256), 256, 0, st, *pl);
         return XS_OK;
     };
-    if ((rc = build()) != XS_OK) return fail(rc);
-    if ((rc = xs::check(cudaStreamSynchronize(st), "xs_plan_create sync")) != XS_OK) return fail(rc);
+    rc = build();
+    if (rc == XS_OK) rc = xs::check(cudaStreamSynchronize(st), "xs_plan_create sync");
+    cudaFree(n_step_rows_dev);
+    if (rc != XS_OK) return fail(rc);
     *out = pl;
     return XS_OK;
 }
 
 extern "C" size_t xs_invert_workspace_bytes(const xs_plan *pl, int64_t n_px, uint32_t flags) {
     if (!pl || n_px < 0) return 0;
-    return ws_layout(pl->fast_ok ? pl->n_inc : 0, n_px, flags, pl->fast_ok ? sort_temp_bytes(n_px) : 0, nullptr, nullptr);
+    return ws_layout(pl->fast_ok ? pl->n_inc : 0, n_px, flags, pl->fast_ok ? sort_temp_bytes(n_px) : 0, pl->cr_step_rows > 0, nullptr, nullptr);
 }
 
 extern "C" int xs_timer_create(xs_timer **out) {
@@ -899,7 +1008,7 @@ extern "C" int xs_invert(const xs_plan *pl, const xs_invert_args *ar, void *stre
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, pl->device);
 
     const size_t sort_bytes = pl->fast_ok ? sort_temp_bytes(n) : 0;  // host-side query of CUB, no launch
-    const size_t need = ws_layout(pl->fast_ok ? pl->n_inc : 0, n, ar->flags, sort_bytes, nullptr, nullptr);
+    const size_t need = ws_layout(pl->fast_ok ? pl->n_inc : 0, n, ar->flags, sort_bytes, pl->cr_step_rows > 0, nullptr, nullptr);
     if (!ar->workspace || ar->workspace_bytes < need) {
         set_error("xs_invert: workspace too small (%zu < %zu)", ar->workspace_bytes, need);
         return XS_E_WORKSPACE;
@@ -909,7 +1018,7 @@ extern "C" int xs_invert(const xs_plan *pl, const xs_invert_args *ar, void *stre
         return XS_E_INVALID;
     }
     Workspace ws;
-    ws_layout(pl->fast_ok ? pl->n_inc : 0, n, ar->flags, sort_bytes, (char *)ar->workspace, &ws);
+    ws_layout(pl->fast_ok ? pl->n_inc : 0, n, ar->flags, sort_bytes, pl->cr_step_rows > 0, (char *)ar->workspace, &ws);
     OutSpec out;
     out.co = ar->out_co;
     out.cr = ar->out_cr;
@@ -949,7 +1058,17 @@ extern "C" int xs_invert(const xs_plan *pl, const xs_invert_args *ar, void *stre
         int64_t grid = ceil_div(warps_needed * 32, 256);
         const int64_t cap = (int64_t)sms * 16;
         if (grid > cap) grid = cap;
-        XS_LAUNCH(k_cross, (int)grid, 256, 0, st, *pl, ra, n, out);
+        // cross-pol only on strictly increasing LUT rows: the step-function kernel settles almost every pixel, k_cross
+        // takes the rest from a list (XS_FLAG_CR_FULL_SCAN keeps the cooperative scan for all of them: tests)
+        const bool step = !ra.s_co && ra.s_cr && pl->cr_step_rows > 0 && !(ar->flags & XS_FLAG_CR_FULL_SCAN) && ws.fallback;
+        if (step) {
+            int64_t g1 = ceil_div(n, 256);
+            if (g1 > (int64_t)sms * 64) g1 = (int64_t)sms * 64;
+            XS_LAUNCH(k_cross_only, (int)g1, 256, 0, st, *pl, ra, n, out, ws.fallback, ws.counters + 4);
+            if (grid > (int64_t)sms * 4) grid = (int64_t)sms * 4;
+            XS_LAUNCH(k_cross, (int)grid, 256, 0, st, *pl, ra, n, out, (const unsigned *)ws.fallback, (const u64 *)(ws.counters + 4));
+        } else
+            XS_LAUNCH(k_cross, (int)grid, 256, 0, st, *pl, ra, n, out, (const unsigned *)nullptr, (const u64 *)nullptr);
     }
     if (ar->counters_dev)
         XS_CUDA(cudaMemcpyAsync(ar->counters_dev, ws.counters, XS_N_COUNTERS * sizeof(u64), cudaMemcpyDeviceToDevice, st));

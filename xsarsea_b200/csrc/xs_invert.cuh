@@ -39,6 +39,12 @@ struct xs_plan {
     // b / cr_vscale[row], b = 0 .. kCrInvBuckets (the last entry is n_wspd_cr): one table look-up replaces most of a bisection
     unsigned short *cr_inv;
     double *cr_vlo, *cr_vscale;
+    // cross-pol-only step function (k_cross_only): on a strictly increasing row the argmin of ((L - s)/dsig)^2 is the number
+    // of midpoints (L[w-1] + L[w])/2, w = 1 .. n_wspd_cr - 1, below s.  cr_step_db[row][w] holds the midpoints in dB,
+    // cr_step_lin[row][w] = 10^(midpoint/10), compared with sigma0 + 1e-15 so that no log10 is taken per pixel (entry 0
+    // of a row is unused); cr_finite bit 2 marks the rows this applies to.
+    double *cr_step_db, *cr_step_lin;
+    int cr_step_rows;  // number of such rows (0: k_cross_only is not launched)
     // uniform grids (np.linspace): a direct index guess replaces the bisection of nearest_bin / of the wspd sign change
     double inc_cr_g0, inc_cr_inv_step, wspd_cr_g0, wspd_cr_inv_step;
     int inc_cr_uniform, wspd_cr_uniform;
@@ -346,13 +352,13 @@ struct Workspace {
     unsigned *val[2];      // [n_px] pixel indices carried by the sort
     void *sort_temp;       // CUB's scratch
     size_t sort_temp_bytes;
-    unsigned *fallback;    // [n_px] pixels for the exhaustive kernel
+    unsigned *fallback;    // [n_px] pixels for the exhaustive kernel; in a cross-pol-only call: the pixels k_cross_only left to k_cross
     PixRec *pix;           // [n_list]
     RefRec *rec;           // [n_list]
     int *idx_tmp;          // [n_px] co-pol argmin when the caller gave no idx_co and the outputs are speed/direction planes
     int64_t n_list;        // n_px + kTilePad * n_inc rounded up to a sort run
 };
-size_t ws_layout(int n_inc, int64_t n_px, unsigned flags, size_t sort_bytes, char *base, Workspace *w);
+size_t ws_layout(int n_inc, int64_t n_px, unsigned flags, size_t sort_bytes, bool cr_list, char *base, Workspace *w);
 
 // ---- outputs ---------------------------------------------------------------------------------------------------------
 // complex128 per pixel (the reference's return type), or -- XS_FLAG_OUT_SPEED_DIR -- two planes [speed | direction] of

@@ -90,7 +90,7 @@ struct ScanSmem {
     unsigned batch_next, batch_end;
 };
 
-template <int KP, int P, int NW, int MB>
+template <int KP, int P, int NW, int MB, bool SC = false>  // SC: scalar FFMA per candidate instead of FFMA2 per pair
 __global__ void __launch_bounds__(NW * 32, MB) k_scan_co(xs_plan pl, Workspace ws, float share_tau) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     using Smem = ScanSmem<KP, P, NW>;
@@ -246,9 +246,15 @@ __global__ void __launch_bounds__(NW * 32, MB) k_scan_co(xs_plan pl, Workspace w
                     for (int p = 0; p < P; ++p) {
 #pragma unroll
                         for (int j = 0; j < KP; ++j) {  // J'' ~ M + (-w/2) g: one FFMA2 per candidate pair
-                            const u64 J = ffma2(nwh, g[p][j], M[j]);
                             float j0, j1;
-                            unpack2(J, j0, j1);
+                            if constexpr (SC) {  // the same two roundings as two scalar FFMA
+                                float g0, g1, M0, M1;
+                                unpack2(g[p][j], g0, g1);
+                                unpack2(M[j], M0, M1);
+                                j0 = __fmaf_rn(rt.x, g0, M0);
+                                j1 = __fmaf_rn(rt.x, g1, M1);
+                            } else
+                                unpack2(ffma2(nwh, g[p][j], M[j]), j0, j1);
                             m[p] = fmin3(m[p], j0, j1);
                         }
                     }
@@ -631,7 +637,14 @@ static int launch_shape(const xs_plan *pl, const RasterArgs &ra, const Workspace
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, pl->device);
     XS_LAUNCH(k_list_prepare, sms * 16, 256, 0, st, *pl, ra, ws, sorted_px, TP);
 
+    static int scalar = -1;  // XS_SCAN_SCALAR: development aid (KP 3, P 8 only)
+    if (scalar < 0) {
+        const char *e = getenv("XS_SCAN_SCALAR");
+        scalar = e ? atoi(e) : 0;
+    }
     auto kern = k_scan_co<KP, P, NW, MB>;
+    if constexpr (KP == 3 && P == 8 && NW == 4 && MB == 4)
+        if (scalar) kern = k_scan_co<KP, P, NW, MB, true>;
     // largest estimated 2 |sigma| Lam for which a warp scans in shared-sigma0 mode (XS_SHARE_BUDGET: development aid; 0 = never)
     static float share_tau = -1.f;
     if (share_tau < 0.f) {
