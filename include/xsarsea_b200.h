@@ -148,6 +148,9 @@ void xs_plan_destroy(xs_plan *plan);
 #define XS_FLAG_DIR_METEO 32u   /* with OUT_SPEED_DIR: direction = (90 - angle + ground_heading) % 360, i.e.
                                    dir_sample_to_meteo (detrend.py:114-130) wrapped to [0, 360) */
 #define XS_FLAG_OUT_F32 64u     /* with OUT_SPEED_DIR: float32 planes */
+#define XS_FLAG_NO_PRUNE 128u   /* co-pol scan: evaluate every candidate of the slab (brute force, what the reference does)
+                                   instead of skipping the 16-row chunks whose rigorous lower bound of the cost exceeds the
+                                   cost of a seed candidate (k_tile_plan); same results, the roofline figure is quoted on it */
 
 /* scan modes */
 #define XS_MODE_FAST 0  /* FP32 FFMA2 scan (k_scan_co) + exact refinement of every candidate inside the error band (k_refine_easy) */
@@ -197,7 +200,8 @@ int xs_invert(const xs_plan *plan, const xs_invert_args *args, void *stream);
  * the stream has reached the end of the call): [0] co-pol tiles, [1] pixels sent to the exhaustive FP64 scan,
  * [2] co-pol pixels settled by the FP32 scan (+ refinement), [3] (lane, chunk) cells re-examined by the refinement,
  * [4] pixels of a cross-pol-only call that the step-function kernel (k_cross_only) left to the general cross-pol pass,
- * [5..7], [9], [10] unused (0),
+ * [5] 16-row chunks the scan CTAs streamed (summed over tiles), [6] chunks the scan warps computed on (summed over the
+ * warps of every tile; without pruning both are tiles x chunks per slab (x warps per tile)), [7], [9], [10] unused (0),
  * [8] tile hand-out cursor, [11] pixels the refinement settled in FP64 (more than one candidate inside the band),
  * [12] pixels with more than two contending lanes, [13] record positions scanned in shared-sigma0 mode. */
 

@@ -380,3 +380,56 @@ def test_cross_pol_only_step_function_kernel(env, dtype):
     assert plan.last_stats()["cross_listed_pixels"] < 0.2 * n
     _, _, _, i2 = plan.invert(d_inc, None, d_s, d_dsig, None, want_idx=True, sigma0_db=True, cr_full_scan=True)
     assert torch.equal(i1, i2)
+
+
+@pytest.mark.parametrize("scene", ["friendly", "hostile"])
+def test_chunk_pruning_equals_brute_force(env, scene):
+    """Exact chunk pruning (k_tile_plan): the scan that skips the chunks whose lower bound exceeds a seed's cost gives the
+    indices of the brute-force scan (XS_FLAG_NO_PRUNE) and of the exhaustive FP64 kernel, bit for bit -- on the benchmark
+    recipe and on the hostile scene -- and it really skips most of the slab."""
+    torch, D, nat, ws, impl = env
+    import bench
+
+    plan = default_plan(ws, impl)
+    inc, s_co, s_cr, anc = bench.synth_scene_device(160, 25000, 5, scene=scene)
+    a, _, ia, _ = plan.invert(inc, s_co, None, 0.1, anc, want_idx=True)
+    st = plan.last_stats()
+    b, _, ib, _ = plan.invert(inc, s_co, None, 0.1, anc, want_idx=True, no_prune=True)
+    st0 = plan.last_stats()
+    c, _, ic, _ = plan.invert(inc, s_co, None, 0.1, anc, want_idx=True, mode=nat.MODE_FP64)
+    assert torch.equal(ia, ib) and torch.equal(ia, ic)
+    bits = lambda z: torch.view_as_real(z).contiguous().view(torch.int64)
+    assert torch.equal(bits(a), bits(b)) and torch.equal(bits(a), bits(c))
+    n_chunks = (499 + 7) // 8 * 8 // 16 + (1 if ((499 + 7) // 8 * 8) % 16 else 0)
+    assert st0["chunks_streamed"] == st0["tiles"] * n_chunks and st0["warp_chunks"] <= 4 * st0["chunks_streamed"]
+    assert st["tiles"] == st0["tiles"] and st["scan_pixels"] == st0["scan_pixels"]
+    assert 4 * st["tiles"] <= st["chunks_streamed"] < 0.6 * st0["chunks_streamed"], (st, st0)
+    assert st["warp_chunks"] < 0.6 * st0["warp_chunks"]
+
+
+def test_chunk_pruning_small_and_ragged_rasters(env):
+    """Sparse bins (tiles whose pixels differ widely in sigma0), a NaN-holding LUT and a coarse LUT with few chunks: pruned
+    == brute force == FP64."""
+    torch, D, nat, ws, impl = env
+    g = torch.Generator(device="cuda").manual_seed(11)
+    f64 = dict(device="cuda", dtype=torch.float64)
+    for (n_w, n_p, w_hi) in ((499, 181, 50.0), (70, 37, 35.0), (130, 73, 80.0)):
+        gi, gw, gp = np.linspace(17, 50, 34), np.linspace(0.2, w_hi, n_w), np.linspace(0, 180, n_p)
+        co = D.lut_to_db(D.lut_build(nat.GMF_IDS["gmf_cmod5n"], gi, gw, gp))
+        plan = D.InversionPlan(co=(co, gi, gw, gp), cr=None)
+        n = 30011
+        inc = 17 + 33 * torch.rand(n, generator=g, **f64)
+        w = 0.5 + 40 * torch.rand(n, generator=g, **f64)
+        p = 360 * torch.rand(n, generator=g, **f64)
+        s = D.gmf_eval(nat.GMF_IDS["gmf_cmod5n"], inc, w, p) * torch.exp(0.5 * torch.randn(n, generator=g, **f64))
+        s[::97] *= 1e4  # far outside the LUT
+        s[5::101] = 0.0
+        anc = torch.polar(60 * torch.rand(n, generator=g, **f64), 6.3 * torch.rand(n, generator=g, **f64))
+        anc[7::89] = 0
+        _, _, ia, _ = plan.invert(inc, s, None, 0.1, anc, want_idx=True)
+        st = plan.last_stats()
+        _, _, ib, _ = plan.invert(inc, s, None, 0.1, anc, want_idx=True, no_prune=True)
+        _, _, ic, _ = plan.invert(inc, s, None, 0.1, anc, want_idx=True, mode=nat.MODE_FP64)
+        assert torch.equal(ia, ib) and torch.equal(ia, ic), (n_w, n_p)
+        assert st["chunks_streamed"] >= 4 * st["tiles"]
+        plan.close()

@@ -284,7 +284,8 @@ class InversionPlan:
 
     def invert(self, inc, sigma0_co=None, sigma0_cr=None, dsig_cr=0.1, ancillary=None, *, sigma0_db=False,
                merge_dual=False, cr_abs=False, mode=nat.MODE_FAST, want_idx=False, out_co=None, out_cr=None,
-               need_co=False, cr_full_scan=False, speed_dir=False, ground_heading=None, out_f32=False, timed=False):
+               need_co=False, cr_full_scan=False, speed_dir=False, ground_heading=None, out_f32=False, timed=False,
+               no_prune=False):
         """Run K1 on device tensors (all the same shape; float64/complex128 or float32/complex64).
 
         Returns (wind_co complex128 | None, wind_cr complex128 (float64 if cr_abs) | None, idx_co, idx_cr).
@@ -319,7 +320,8 @@ class InversionPlan:
             a.dsig_cr_scalar = float(dsig_cr)
         a.dtype = nat.XS_F32 if f32 else nat.XS_F64
         flags = (nat.FLAG_SIGMA0_DB if sigma0_db else 0) | (nat.FLAG_MERGE_DUAL if merge_dual else 0) | (
-            nat.FLAG_CR_ABS if cr_abs else 0) | (nat.FLAG_CR_FULL_SCAN if cr_full_scan else 0)
+            nat.FLAG_CR_ABS if cr_abs else 0) | (nat.FLAG_CR_FULL_SCAN if cr_full_scan else 0) | (
+            nat.FLAG_NO_PRUNE if no_prune else 0)
         if speed_dir:
             flags |= nat.FLAG_OUT_SPEED_DIR | (nat.FLAG_OUT_F32 if out_f32 else 0)
             if ground_heading is not None:
@@ -386,4 +388,4 @@ class InversionPlan:
     def last_stats(self):
         c = self.debug_counters()
         return dict(scan_pixels=c[2], fp64_chunks=c[3], exhaustive_pixels=c[1], tiles=c[0], fp64_pixels=c[11], many_lane_pixels=c[12],
-                    shared_mode_positions=c[13], cross_listed_pixels=c[4])
+                    shared_mode_positions=c[13], cross_listed_pixels=c[4], chunks_streamed=c[5], warp_chunks=c[6])

@@ -19,7 +19,7 @@ CSRC = os.path.join(_HERE, "csrc")
 
 XS_F64, XS_F32 = 0, 1
 FLAG_SIGMA0_DB, FLAG_MERGE_DUAL, FLAG_CR_ABS, FLAG_CR_FULL_SCAN = 1, 2, 4, 8
-FLAG_OUT_SPEED_DIR, FLAG_DIR_METEO, FLAG_OUT_F32 = 16, 32, 64
+FLAG_OUT_SPEED_DIR, FLAG_DIR_METEO, FLAG_OUT_F32, FLAG_NO_PRUNE = 16, 32, 64, 128
 ABI_VERSION = 2
 N_COUNTERS = 16
 MODE_FAST, MODE_FP64 = 0, 1

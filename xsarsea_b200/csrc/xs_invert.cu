@@ -44,6 +44,7 @@ size_t ws_layout(int n_inc, int64_t n_px, unsigned flags, size_t sort_bytes, boo
     char *fb = take(sizeof(unsigned) * (size_t)((n_inc > 0 || cr_list) ? n_px : 0));  // also k_cross_only's slow list
     char *pr = take(sizeof(PixRec) * (size_t)n_list);
     char *rr = take(sizeof(RefRec) * (size_t)n_list);
+    char *tp = take(sizeof(unsigned) * kPlanWords * (size_t)(n_list / kMinTilePx + 1));
     char *it = take((flags & XS_FLAG_OUT_SPEED_DIR) ? sizeof(int) * (size_t)n_px : 0);
     if (w) {
         w->counters = (u64 *)c;
@@ -60,6 +61,7 @@ size_t ws_layout(int n_inc, int64_t n_px, unsigned flags, size_t sort_bytes, boo
         w->fallback = (unsigned *)fb;
         w->pix = (PixRec *)pr;
         w->rec = (RefRec *)rr;
+        w->tile_plan = (unsigned *)tp;
         w->idx_tmp = (int *)it;
         w->n_list = n_list;
     }
@@ -107,6 +109,46 @@ __global__ void k_build_rowtab(xs_plan pl) {
         v = make_float2((float)(-0.5 * w), (float)(0.25 * w * w));
     }
     pl.rowtab[i] = v;
+}
+// value range of every chunk of every slab (all phi nodes, the chunk's valid rows) and the |wspd| range of every chunk:
+// what k_tile_plan's lower bounds are made of.  One warp per (bin, chunk).
+__global__ void k_build_chunk_ranges(xs_plan pl) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (warp >= (int64_t)pl.n_inc * pl.n_chunks) return;
+    const int bin = (int)(warp / pl.n_chunks), c = (int)(warp % pl.n_chunks);
+    const int r0 = c * kChunkRows, r1 = min(r0 + kChunkRows, pl.n_wspd);
+    double lo = CUDART_INF, hi = -CUDART_INF, wlo = CUDART_INF, whi = -CUDART_INF;
+    bool finite = true;
+    const double *slab = pl.co_lut + (int64_t)bin * pl.n_wspd * pl.n_phi;
+    for (int i = r0 * pl.n_phi + lane; i < r1 * pl.n_phi; i += 32) {
+        const double v = slab[i];
+        finite &= isfinite(v);
+        lo = fmin(lo, v);
+        hi = fmax(hi, v);
+    }
+    for (int r = r0 + lane; r < r1; r += 32) {
+        const double w = fabs(pl.wspd_grid[r]);
+        wlo = fmin(wlo, w);
+        whi = fmax(whi, w);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+        wlo = fmin(wlo, __shfl_xor_sync(0xffffffffu, wlo, o));
+        whi = fmax(whi, __shfl_xor_sync(0xffffffffu, whi, o));
+    }
+    finite = __all_sync(0xffffffffu, finite);
+    if (lane == 0) {
+        // a chunk with a non-finite value (or without valid rows) gives no sigma0 bound
+        pl.chunk_lo[warp] = (finite && r1 > r0) ? lo : -CUDART_INF;
+        pl.chunk_hi[warp] = (finite && r1 > r0) ? hi : CUDART_INF;
+        if (bin == 0) {
+            pl.chunk_wlo[c] = r1 > r0 ? wlo : 0.0;
+            pl.chunk_whi[c] = r1 > r0 ? whi : CUDART_INF;
+        }
+    }
 }
 // plans without a scan image still need the first-NaN table
 __global__ void k_find_first_nan(xs_plan pl) {
@@ -780,6 +822,10 @@ extern "C" void xs_plan_destroy(xs_plan *pl) {
     cudaFree(pl->first_nan);
     cudaFree(pl->slab_absmax);
     cudaFree(pl->slab_range);
+    cudaFree(pl->chunk_lo);
+    cudaFree(pl->chunk_hi);
+    cudaFree(pl->chunk_wlo);
+    cudaFree(pl->chunk_whi);
     cudaFree(pl->inc_cr_grid);
     cudaFree(pl->wspd_cr_grid);
     cudaFree(pl->wspd_cr_half);
@@ -859,6 +905,13 @@ extern "C" int xs_plan_create(const xs_plan_desc *d, void *stream, xs_plan **out
             if ((rc = xs::check(cudaMalloc(&pl->rowtab, sizeof(float2) * (size_t)pl->n_wspd_pad), "cudaMalloc")) != XS_OK) return fail(rc);
             if ((rc = xs::check(cudaMalloc(&pl->slab_absmax, sizeof(float) * (size_t)d->n_inc), "cudaMalloc")) != XS_OK) return fail(rc);
             if ((rc = xs::check(cudaMalloc(&pl->slab_range, sizeof(int) * 2 * (size_t)d->n_inc), "cudaMalloc")) != XS_OK) return fail(rc);
+            pl->n_chunks = (pl->n_wspd_pad + kChunkRows - 1) / kChunkRows;
+            while ((pl->n_chunks + (1 << pl->mask_sh) - 1) >> pl->mask_sh > 32) ++pl->mask_sh;
+            const size_t n_cr = (size_t)d->n_inc * pl->n_chunks;
+            if ((rc = xs::check(cudaMalloc(&pl->chunk_lo, sizeof(double) * n_cr), "cudaMalloc")) != XS_OK) return fail(rc);
+            if ((rc = xs::check(cudaMalloc(&pl->chunk_hi, sizeof(double) * n_cr), "cudaMalloc")) != XS_OK) return fail(rc);
+            if ((rc = xs::check(cudaMalloc(&pl->chunk_wlo, sizeof(double) * (size_t)pl->n_chunks), "cudaMalloc")) != XS_OK) return fail(rc);
+            if ((rc = xs::check(cudaMalloc(&pl->chunk_whi, sizeof(double) * (size_t)pl->n_chunks), "cudaMalloc")) != XS_OK) return fail(rc);
         }
     }
     if (has_cr) {
@@ -913,6 +966,7 @@ extern "C" int xs_plan_create(const xs_plan_desc *d, void *stream, xs_plan **out
             XS_LAUNCH(k_init_slab_range, (int)ceil_div(pl->n_inc, 256), 256, 0, st, *pl);
             XS_LAUNCH(k_build_scan, kNumSMs * 8, 256, 0, st, *pl);
             XS_LAUNCH(k_build_rowtab, (int)ceil_div(pl->n_wspd_pad, 256), 256, 0, st, *pl);
+            XS_LAUNCH(k_build_chunk_ranges, (int)ceil_div((int64_t)pl->n_inc * pl->n_chunks * 32, 256), 256, 0, st, *pl);
         } else {
             XS_LAUNCH(k_find_first_nan, kNumSMs * 8, 256, 0, st, *pl);
         }

@@ -22,6 +22,11 @@ struct xs_plan {
     int kp;             // float2 pairs per lane: nph_pad = 64*kp
     int nph_pad, n_wspd_pad;
     int fast_ok;        // the FP32 scan can be used for this plan
+    // exact chunk pruning (k_tile_plan): value range of every 16-row chunk of every slab over all phi nodes (FP64 dB;
+    // -inf / +inf when the chunk holds a non-finite value) and the range of |wspd| over the chunk's rows
+    int n_chunks, mask_sh;  // chunks per slab; a bit of the 32-bit chunk masks covers 2^mask_sh chunks
+    double *chunk_lo, *chunk_hi;    // [n_inc][n_chunks]
+    double *chunk_wlo, *chunk_whi;  // [n_chunks]
     int inc_sorted;     // inc_grid strictly ascending (binary search allowed)
     // ---- cross-pol model (n_inc_cr == 0 when absent) ----
     int n_inc_cr, n_wspd_cr;
@@ -66,6 +71,8 @@ constexpr int kStages = 4;         // shared-memory ring depth of the scan (4 x 
 constexpr int kCrInvBuckets = 1024;
 constexpr float kBandMargin = 0.5f;  // every accepted error band is narrower than this (2 E < kBandMargin)
 constexpr int kTilePad = 64;       // upper bound of the pixels per scan tile (the bin segments of the pixel list are padded to tiles)
+constexpr int kPlanWords = 8;      // 32-byte scan plan of a tile: [0] chunks the CTA streams, [1 + w] chunks warp w computes on
+constexpr int kMinTilePx = 16;     // smallest scan tile (sizes the tile-plan array)
 constexpr int kMaxIncBins = 6144;  // bins whose two shared-memory histograms (k_bin_scatter) fit the default 48 KB
 
 // raster element access: XS_F64 / XS_F32, promoted to double on load
@@ -355,6 +362,7 @@ struct Workspace {
     unsigned *fallback;    // [n_px] pixels for the exhaustive kernel; in a cross-pol-only call: the pixels k_cross_only left to k_cross
     PixRec *pix;           // [n_list]
     RefRec *rec;           // [n_list]
+    unsigned *tile_plan;   // [tiles][kPlanWords] chunk masks of every tile (k_tile_plan)
     int *idx_tmp;          // [n_px] co-pol argmin when the caller gave no idx_co and the outputs are speed/direction planes
     int64_t n_list;        // n_px + kTilePad * n_inc rounded up to a sort run
 };

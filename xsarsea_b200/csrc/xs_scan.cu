@@ -77,12 +77,161 @@ __global__ void __launch_bounds__(256) k_list_prepare(xs_plan pl, RasterArgs a, 
     }
 }
 
+// ---- exact chunk pruning ---------------------------------------------------------------------------------------------
+// J(w, phi) = Jwind + Jsig is a sum of two non-negative terms, and each has a lower bound that holds for every candidate
+// of a 16-row chunk of the slab:
+//   Jsig  >= (dist(s, [lo_c, hi_c]) / dsig_co)^2    [lo_c, hi_c] = value range of the chunk over all phi nodes (plan table)
+//   Jwind >= (dist(A, [wlo_c, whi_c]) / 2)^2        A = |ancillary|:  (w cos - a)^2 + (w sin - b)^2 >= (|w| - A)^2
+// With U = the reference's FP64 cost of ANY candidate (the seed), a chunk whose bound exceeds U cannot hold the argmin (nor a
+// tie with it), so the scan may skip it: the argmin c* is scanned, and the error-band argument of k_scan_co --
+// J32(c*) <= J(c*) + E <= J(c^) + E <= m32 + 2E with c^ the scanned FP32 minimum -- needs nothing else.  The comparison
+// keeps a margin of 1e-6 relative + 1e-6 (1 + A^2 + W^2) absolute, ten orders of magnitude above the FP64 rounding of
+// either side, so no rounding argument is needed.  The pixels of a tile are neighbours in sigma0 order and share the
+// slab, so they keep nearly the same chunks: the CTA streams the union (word 0 of the tile's plan) and every warp
+// computes only on the chunks its own pixels keep (words 1 ..).
+// Seed: on up to 64 phi nodes (constant stride) the row where the slab crosses the tile's median sigma0 (bisection; any
+// row is a valid seed, monotonicity only makes it a good one); every pixel takes the cheapest of them by an FP32 estimate
+// and evaluates that one with the reference's FP64 operations.
+constexpr int kSeedMax = 64;
+
+// chunks covered by a mask (a bit covers 2^sh chunks, the last bit possibly fewer)
+__device__ __forceinline__ int mask_chunks(unsigned mask, int sh, int n_chunks) {
+    if (sh == 0) return __popc(mask);
+    int n = 0;
+    while (mask) {
+        const int b = __ffs(mask) - 1;
+        mask &= mask - 1;
+        n += min(1 << sh, n_chunks - (b << sh));
+    }
+    return n;
+}
+// smallest chunk > c whose mask bit is set, or n_chunks
+__device__ __forceinline__ int next_chunk(unsigned mask, int c, int sh, int n_chunks) {
+    const int c1 = c + 1;
+    if (c1 >= n_chunks) return n_chunks;
+    const int b = c1 >> sh;
+    if ((mask >> b) & 1u) return c1;
+    const unsigned rest = b >= 31 ? 0u : (mask >> (b + 1)) << (b + 1);
+    if (!rest) return n_chunks;
+    const int c2 = (__ffs(rest) - 1) << sh;
+    return c2 < n_chunks ? c2 : n_chunks;
+}
+
+__global__ void __launch_bounds__(256) k_tile_plan(xs_plan pl, Workspace ws, int tile_px, int nw, int min_items, int prune) {
+    __shared__ float4 seed_s[8][kSeedMax];  // {w cos phi, w sin phi, L / dsig_co, flat index} of the warp's seeds
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_gw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t n_tiles = (int64_t)ws.counters[0];
+    const int sh = pl.mask_sh, n_chunks = pl.n_chunks;
+    const int nb = (n_chunks + (1 << sh) - 1) >> sh;
+    const unsigned all = nb >= 32 ? 0xffffffffu : ((1u << nb) - 1u);
+    const int P = tile_px / nw;
+    const unsigned pmask = P >= 32 ? 0xffffffffu : ((1u << P) - 1u);
+    const int stride = (pl.n_phi + kSeedMax - 1) / kSeedMax, n_seed = (pl.n_phi + stride - 1) / stride;
+    const double inv_d = 1.0 / fabs(pl.dsig_co);
+    unsigned n_items = 0, n_warp_items = 0;
+    for (int64_t t = gw; t < n_tiles; t += n_gw) {
+        unsigned uni = all, wm[4] = {all, all, all, all};
+        PixRec rec;
+        rec.qa = rec.qb = rec.s = 0.0;
+        rec.bin = 0;
+        rec.state = 0;
+        if (lane < tile_px) rec = ws.pix[t * tile_px + lane];
+        const bool on = rec.state == 1;
+        const unsigned on_mask = __ballot_sync(0xffffffffu, on);
+        const int bin = __shfl_sync(0xffffffffu, (int)rec.bin, 0);  // position 0 of a tile is never padding
+        if (prune && on_mask) {
+            const double s_mid = __shfl_sync(0xffffffffu, rec.s, __fns(on_mask, 0, __popc(on_mask) / 2 + 1));
+            const double *slab = pl.co_lut + (size_t)bin * pl.n_wspd * pl.n_phi;
+            for (int j = lane; j < n_seed; j += 32) {
+                const int ip = j * stride;
+                int lo = 0, hi = pl.n_wspd;  // first row whose value reaches s_mid
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (slab[(size_t)mid * pl.n_phi + ip] < s_mid)
+                        lo = mid + 1;
+                    else
+                        hi = mid;
+                }
+                int r = min(lo, pl.n_wspd - 1);
+                if (lo > 0 && lo < pl.n_wspd &&
+                    fabs(slab[(size_t)(lo - 1) * pl.n_phi + ip] - s_mid) <= fabs(slab[(size_t)lo * pl.n_phi + ip] - s_mid))
+                    r = lo - 1;
+                const double w = pl.wspd_grid[r];
+                seed_s[wid][j] = make_float4((float)(w * pl.cos_phi[ip]), (float)(w * pl.sin_phi[ip]),
+                                             (float)(slab[(size_t)r * pl.n_phi + ip] * inv_d), __int_as_float(r * pl.n_phi + ip));
+            }
+            __syncwarp();
+            float best = CUDART_INF_F;
+            int bflat = __float_as_int(seed_s[wid][0].w);
+            {
+                const float fa = (float)rec.qa, fb = (float)rec.qb, fs = (float)(rec.s * inv_d);
+                for (int j = 0; j < n_seed; ++j) {
+                    const float4 v = seed_s[wid][j];
+                    const float ta = 0.5f * (v.x - fa), tz = 0.5f * (v.y - fb), ts = v.z - fs;
+                    const float J = ta * ta + tz * tz + ts * ts;
+                    if (J < best) {
+                        best = J;
+                        bflat = __float_as_int(v.w);
+                    }
+                }
+            }
+            __syncwarp();
+            double thr = CUDART_INF;
+            const double A = hypot(rec.qa, rec.qb);
+            if (on) {
+                const int iw = bflat / pl.n_phi, ip = bflat - iw * pl.n_phi;
+                const double U = exact_cost_co(pl.wspd_grid[iw], pl.cos_phi[ip], pl.sin_phi[ip], slab[bflat], rec.qa, rec.qb, rec.s, pl.dsig_co);
+                thr = U * (1.0 + 1e-6) + 1e-6 * (1.0 + A * A + pl.w_absmax * pl.w_absmax);
+            }
+            uni = 0u;
+            wm[0] = wm[1] = wm[2] = wm[3] = 0u;
+            const double *clo = pl.chunk_lo + (size_t)bin * n_chunks, *chi = pl.chunk_hi + (size_t)bin * n_chunks;
+            for (int c = 0; c < n_chunks; ++c) {
+                const double ds = fmax(fmax(clo[c] - rec.s, rec.s - chi[c]), 0.0) * inv_d;
+                const double dw = fmax(fmax(pl.chunk_wlo[c] - A, A - pl.chunk_whi[c]), 0.0) * 0.5;
+                const double lb = (ds * ds + dw * dw) * (1.0 - 1e-9);
+                const unsigned keep = __ballot_sync(0xffffffffu, on && !(lb > thr));  // NaN / inf thresholds keep everything
+                const unsigned bit = 1u << (c >> sh);
+                if (keep) uni |= bit;
+#pragma unroll
+                for (int w = 0; w < 4; ++w)
+                    if (w < nw && ((keep >> (w * P)) & pmask)) wm[w] |= bit;
+            }
+            // the scan's ring looks kStages chunks ahead, at most into the next tile
+            while (mask_chunks(uni, sh, n_chunks) < min_items) {
+                unsigned ext = ((uni << 1) | (uni >> 1)) & ~uni & all;
+                if (!ext) ext = ~uni & all;
+                if (!ext) break;
+                uni |= ext & (0u - ext);
+            }
+        } else if (prune && !on_mask) {
+            wm[0] = wm[1] = wm[2] = wm[3] = 0u;  // nothing to scan in this tile (NaN slab / exhaustive pixels only)
+            uni = 0u;
+            for (int c = 0, k = 0; c < n_chunks && k < min_items; ++c, ++k) uni |= 1u << (c >> sh);
+        }
+        if (lane == 0) {
+            uint4 *dst = reinterpret_cast<uint4 *>(ws.tile_plan + (size_t)t * kPlanWords);
+            dst[0] = make_uint4(uni, wm[0], wm[1], wm[2]);
+            dst[1] = make_uint4(wm[3], 0u, 0u, 0u);
+            n_items += (unsigned)mask_chunks(uni, sh, n_chunks);
+            for (int w = 0; w < nw && w < 4; ++w) n_warp_items += (unsigned)mask_chunks(wm[w] & uni, sh, n_chunks);
+        }
+    }
+    if (lane == 0) {
+        if (n_items) atomicAdd(&ws.counters[5], (u64)n_items);
+        if (n_warp_items) atomicAdd(&ws.counters[6], (u64)n_warp_items);
+    }
+}
+
 // ---- the FP32 scan ----------------------------------------------------------------------------------------------------
 template <int KP, int P, int NW>
 struct ScanSmem {
     static constexpr int kRowFloats = 64 * KP;
     alignas(128) float ring[kStages][kChunkRows * kRowFloats];
     alignas(16) PixRec pix[2][NW * P];
+    alignas(16) unsigned plan[2][kPlanWords];  // chunk masks of the tile (k_tile_plan)
     alignas(8) uint64_t full[kStages];    // a chunk has landed in the stage
     uint64_t pix_full[2];                 // the tile's records (or the end-of-work mark) have landed
     unsigned done[kStages];               // warps that have finished with the stage's chunk (monotonic)
@@ -99,13 +248,14 @@ __global__ void __launch_bounds__(NW * 32, MB) k_scan_co(xs_plan pl, Workspace w
     constexpr int TP = NW * P;                                               // list positions per tile
     constexpr int NS = kStages;
     constexpr uint32_t kPixBytes = TP * sizeof(PixRec);
+    constexpr uint32_t kPlanBytes = kPlanWords * sizeof(unsigned);
+    static_assert(NW <= 4, "a tile plan holds four warp masks");
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned n_tiles = (unsigned)ws.counters[0];
-    const int n_chunks = (pl.n_wspd_pad + kChunkRows - 1) / kChunkRows;  // >= NS (plan creation checks); the last may be shorter
+    const int n_chunks = pl.n_chunks;  // >= NS (plan creation checks); the last may be shorter
     const size_t slab_floats = (size_t)pl.n_wspd_pad * Smem::kRowFloats;
-    int mask_sh = 0;  // chunks per bit of the chunk masks: 2^mask_sh (32 bits cover the slab)
-    while ((n_chunks + (1 << mask_sh) - 1) >> mask_sh > 32) ++mask_sh;
+    const int mask_sh = pl.mask_sh;  // chunks per bit of the chunk masks: 2^mask_sh (32 bits cover the slab)
 
     // one chunk of a slab into its ring stage
     auto load_chunk = [&](int bin, int c, int stage) {
@@ -127,8 +277,9 @@ __global__ void __launch_bounds__(NW * 32, MB) k_scan_co(xs_plan pl, Workspace w
         sm.tile_of[buf] = t;
         if (t != kTileEnd) {
             fence_proxy_async();  // the buffer's previous records were read through the generic proxy
-            mbar_expect_tx(&sm.pix_full[buf], kPixBytes);
+            mbar_expect_tx(&sm.pix_full[buf], kPixBytes + kPlanBytes);
             bulk_g2s(sm.pix[buf], ws.pix + (size_t)t * TP, kPixBytes, &sm.pix_full[buf]);
+            bulk_g2s(sm.plan[buf], ws.tile_plan + (size_t)t * kPlanWords, kPlanBytes, &sm.pix_full[buf]);
         } else
             mbar_arrive(&sm.pix_full[buf]);
     };
@@ -145,12 +296,16 @@ __global__ void __launch_bounds__(NW * 32, MB) k_scan_co(xs_plan pl, Workspace w
     }
     for (int i = threadIdx.x; i < pl.n_wspd_pad; i += blockDim.x) rowtab_s[i] = pl.rowtab[i];
     __syncthreads();
-    if (threadIdx.x == 0) {  // first tile and the first NS chunks of its slab
+    if (threadIdx.x == 0) {  // first tile and the first NS chunks of its plan (every plan lists at least NS)
         fetch_tile(0);
         if (sm.tile_of[0] != kTileEnd) {
             mbar_wait(&sm.pix_full[0], 0);
             const int bin0 = sm.pix[0][0].bin;
-            for (int c = 0; c < NS; ++c) load_chunk(bin0, c, c);
+            const unsigned mk0 = sm.plan[0][0];
+            for (int i = 0, c = -1; i < NS; ++i) {
+                c = next_chunk(mk0, c, mask_sh, n_chunks);
+                load_chunk(bin0, c, i);
+            }
         }
     }
 
@@ -226,10 +381,13 @@ __global__ void __launch_bounds__(NW * 32, MB) k_scan_co(xs_plan pl, Workspace w
         }
         const u64 ncs2 = pack2(-cs, -cs);
 
-        // ---- the slab, 16 wspd rows at a time ----
-        for (int c = 0; c < n_chunks; ++c) {
+        // ---- the chunks of the tile's plan, 16 wspd rows at a time ----
+        const unsigned tmask = sm.plan[b][0];
+        const int c_first = next_chunk(tmask, -1, mask_sh, n_chunks);
+        for (int c = c_first; c < n_chunks; c = next_chunk(tmask, c, mask_sh, n_chunks)) {
             mbar_wait(&sm.full[stage], phase);
-            if (shared) {
+            const bool mine_on = (sm.plan[b][1 + warp] >> (c >> mask_sh)) & 1u;  // one of this warp's pixels keeps the chunk
+            if (mine_on && shared) {
                 const u64 *rows = reinterpret_cast<const u64 *>(sm.ring[stage]);
                 const int rows_here = min(kChunkRows, pl.n_wspd_pad - c * kChunkRows);
 #pragma unroll 2
@@ -259,7 +417,7 @@ __global__ void __launch_bounds__(NW * 32, MB) k_scan_co(xs_plan pl, Workspace w
                         }
                     }
                 }
-            } else if (any) {
+            } else if (mine_on && any) {
                 const u64 *rows = reinterpret_cast<const u64 *>(sm.ring[stage]);
                 const int rows_here = min(kChunkRows, pl.n_wspd_pad - c * kChunkRows);  // even (n_wspd_pad is a multiple of 8)
 #pragma unroll 2
@@ -294,14 +452,23 @@ __global__ void __launch_bounds__(NW * 32, MB) k_scan_co(xs_plan pl, Workspace w
                 const unsigned old = atom_add_shared(&sm.done[stage], 1u);
                 if (old % NW == NW - 1) {
                     __threadfence_block();  // the other warps' arrivals (and what they wrote before them) are visible
-                    if (c == 0) fetch_tile(b ^ 1);
-                    int c2 = c + NS, bin2 = bin;
+                    if (c == c_first) fetch_tile(b ^ 1);
+                    // the chunk NS places ahead in the CTA's stream: of this tile's plan, or -- every plan lists at least
+                    // NS chunks -- of the next tile's
+                    int c2 = c, bin2 = bin;
+                    unsigned mk = tmask;
                     bool ok = true;
-                    if (c2 >= n_chunks) {  // belongs to the next tile
-                        c2 -= n_chunks;
-                        mbar_wait(&sm.pix_full[b ^ 1], ((u + 1) >> 1) & 1);
-                        ok = sm.tile_of[b ^ 1] != kTileEnd;
-                        if (ok) bin2 = sm.pix[b ^ 1][0].bin;
+                    for (int i = 0; i < NS && ok; ++i) {
+                        c2 = next_chunk(mk, c2, mask_sh, n_chunks);
+                        if (c2 >= n_chunks) {
+                            mbar_wait(&sm.pix_full[b ^ 1], ((u + 1) >> 1) & 1);
+                            ok = sm.tile_of[b ^ 1] != kTileEnd;
+                            if (ok) {
+                                bin2 = sm.pix[b ^ 1][0].bin;
+                                mk = sm.plan[b ^ 1][0];
+                                c2 = next_chunk(mk, -1, mask_sh, n_chunks);
+                            }
+                        }
                     }
                     if (ok) {
                         fence_proxy_async();
@@ -413,9 +580,7 @@ __global__ void __launch_bounds__(256, 3) k_refine_easy(xs_plan pl, Workspace ws
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int64_t n_pos = (int64_t)ws.counters[0] * tile_px;
     static_assert(kChunkRows % G == 0, "whole rows per lane of a group");
-    const int n_chunks = (pl.n_wspd_pad + kChunkRows - 1) / kChunkRows;
-    int mask_sh = 0;
-    while ((n_chunks + (1 << mask_sh) - 1) >> mask_sh > 32) ++mask_sh;
+    const int n_chunks = pl.n_chunks, mask_sh = pl.mask_sh;
     unsigned n_settled = 0, n_cells = 0, n_fp64 = 0, n_many = 0;
     for (int64_t e0 = warp * PW; e0 < n_pos; e0 += n_warps * PW) {
         const int64_t e = e0 + grp;
@@ -619,7 +784,6 @@ static Shape scan_shape(int kp) {
         if (ep == 8 && em == 3) s = {8, 4, 3};
         if (ep == 7 && em == 4) s = {7, 4, 4};
         if (ep == 6 && em == 4) s = {6, 4, 4};
-        if (ep == 8 && em == 2) s = {8, 8, 2};  // 8 warps per CTA: a tile of 64 pixels shares one ring (half the L2 -> SM traffic)
     }
     return s;
 }
@@ -636,6 +800,12 @@ static int launch_shape(const xs_plan *pl, const RasterArgs &ra, const Workspace
     int sms = kNumSMs;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, pl->device);
     XS_LAUNCH(k_list_prepare, sms * 16, 256, 0, st, *pl, ra, ws, sorted_px, TP);
+    static int no_prune = -1;  // XS_NO_PRUNE: development aid (same as XS_FLAG_NO_PRUNE on every call)
+    if (no_prune < 0) {
+        const char *e = getenv("XS_NO_PRUNE");
+        no_prune = e ? atoi(e) : 0;
+    }
+    XS_LAUNCH(k_tile_plan, sms * 16, 256, 0, st, *pl, ws, TP, NW, kStages, (ra.flags & XS_FLAG_NO_PRUNE) || no_prune ? 0 : 1);
 
     static int scalar = -1;  // XS_SCAN_SCALAR: development aid (KP 3, P 8 only)
     if (scalar < 0) {
@@ -695,7 +865,6 @@ int launch_scan_pipeline(const xs_plan *pl, const RasterArgs &ra, const Workspac
     XS_SHAPE(3, 8, 3);
     XS_SHAPE(3, 7, 4);
     XS_SHAPE(3, 6, 4);
-    XS_SHAPE_NW(3, 8, 8, 2);
     XS_SHAPE(4, 4, 3);
     XS_SHAPE(6, 4, 2);
 #undef XS_SHAPE
