@@ -317,6 +317,27 @@ def wind_diff(got, want, tie=None):
                 max_dspeed=float(dspd.max()) if dspd.size else 0.0, max_ddir_deg=float(ddir.max()) if ddir.size else 0.0)
 
 
+def evaluated(stats, n_phi=181, rows=16, px_per_warp=8):
+    """Candidates the scan really evaluated per scanned pixel (padding rows of the last chunk included): every warp-chunk is
+    16 wspd rows x n_phi nodes for the warp's 8 pixels."""
+    return stats["warp_chunks"] * rows * n_phi * px_per_warp / max(stats["scan_pixels"], 1)
+
+
+def scan_roof(stats, scan_ms, peak_tflops, peak_src):
+    """FP32 roofline of one k_scan_co launch with exact chunk pruning: the brute-force-equivalent figure (8 flop x every
+    candidate of the slab, what the reference evaluates) AND the figure on the candidates the kernel really evaluated."""
+    px = stats["scan_pixels"]
+    ev = evaluated(stats)
+    eq = FLOP_CO * px / (scan_ms * 1e-3) / 1e12
+    ex = 8 * ev * px / (scan_ms * 1e-3) / 1e12
+    return {"bound": "fp32 cuda-core (FMA pipe)", "kernel": "k_scan_co (pruned)", "peak": peak_tflops, "unit": "TFLOP/s",
+            "peak_source": peak_src, "achieved": ex, "frac": ex / peak_tflops,
+            "accounting": "8 flop x the candidates the pruned scan evaluated (candidates_evaluated_per_px)",
+            "candidates_evaluated_per_px": ev, "candidates_per_px_reference": FLOP_CO / 8,
+            "evaluated_fraction": ev / (FLOP_CO / 8), "chunks_streamed_per_tile": stats["chunks_streamed"] / max(stats["tiles"], 1),
+            "brute_force_equivalent_tflops": eq, "brute_force_equivalent_frac": eq / peak_tflops, "scan_ms": scan_ms}
+
+
 def run_aux(args, plan, model, peak_tflops, hbm_gbs, hbm_src):
     """The other BASELINE.json configs, a hostile scene and the F2 epilogue, each with its own roofline (N = 1 only)."""
     import torch
@@ -353,10 +374,15 @@ def run_aux(args, plan, model, peak_tflops, hbm_gbs, hbm_src):
     s_co = D.gmf_eval(nat.GMF_IDS["gmf_cmod5n"], inc, w, p) * torch.exp(0.05 * torch.randn(H, W, generator=g, **f64))
     anc = torch.polar((w + 2 * torch.randn(H, W, generator=g, **f64)).abs(), torch.deg2rad(p + 20 * torch.randn(H, W, generator=g, **f64)))
     oc, ox = torch.empty_like(anc), torch.empty_like(anc)
-    best, mean = timeit(lambda: plan_c.invert(inc, s_co, None, 0.1, anc, out_co=oc, out_cr=ox))
+    best0, _ = timeit(lambda: plan_c.invert(inc, s_co, None, 0.1, anc, out_co=oc, out_cr=ox, no_prune=True))
+    best, mean = timeit(lambda: plan_c.invert(inc, s_co, None, 0.1, anc, out_co=oc, out_cr=ox, timed=True))
+    st = plan_c.last_stats()
     aux["config1_copol_1000x1000"] = dict(value=H * W / (best * 1e-3), unit="px/s", ms=best, ms_mean=mean,
-                                          roofline=fp32_roof(FLOP_CO, H * W, best), stats=plan_c.last_stats(),
-                                          note="1 Mpx is 53 tiles per CTA: launch, binning and the kernel's tail are a visible share")
+                                          roofline=dict(fp32_roof(FLOP_CO, H * W, best0), variant="brute force (XS_FLAG_NO_PRUNE), whole call",
+                                                        ms=best0, pruned=scan_roof(st, plan_c.last_scan_ms()[0], peak_tflops, fp32_src)),
+                                          stats=st,
+                                          note="1 Mpx is 53 tiles per CTA: launch, sort and the kernel's tail are a visible share; "
+                                               "`value` is the shipped (pruned) call, roofline.frac the brute-force call")
     plan_c.close()
     del inc, w, p, s_co, anc, oc, ox
 
@@ -413,7 +439,7 @@ def run_aux(args, plan, model, peak_tflops, hbm_gbs, hbm_src):
     st = plan.last_stats()
     aux["config5_ew_scene_dualpol_dsig_raster"] = dict(
         value=H * W / (best * 1e-3), unit="px/s", ms=best, ms_mean=mean, stats=st,
-        roofline=dict(fp32_roof(FLOP_CO, st["scan_pixels"], scan_ms), kernel="k_scan_co", scan_ms=scan_ms, refine_ms=refine_ms))
+        roofline=dict(scan_roof(st, scan_ms, peak_tflops, fp32_src), refine_ms=refine_ms))
     best, mean = timeit(lambda: xsarsea_b200.sigma0_detrend(s_co, inc, model="gmf_cmod5n"), warm=5, reps=5, inner=5)
     aux["config5_sigma0_detrend_10000x10400"] = dict(value=H * W / (best * 1e-3), unit="px/s", ms=best, ms_mean=mean,
                                                      roofline=hbm_roof(16, H * W, best, "sigma0 in + detrended sigma0 out; public API call incl. the GMF profile"))
@@ -440,7 +466,8 @@ def run_aux(args, plan, model, peak_tflops, hbm_gbs, hbm_src):
                          co_px_per_s=n_co / (best * 1e-3), refined_cells_per_px=st["fp64_chunks"] / n_co,
                          fp64_pixels_frac=st["fp64_pixels"] / n_co, exhaustive_pixels=st["exhaustive_pixels"],
                          many_lane_pixels_frac=st["many_lane_pixels"] / n_co, shared_mode_frac=st["shared_mode_positions"] / n_co,
-                         scan_ms=sm, refine_ms=rm)
+                         scan_ms=sm, refine_ms=rm, candidates_evaluated_per_px=evaluated(st),
+                         chunks_streamed_per_tile=st["chunks_streamed"] / max(st["tiles"], 1))
         del inc, s_co, s_cr, anc
     res["hostile_over_friendly_px_rate"] = res["hostile"]["value"] / res["friendly"]["value"]
     res["hostile_over_friendly_co_px_rate"] = res["hostile"]["co_px_per_s"] / res["friendly"]["co_px_per_s"]
@@ -558,15 +585,39 @@ def main():
     # the scan kernel does the co-pol candidates of the pixels it scans (NaN pixels are never listed; the cross-pol
     # candidates belong to k_cross): 8 flop x 499 x 181 per scanned pixel
     scan_px = stats["scan_pixels"]
+    pruned = scan_roof(stats, scan_avg_ms, pk["measured_tflops"], "xs_bench_fp32_peak: register-resident FFMA2 loop measured in this run")
+    pruned.update(refine_ms=refine_avg_ms, share_of_step=scan_avg_ms / (ms / args.steps))
+    # The roofline fraction is quoted on the BRUTE-FORCE launch of the same kernel (XS_FLAG_NO_PRUNE: every candidate of the
+    # slab, what the reference evaluates), timed here on the same scene; `value` is the shipped call, which skips the chunks
+    # that provably cannot hold the argmin.
+    bf_steps = max(1, min(args.steps, 2))
+    plan.invert(inc, s_co, s_cr, 0.1, anc, merge_dual=True, out_co=out_co, out_cr=out_cr, no_prune=True)
+    barrier()
+    b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    bf_scan, bf_refine = [], []
+    b0.record()
+    for _ in range(bf_steps):
+        plan.invert(inc, s_co, s_cr, 0.1, anc, merge_dual=True, out_co=out_co, out_cr=out_cr, timed=True, no_prune=True)
+        a, b = plan.last_scan_ms()
+        bf_scan.append(a)
+        bf_refine.append(b)
+    b1.record()
+    barrier()
+    bf_ms = max_over_ranks(b0.elapsed_time(b1)) / bf_steps
+    bf_stats = plan.last_stats()
+    scan_avg_ms, refine_avg_ms = float(np.mean(bf_scan)), float(np.mean(bf_refine))
     achieved = FLOP_CO * scan_px / (scan_avg_ms * 1e-3) / 1e12
     prof = profiled_counters()
     roofline = {"bound": "fp32 cuda-core (FMA pipe)", "kernel": "k_scan_co", "achieved": achieved,
+                "variant": "brute force (XS_FLAG_NO_PRUNE): every candidate of the slab evaluated; timed in this run after the headline steps",
+                "brute_force_step_ms": bf_ms, "brute_force_px_per_s": world * n_px / (bf_ms * 1e-3), "brute_force_steps": bf_steps,
+                "candidates_evaluated_per_px": evaluated(bf_stats), "pruned": pruned,
                 "peak": pk["measured_tflops"], "unit": "TFLOP/s", "frac": achieved / pk["measured_tflops"],
                 "peak_source": "xs_bench_fp32_peak: register-resident FFMA2 loop measured in this run",
                 "peak_nominal": pk["nominal_tflops"], "frac_of_nominal": achieved / pk["nominal_tflops"],
                 "peak_nominal_source": pk["source"], "scan_ms_per_launch": scan_avg_ms, "refine_ms_per_launch": refine_avg_ms,
                 "frac_incl_refinement": FLOP_CO * scan_px / ((scan_avg_ms + refine_avg_ms) * 1e-3) / 1e12 / pk["measured_tflops"],
-                "flop_per_px": FLOP_CO, "px_per_launch": scan_px, "share_of_step": scan_avg_ms / (ms / args.steps),
+                "flop_per_px": FLOP_CO, "px_per_launch": scan_px, "share_of_step": scan_avg_ms / bf_ms,
                 "accounting": "algorithmic: the reference's 8 flop per candidate (SURVEY D4); the centred form executes ~4.5",
                 "traffic": None if prof is None else prof["dram_bytes_per_px"] * scan_px,
                 "traffic_note": None if prof is None else "from profile (not measured in this run): DRAM read+write bytes of k_scan_co "

@@ -320,52 +320,48 @@ __global__ void __launch_bounds__(NW * 32, MB) k_scan_co(xs_plan pl, Workspace w
         const PixRec *mine = &sm.pix[b][warp * P];
         const int bin = sm.pix[b][0].bin;  // position 0 of a tile is never padding
 
-        // ---- per-warp centre and per-lane per-pixel query constants ----
-        bool any = false;
-        float cs = 0.f;
-        {
-            double smin = CUDART_INF, smax = -CUDART_INF;
-#pragma unroll
-            for (int p = 0; p < P; ++p)
-                if (mine[p].state == 1) {
-                    const double v = mine[p].s / pl.dsig_co;
-                    smin = fmin(smin, v);
-                    smax = fmax(smax, v);
-                    any = true;
-                }
-            if (any) cs = (float)(0.5 * (smin + smax));
-        }
+        // ---- per-warp centre and per-pixel query constants: lane p < P works for the warp's pixel p ----
+        // (the per-pixel scalars are the same in every lane: computed once in the pixel's lane and broadcast where needed)
+        const PixRec *own = &mine[lane < P ? lane : 0];
+        const bool on_l = lane < P && own->state == 1;
+        const double v_l = own->s / pl.dsig_co;           // s/dsig_co of this lane's pixel
+        const float sp_l = (float)v_l;
+        const unsigned on_lanes = __ballot_sync(0xffffffffu, on_l);
+        const bool any = on_lanes != 0u;
+        // centre: midpoint of the FP32 images of the warp's s/dsig_co (any constant will do; the refinement gets it in the RefRec)
+        const float cs = !any ? 0.f
+                              : 0.5f * (float_from_order_key(__reduce_min_sync(0xffffffffu, on_l ? float_order_key(sp_l) : 0x7fffffff)) +
+                                        float_from_order_key(__reduce_max_sync(0xffffffffu, on_l ? float_order_key(sp_l) : (int)0x80000000)));
         // Shared-sigma0 mode: the list is in sigma0 order, so the warp's pixels usually differ from the centre by a tiny
         // |sigma|; then k lambda = -2 sigma lambda is left out of the scanned cost altogether -- one FFMA2 per pixel and
         // candidate pair instead of two -- and the band is widened by what the omission can change BETWEEN two candidates
         // that can win, 2 |sigma| |lambda(c1) - lambda(c2)| (see the band section below).  The mode is chosen from an
         // estimate of that quantity (performance only -- the band uses the rigorous bound).
         const float slab_lo = float_from_order_key(pl.slab_range[2 * bin]), slab_hi = float_from_order_key(pl.slab_range[2 * bin + 1]);
-        float budget_need = 0.f;
-#pragma unroll
-        for (int p = 0; p < P; ++p)
-            if (mine[p].state == 1) {
-                const float sp = (float)(mine[p].s / pl.dsig_co);
-                const float dmin = fmaxf(fmaxf(slab_lo - sp, sp - slab_hi), 0.f);
-                // |d| of a winning candidate lies in [dmin, ~sqrt(dmin^2 + 6)]: outside the slab's range the spread is small
-                const float spread = dmin > 0.f ? sqrtf(dmin * dmin + 6.f) - dmin : 5.f;
-                budget_need = fmaxf(budget_need, fabsf(sp - cs) * spread);
-            }
-        const bool shared = any && budget_need <= share_tau;  // warp-uniform
-        float nqs[P];   // k_p = -2 (s_p/dsig - cs); 0 in shared mode
+        float need_l = 0.f;
+        if (on_l) {
+            const float dmin = fmaxf(fmaxf(slab_lo - sp_l, sp_l - slab_hi), 0.f);
+            // |d| of a winning candidate lies in [dmin, ~sqrt(dmin^2 + 6)]: outside the slab's range the spread is small
+            const float spread = dmin > 0.f ? sqrtf(dmin * dmin + 6.f) - dmin : 5.f;
+            need_l = fabsf(sp_l - cs) * spread;
+        }
+        // non-negative floats order like their bit patterns; a NaN estimate reads as a huge number (exact-k mode)
+        const bool shared = any && __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(need_l) & 0x7fffffffu)) <= share_tau;
+        const float nq_l = (on_l && !shared) ? (float)(-2.0 * (v_l - (double)cs)) : 0.f;  // k_p = -2 (s_p/dsig - cs); 0 in shared mode
+        float nqs[P];
         u64 g[P][KP];   // {g(phi_even), g(phi_odd)} as packed FP32
 #pragma unroll
-        for (int p = 0; p < P; ++p) {
-            const bool on = mine[p].state == 1;
-            nqs[p] = (on && !shared) ? (float)(-2.0 * (mine[p].s / pl.dsig_co - (double)cs)) : 0.f;
-            const double qa = mine[p].qa, qb = mine[p].qb;
+        for (int p = 0; p < P; ++p) nqs[p] = __shfl_sync(0xffffffffu, nq_l, p);
 #pragma unroll
-            for (int j = 0; j < KP; ++j) {
-                // (cos, sin) of the lane's phi nodes: 12 L1-resident loads per tile; 0 in the padding (+inf image values there)
-                const int ip = 2 * (lane + 32 * j);
-                const double c0x = ip < pl.n_phi ? pl.cos_phi[ip] : 0.0, c0y = ip < pl.n_phi ? pl.sin_phi[ip] : 0.0;
-                const double c1x = ip + 1 < pl.n_phi ? pl.cos_phi[ip + 1] : 0.0, c1y = ip + 1 < pl.n_phi ? pl.sin_phi[ip + 1] : 0.0;
-                g[p][j] = on ? pack2(g32(qa, qb, c0x, c0y), g32(qa, qb, c1x, c1y)) : 0ull;
+        for (int j = 0; j < KP; ++j) {
+            // (cos, sin) of the lane's phi nodes: 12 L1-resident loads per tile; 0 in the padding (+inf image values there)
+            const int ip = 2 * (lane + 32 * j);
+            const double c0x = ip < pl.n_phi ? pl.cos_phi[ip] : 0.0, c0y = ip < pl.n_phi ? pl.sin_phi[ip] : 0.0;
+            const double c1x = ip + 1 < pl.n_phi ? pl.cos_phi[ip + 1] : 0.0, c1y = ip + 1 < pl.n_phi ? pl.sin_phi[ip + 1] : 0.0;
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+                const double qa = mine[p].qa, qb = mine[p].qb;
+                g[p][j] = ((on_lanes >> p) & 1u) ? pack2(g32(qa, qb, c0x, c0y), g32(qa, qb, c1x, c1y)) : 0ull;
             }
         }
         // per lane and pixel: the running minimum and the set of chunks (bit c >> mask_sh) whose minimum came within
@@ -495,20 +491,24 @@ __global__ void __launch_bounds__(NW * 32, MB) k_scan_co(xs_plan pl, Workspace w
         if (shared) n_shared += P;
 
         // ---- band of every pixel -> RefRec ---------------------------------------------------------------------------
-        // m32 = warp-shuffle min of the FP32 costs; E bounds |J''_fp32 - J''_exact| for every candidate that can still
+        // m32 = warp minimum of the FP32 costs; E bounds |J''_fp32 - J''_exact| for every candidate that can still
         // win (derivation: DESIGN.md 4.1, checked on the CPU by tests/test_error_bound.py), so the reference's FP64 argmin
         // lies in S = {c : J''_fp32(c) <= m32 + 2E}; k_refine_easy collects S from the cells recorded here.
-        const float lmax = pl.slab_absmax[bin];
-        const float W = (float)pl.w_absmax * 1.0000002f;
+        // The bound of pixel p is evaluated once, in lane p.
+        float m32_l = CUDART_INF_F;
 #pragma unroll
         for (int p = 0; p < P; ++p) {
-            if (mine[p].state != 1) continue;  // warp-uniform
-            float m32 = best[p];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) m32 = fminf(m32, __shfl_xor_sync(0xffffffffu, m32, o));
-            const float fa = fabsf((float)mine[p].qa), fb = fabsf((float)mine[p].qb);
+            const float mp = float_from_order_key(__reduce_min_sync(0xffffffffu, float_order_key(best[p])));
+            if (lane == p) m32_l = mp;
+        }
+        float thr_l = -CUDART_INF_F, efp_l = 0.f;  // thr = -inf: no lane contends (the scan could not bound its error)
+        if (on_l) {
+            const float lmax = pl.slab_absmax[bin];
+            const float W = (float)pl.w_absmax * 1.0000002f;
+            const float m32 = m32_l;
+            const float fa = fabsf((float)own->qa), fb = fabsf((float)own->qb);
             const float A = sqrtf(fa * fa + fb * fb) * 1.000001f;  // >= |ancillary|
-            const float SC = fabsf((float)(mine[p].s / pl.dsig_co - (double)cs)) * 1.0000002f;
+            const float SC = fabsf((float)(v_l - (double)cs)) * 1.0000002f;
             const float T = W * A + 0.25f * W * W;
             // J'' = J' - sc^2: candidates that can still win have |L/dsig - s/dsig| <= D and |L/dsig - cs| <= Lam = D + |sc|.
             // Error terms (u = 2^-24): image value and lambda roundings 2 Lam (lmax + Lam) through lambda^2 and
@@ -521,24 +521,29 @@ __global__ void __launch_bounds__(NW * 32, MB) k_scan_co(xs_plan pl, Workspace w
             const float D = sqrtf(fmaxf(m32 + SC * SC * 1.0000002f, 0.f) + 0.25f * A * A + 1.0f + (shared ? 2.f * SC * R0 * 1.000001f : 0.f));
             const float Lam = D + SC;
             float E = 5.9604645e-8f * 1.5f * (2.f * Lam * lmax + 2.f * SC * lmax + 4.f * Lam * Lam + 6.f * SC * Lam + SC * SC + D * D + 4.f * T);
-            const float efp = E;  // bound of the full centred form's FP32 error (the refinement's second filter in shared mode)
+            efp_l = E;  // bound of the full centred form's FP32 error (the refinement's second filter in shared mode)
             if (shared) {
                 // J32_a(c*) <= J_a(c*) + E_fp = J''(c*) - k lambda(c*) + E_fp <= J''(c^) - k lambda(c*) + E_fp
                 //           <= J32_a(c^) + 2 E_fp + |k| |lambda(c^) - lambda(c*)|,   lambda(c^) - lambda(c*) = d(c^) - d(c*).
                 // Both |d| are at most Lam; when sigma0 lies outside the slab's value range by dmin, every d has the same
                 // sign and magnitude >= dmin, so the difference is at most Lam - dmin (a pixel far outside the LUT has a
                 // large lambda but a small spread); otherwise it is at most 2 Lam.
-                const float sp = (float)(mine[p].s / pl.dsig_co);
-                const float dist = fmaxf(slab_lo - sp, sp - slab_hi);  // scan-image values; the exact L/dsig differ by <= 1 ulp
-                const float dmin = fmaxf(dist * 0.999999f - 1e-6f * lmax - 1e-6f * fabsf(sp), 0.f);
+                const float dist = fmaxf(slab_lo - sp_l, sp_l - slab_hi);  // scan-image values; the exact L/dsig differ by <= 1 ulp
+                const float dmin = fmaxf(dist * 0.999999f - 1e-6f * lmax - 1e-6f * fabsf(sp_l), 0.f);
                 const float dl = dmin > 0.f ? fmaxf(Lam - dmin, 0.f) : 2.f * Lam;
                 E += SC * dl * 1.000001f;  // half of |k| dl: the band is m32 + 2E
             }
-            const float thr = m32 + 2.f * E;
             // 2 E < kBandMargin keeps the chunk masks complete; a larger bound means magnitudes outside the range the
             // bound was derived for
             const bool sane = (E < 0.5f * kBandMargin) && (m32 < CUDART_INF_F);
-            const unsigned cont = __ballot_sync(0xffffffffu, sane && best[p] <= thr);  // lanes holding band members
+            if (sane) thr_l = m32 + 2.f * E;
+        }
+        unsigned cont_l = 0u, m0_l = 0u, m1_l = 0u, m2_l = 0u;
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            if (!((on_lanes >> p) & 1u)) continue;  // warp-uniform
+            const float thr = __shfl_sync(0xffffffffu, thr_l, p);
+            const unsigned cont = __ballot_sync(0xffffffffu, best[p] <= thr);  // lanes holding band members
             // the record carries the chunk masks of the first two contending lanes (one or two in 99 % of the pixels) and
             // the union of the masks of all further ones (a superset for each of them)
             const bool mine_c = (cont >> lane) & 1u;
@@ -546,18 +551,24 @@ __global__ void __launch_bounds__(NW * 32, MB) k_scan_co(xs_plan pl, Workspace w
             const unsigned m0 = __reduce_or_sync(0xffffffffu, (mine_c && rank == 0) ? cmask[p] : 0u);
             const unsigned m1 = __reduce_or_sync(0xffffffffu, (mine_c && rank == 1) ? cmask[p] : 0u);
             const unsigned m2 = __reduce_or_sync(0xffffffffu, (mine_c && rank >= 2) ? cmask[p] : 0u);
-            if (lane == 0) {
-                RefRec rr;
-                rr.thr = thr;
-                rr.cs = cs;
-                rr.nq = nqs[p];
-                rr.efp = efp;
-                rr.cont = cont;
-                rr.mask[0] = m0;
-                rr.mask[1] = m1;
-                rr.mask[2] = m2;
-                ws.rec[(size_t)tile * TP + warp * P + p] = rr;
+            if (lane == p) {
+                cont_l = cont;
+                m0_l = m0;
+                m1_l = m1;
+                m2_l = m2;
             }
+        }
+        if (on_l) {
+            RefRec rr;
+            rr.thr = thr_l;
+            rr.cs = cs;
+            rr.nq = nq_l;
+            rr.efp = efp_l;
+            rr.cont = cont_l;
+            rr.mask[0] = m0_l;
+            rr.mask[1] = m1_l;
+            rr.mask[2] = m2_l;
+            ws.rec[(size_t)tile * TP + warp * P + lane] = rr;
         }
     }
     if (lane == 0 && n_shared) atomicAdd(&ws.counters[13], (u64)n_shared);
