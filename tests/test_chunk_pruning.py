@@ -44,8 +44,10 @@ def chunk_ranges(slab, gw):
     return lo, hi, wlo, whi
 
 
-def kept_chunks(slab, gw, cphi, sphi, ranges, a, b, s, s_mid, dsig):
-    """Transcription of k_tile_plan for one pixel of a tile whose median sigma0 is s_mid."""
+def kept_chunks(slab, gw, cphi, sphi, ranges, a, b, s, s_mid, dsig, s_rng=None):
+    """Transcription of k_tile_plan for one pixel of a tile whose median sigma0 is s_mid.  s_rng = (s_lo, s_hi): the kernel
+    evaluates the sigma0 part of the bound once per tile, for an interval that encloses the sigma0 of all its pixels (a
+    weaker bound than the pixel's own, which is what s_rng=None gives)."""
     lo, hi, wlo, whi = ranges
     n_w, n_p = slab.shape
     stride = (n_p + SEED_MAX - 1) // SEED_MAX
@@ -73,10 +75,11 @@ def kept_chunks(slab, gw, cphi, sphi, ranges, a, b, s, s_mid, dsig):
     r, ip = bflat
     U = ((gw[r] * cphi[ip] - a) / 2) ** 2 + ((gw[r] * sphi[ip] - b) / 2) ** 2 + ((slab[r, ip] - s) / dsig) ** 2
     A = np.hypot(a, b)
-    thr = U * (1 + 1e-6) + 1e-6 * (1 + A * A + np.abs(gw).max() ** 2)
-    ds = np.maximum(np.maximum(lo - s, s - hi), 0.0) * inv_d
+    thr = (U * (1 + 1e-6) + 1e-6 * (1 + A * A + np.abs(gw).max() ** 2)) * (1 + 2e-9)
+    s_lo, s_hi = (s, s) if s_rng is None else s_rng
+    ds = np.maximum(np.maximum(lo - s_hi, s_lo - hi), 0.0) * inv_d
     dw = np.maximum(np.maximum(wlo - A, A - whi), 0.0) * 0.5
-    lb = (ds * ds + dw * dw) * (1 - 1e-9)
+    lb = ds * ds + dw * dw
     return ~(lb > thr)
 
 
@@ -115,8 +118,11 @@ def test_argmin_chunk_is_never_pruned(slabs, kind):
         for k0 in range(0, len(order), 32):       # tiles of 32 pixels in sigma0 order share the seed rows
             tile = order[k0:k0 + 32]
             s_mid = s[tile[len(tile) // 2]]
+            f_lo, f_hi = np.float32(s[tile].min()), np.float32(s[tile].max())   # FP32 images widened by one ulp, as in the kernel
+            s_rng = (float(np.nextafter(f_lo, np.float32(-np.inf))), float(np.nextafter(f_hi, np.float32(np.inf))))
+            assert s_rng[0] <= s[tile].min() and s[tile].max() <= s_rng[1]
             for q in tile:
-                keep = kept_chunks(slab, gw, cphi, sphi, ranges, a[q], b[q], s[q], s_mid, dsig)
+                keep = kept_chunks(slab, gw, cphi, sphi, ranges, a[q], b[q], s[q], s_mid, dsig, s_rng)
                 J = exact_cost(slab, gw, cphi, sphi, a[q], b[q], s[q], dsig)
                 ties = np.argwhere(J == J.min())
                 assert keep[ties[:, 0] // CHUNK].all(), (kind, b_, q)

@@ -93,6 +93,28 @@ __global__ void k_build_scan(xs_plan pl) {
         pl.scan[i] = v;
     }
 }
+// cell image of the refinement (layout: xs_plan::cell), from the scan image
+__global__ void k_build_cell(xs_plan pl) {
+    const int kp = pl.kp;
+    const int64_t per_slab = (int64_t)pl.n_chunks * kChunkRows * pl.nph_pad;
+    const int64_t n = per_slab * pl.n_inc;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride) {
+        const int bin = (int)(e / per_slab);
+        int64_t r = e % per_slab;
+        const int i = (int)(r & 3);
+        r >>= 2;
+        const int sub = (int)(r & 7);
+        r >>= 3;
+        const int m = (int)(r % kp);
+        r /= kp;
+        const int L = (int)(r & 31);
+        const int c = (int)(r >> 5);
+        const int idx = 4 * m + i, h = idx / (2 * kp), k = idx - h * 2 * kp;
+        const int row = c * kChunkRows + sub + 8 * h, slot = 2 * (L + 32 * (k >> 1)) + (k & 1);
+        pl.cell[e] = row < pl.n_wspd_pad ? pl.scan[((int64_t)bin * pl.n_wspd_pad + row) * pl.nph_pad + slot] : CUDART_INF_F;
+    }
+}
 __global__ void k_init_slab_range(xs_plan pl) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < pl.n_inc) {
@@ -818,6 +840,7 @@ extern "C" void xs_plan_destroy(xs_plan *pl) {
     cudaFree(pl->cos_phi);
     cudaFree(pl->sin_phi);
     cudaFree(pl->scan);
+    cudaFree(pl->cell);
     cudaFree(pl->rowtab);
     cudaFree(pl->first_nan);
     cudaFree(pl->slab_absmax);
@@ -907,6 +930,7 @@ extern "C" int xs_plan_create(const xs_plan_desc *d, void *stream, xs_plan **out
             if ((rc = xs::check(cudaMalloc(&pl->slab_range, sizeof(int) * 2 * (size_t)d->n_inc), "cudaMalloc")) != XS_OK) return fail(rc);
             pl->n_chunks = (pl->n_wspd_pad + kChunkRows - 1) / kChunkRows;
             while ((pl->n_chunks + (1 << pl->mask_sh) - 1) >> pl->mask_sh > 32) ++pl->mask_sh;
+            if ((rc = xs::check(cudaMalloc(&pl->cell, sizeof(float) * (size_t)d->n_inc * pl->n_chunks * kChunkRows * pl->nph_pad), "cudaMalloc cell image")) != XS_OK) return fail(rc);
             const size_t n_cr = (size_t)d->n_inc * pl->n_chunks;
             if ((rc = xs::check(cudaMalloc(&pl->chunk_lo, sizeof(double) * n_cr), "cudaMalloc")) != XS_OK) return fail(rc);
             if ((rc = xs::check(cudaMalloc(&pl->chunk_hi, sizeof(double) * n_cr), "cudaMalloc")) != XS_OK) return fail(rc);
@@ -965,6 +989,7 @@ extern "C" int xs_plan_create(const xs_plan_desc *d, void *stream, xs_plan **out
             XS_CUDA(cudaMemsetAsync(pl->slab_absmax, 0, sizeof(float) * (size_t)pl->n_inc, st));
             XS_LAUNCH(k_init_slab_range, (int)ceil_div(pl->n_inc, 256), 256, 0, st, *pl);
             XS_LAUNCH(k_build_scan, kNumSMs * 8, 256, 0, st, *pl);
+            XS_LAUNCH(k_build_cell, kNumSMs * 8, 256, 0, st, *pl);
             XS_LAUNCH(k_build_rowtab, (int)ceil_div(pl->n_wspd_pad, 256), 256, 0, st, *pl);
             XS_LAUNCH(k_build_chunk_ranges, (int)ceil_div((int64_t)pl->n_inc * pl->n_chunks * 32, 256), 256, 0, st, *pl);
         } else {

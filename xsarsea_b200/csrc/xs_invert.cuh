@@ -15,6 +15,10 @@ struct xs_plan {
     double *inc_grid, *wspd_grid, *phi_grid, *cos_phi, *sin_phi;  // device copies of the host grids
     // scan image: [n_inc][n_wspd_pad][nph_pad] float, value = L_dB / dsig_co, +inf in the padding
     float *scan;
+    // the same values regrouped for the refinement (k_refine_easy): the 16 rows x 2 kp slots a scan lane L sees in chunk c are
+    // contiguous, [n_inc][n_chunks][32 lanes][kp quads][8 row-lanes][4 floats] -- quad m of row-lane `sub` holds elements
+    // 4m .. 4m+3 of its 4 kp candidates ordered (row sub | row sub + 8) x slot -- so a cell is kp full 128-byte lines
+    float *cell;
     float2 *rowtab;     // [n_wspd_pad] {-w/2, w*w/4} (0,0 in the padding)
     int *first_nan;     // [n_inc] flat index (w*n_phi+p) of the first NaN of the slab, or -1
     float *slab_absmax; // [n_inc] max finite |scan value| of the slab

@@ -117,8 +117,12 @@ __device__ __forceinline__ int next_chunk(unsigned mask, int c, int sh, int n_ch
     return c2 < n_chunks ? c2 : n_chunks;
 }
 
+constexpr int kPlanMaxChunks = 256;  // plan creation: n_wspd_pad <= 256 * kChunkRows
+
 __global__ void __launch_bounds__(256) k_tile_plan(xs_plan pl, Workspace ws, int tile_px, int nw, int min_items, int prune) {
-    __shared__ float4 seed_s[8][kSeedMax];  // {w cos phi, w sin phi, L / dsig_co, flat index} of the warp's seeds
+    __shared__ float4 seed_s[8][kSeedMax];       // {w cos phi, w sin phi, L / dsig_co, flat index} of the warp's seeds
+    __shared__ double lbs_s[8][kPlanMaxChunks];  // sigma0 part of the tile's lower bounds, per chunk
+    __shared__ double2 wr_s[kPlanMaxChunks];     // {wlo, whi} of every chunk
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_gw = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -127,11 +131,21 @@ __global__ void __launch_bounds__(256) k_tile_plan(xs_plan pl, Workspace ws, int
     const int nb = (n_chunks + (1 << sh) - 1) >> sh;
     const unsigned all = nb >= 32 ? 0xffffffffu : ((1u << nb) - 1u);
     const int P = tile_px / nw;
-    const unsigned pmask = P >= 32 ? 0xffffffffu : ((1u << P) - 1u);
     const int stride = (pl.n_phi + kSeedMax - 1) / kSeedMax, n_seed = (pl.n_phi + stride - 1) / stride;
     const double inv_d = 1.0 / fabs(pl.dsig_co);
+    for (int c = threadIdx.x; c < n_chunks; c += blockDim.x) wr_s[c] = make_double2(pl.chunk_wlo[c], pl.chunk_whi[c]);
+    __syncthreads();
+    // lanes of the scan warp w of a tile (pixels [w P, (w + 1) P))
+    unsigned grp[4];
+#pragma unroll
+    for (int w = 0; w < 4; ++w) grp[w] = (w < nw && lane >= w * P && lane < (w + 1) * P) ? 0xffffffffu : 0u;
     unsigned n_items = 0, n_warp_items = 0;
-    for (int64_t t = gw; t < n_tiles; t += n_gw) {
+    // a warp plans a contiguous range of tiles: neighbouring tiles of a bin have nearly the same sigma0, so the rows where the
+    // slab crosses it are those of the previous tile almost always (two loads verify that; a bisection otherwise)
+    const int64_t per = (n_tiles + n_gw - 1) / n_gw;
+    const int64_t t_end = min((gw + 1) * per, n_tiles);
+    int lo_prev[2] = {-1, -1}, bin_prev = -1;
+    for (int64_t t = gw * per; t < t_end; ++t) {
         unsigned uni = all, wm[4] = {all, all, all, all};
         PixRec rec;
         rec.qa = rec.qb = rec.s = 0.0;
@@ -144,23 +158,56 @@ __global__ void __launch_bounds__(256) k_tile_plan(xs_plan pl, Workspace ws, int
         if (prune && on_mask) {
             const double s_mid = __shfl_sync(0xffffffffu, rec.s, __fns(on_mask, 0, __popc(on_mask) / 2 + 1));
             const double *slab = pl.co_lut + (size_t)bin * pl.n_wspd * pl.n_phi;
-            for (int j = lane; j < n_seed; j += 32) {
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const int j = lane + 32 * k;
+                if (j >= n_seed) continue;
                 const int ip = j * stride;
-                int lo = 0, hi = pl.n_wspd;  // first row whose value reaches s_mid
-                while (lo < hi) {
-                    const int mid = (lo + hi) >> 1;
-                    if (slab[(size_t)mid * pl.n_phi + ip] < s_mid)
-                        lo = mid + 1;
-                    else
-                        hi = mid;
+                int lo = lo_prev[k];  // first row whose value reaches s_mid
+                bool known = false;
+                double v_lo = 0.0, v_hi = 0.0;  // slab[lo - 1], slab[lo]
+                if (bin == bin_prev && lo >= 0) {
+                    if (lo > 0) v_lo = slab[(size_t)(lo - 1) * pl.n_phi + ip];
+                    if (lo < pl.n_wspd) v_hi = slab[(size_t)lo * pl.n_phi + ip];
+                    known = (lo == 0 || v_lo < s_mid) && (lo == pl.n_wspd || !(v_hi < s_mid));
                 }
+                if (!known) {
+                    int hi = pl.n_wspd;
+                    lo = 0;
+                    while (lo < hi) {
+                        const int mid = (lo + hi) >> 1;
+                        if (slab[(size_t)mid * pl.n_phi + ip] < s_mid)
+                            lo = mid + 1;
+                        else
+                            hi = mid;
+                    }
+                    if (lo > 0) v_lo = slab[(size_t)(lo - 1) * pl.n_phi + ip];
+                    if (lo < pl.n_wspd) v_hi = slab[(size_t)lo * pl.n_phi + ip];
+                }
+                lo_prev[k] = lo;
                 int r = min(lo, pl.n_wspd - 1);
-                if (lo > 0 && lo < pl.n_wspd &&
-                    fabs(slab[(size_t)(lo - 1) * pl.n_phi + ip] - s_mid) <= fabs(slab[(size_t)lo * pl.n_phi + ip] - s_mid))
+                double v = lo < pl.n_wspd ? v_hi : v_lo;
+                if (lo > 0 && lo < pl.n_wspd && fabs(v_lo - s_mid) <= fabs(v_hi - s_mid)) {
                     r = lo - 1;
+                    v = v_lo;
+                }
                 const double w = pl.wspd_grid[r];
-                seed_s[wid][j] = make_float4((float)(w * pl.cos_phi[ip]), (float)(w * pl.sin_phi[ip]),
-                                             (float)(slab[(size_t)r * pl.n_phi + ip] * inv_d), __int_as_float(r * pl.n_phi + ip));
+                seed_s[wid][j] = make_float4((float)(w * pl.cos_phi[ip]), (float)(w * pl.sin_phi[ip]), (float)(v * inv_d),
+                                             __int_as_float(r * pl.n_phi + ip));
+            }
+            bin_prev = bin;
+            // sigma0 part of the bounds, once per tile: dist([s_lo, s_hi], [lo_c, hi_c]) with [s_lo, s_hi] enclosing the sigma0
+            // of every pixel of the tile (FP32 minimum / maximum widened by one ulp), lane <-> chunk
+            {
+                const float sf = (float)rec.s;
+                const float f_lo = float_from_order_key(__reduce_min_sync(0xffffffffu, on ? float_order_key(sf) : 0x7fffffff));
+                const float f_hi = float_from_order_key(__reduce_max_sync(0xffffffffu, on ? float_order_key(sf) : (int)0x80000000));
+                const double s_lo = (double)nextafterf(f_lo, -CUDART_INF_F), s_hi = (double)nextafterf(f_hi, CUDART_INF_F);
+                const double *clo = pl.chunk_lo + (size_t)bin * n_chunks, *chi = pl.chunk_hi + (size_t)bin * n_chunks;
+                for (int c = lane; c < n_chunks; c += 32) {
+                    const double ds = fmax(fmax(clo[c] - s_hi, s_lo - chi[c]), 0.0) * inv_d;
+                    lbs_s[wid][c] = ds * ds;
+                }
             }
             __syncwarp();
             float best = CUDART_INF_F;
@@ -177,28 +224,25 @@ __global__ void __launch_bounds__(256) k_tile_plan(xs_plan pl, Workspace ws, int
                     }
                 }
             }
-            __syncwarp();
             double thr = CUDART_INF;
             const double A = hypot(rec.qa, rec.qb);
             if (on) {
                 const int iw = bflat / pl.n_phi, ip = bflat - iw * pl.n_phi;
                 const double U = exact_cost_co(pl.wspd_grid[iw], pl.cos_phi[ip], pl.sin_phi[ip], slab[bflat], rec.qa, rec.qb, rec.s, pl.dsig_co);
-                thr = U * (1.0 + 1e-6) + 1e-6 * (1.0 + A * A + pl.w_absmax * pl.w_absmax);
+                // the margin: 1e-6 relative and absolute (in units of the magnitudes involved), plus the (1 - 1e-9) of the bound
+                thr = (U * (1.0 + 1e-6) + 1e-6 * (1.0 + A * A + pl.w_absmax * pl.w_absmax)) * (1.0 + 2e-9);
             }
-            uni = 0u;
-            wm[0] = wm[1] = wm[2] = wm[3] = 0u;
-            const double *clo = pl.chunk_lo + (size_t)bin * n_chunks, *chi = pl.chunk_hi + (size_t)bin * n_chunks;
+            unsigned km = 0u;  // chunk bits this lane's pixel keeps
             for (int c = 0; c < n_chunks; ++c) {
-                const double ds = fmax(fmax(clo[c] - rec.s, rec.s - chi[c]), 0.0) * inv_d;
-                const double dw = fmax(fmax(pl.chunk_wlo[c] - A, A - pl.chunk_whi[c]), 0.0) * 0.5;
-                const double lb = (ds * ds + dw * dw) * (1.0 - 1e-9);
-                const unsigned keep = __ballot_sync(0xffffffffu, on && !(lb > thr));  // NaN / inf thresholds keep everything
-                const unsigned bit = 1u << (c >> sh);
-                if (keep) uni |= bit;
-#pragma unroll
-                for (int w = 0; w < 4; ++w)
-                    if (w < nw && ((keep >> (w * P)) & pmask)) wm[w] |= bit;
+                const double2 wr = wr_s[c];
+                const double dw = fmax(fmax(wr.x - A, A - wr.y), 0.0) * 0.5;
+                const double lb = fma(dw, dw, lbs_s[wid][c]);
+                km |= (on && !(lb > thr)) ? (1u << (c >> sh)) : 0u;  // NaN / inf thresholds keep everything
             }
+            __syncwarp();  // the next tile overwrites the warp's shared-memory tables
+            uni = __reduce_or_sync(0xffffffffu, km);
+#pragma unroll
+            for (int w = 0; w < 4; ++w) wm[w] = __reduce_or_sync(0xffffffffu, km & grp[w]);
             // the scan's ring looks kStages chunks ahead, at most into the next tile
             while (mask_chunks(uni, sh, n_chunks) < min_items) {
                 unsigned ext = ((uni << 1) | (uni >> 1)) & ~uni & all;
@@ -583,7 +627,7 @@ __global__ void __launch_bounds__(NW * 32, MB) k_scan_co(xs_plan pl, Workspace w
 // several are evaluated in FP64 with the reference's operation order and reduced to the lexicographic (J, flat index)
 // minimum = numpy's first minimum.
 template <int KP, int G>  // G lanes per record position (32 / G positions per warp in flight)
-__global__ void __launch_bounds__(256, 3) k_refine_easy(xs_plan pl, Workspace ws, OutSpec out, int tile_px) {
+__global__ void __launch_bounds__(256, 2) k_refine_easy(xs_plan pl, Workspace ws, OutSpec out, int tile_px) {
     constexpr int PW = 32 / G;  // positions per warp
     const int lane = threadIdx.x & 31, sub = lane & (G - 1), grp = lane / G;
     const unsigned gmask = (G == 32 ? 0xffffffffu : ((1u << G) - 1u)) << (G * grp);
@@ -613,7 +657,7 @@ __global__ void __launch_bounds__(256, 3) k_refine_easy(xs_plan pl, Workspace ws
             continue;
         }
         if (sub == 0 && __popc(rc.cont) > 2) ++n_many;
-        const float *slab32 = pl.scan + (size_t)px.bin * pl.n_wspd_pad * pl.nph_pad;
+        const float *cell_img = pl.cell + (size_t)px.bin * pl.n_chunks * kChunkRows * pl.nph_pad;
         const double *slab64 = pl.co_lut + (size_t)px.bin * pl.n_wspd * pl.n_phi;
         // Shared-sigma0 records (nq == 0): the scanned cost left k lambda out and the band is wider by 2 |sigma| Lam.  The
         // members of that wide band are filtered a second time with the full centred FP32 cost (k recomputed as the scan's
@@ -663,43 +707,74 @@ __global__ void __launch_bounds__(256, 3) k_refine_easy(xs_plan pl, Workspace ws
                         cm &= cm - 1;
                     }
                     if (sub == 0 && stage == 0) ++n_cells;
+                    // the cell's kp lines first (independent loads: their latencies overlap), then the costs, branch-free; only a
+                    // lane that holds a band member (rare) goes on to the bookkeeping below
+                    constexpr int RH = kChunkRows / G;
+                    static_assert(G == 8 && RH == 2, "the cell image is laid out for 8 row-lanes with 2 rows each");
+                    float2 rtt[RH];
+                    float val[RH][2 * KP];
+                    {
+                        const float4 *cp = reinterpret_cast<const float4 *>(cell_img) + (((size_t)c * 32 + L) * KP) * 8 + sub;
+                        float4 q[KP];
 #pragma unroll
-                    for (int h = 0; h < kChunkRows / G; ++h) {
-                        const int iw = c * kChunkRows + sub + G * h;
-                        if (iw >= pl.n_wspd) continue;
-                        const float2 rt = pl.rowtab[iw];
-                        const float2 *rowp = reinterpret_cast<const float2 *>(slab32 + (size_t)iw * pl.nph_pad) + L;
+                        for (int m = 0; m < KP; ++m) q[m] = cp[m * 8];
 #pragma unroll
-                        for (int j = 0; j < KP; ++j) {
-                            const float2 v = rowp[32 * j];
+                        for (int h = 0; h < RH; ++h) rtt[h] = pl.rowtab[min(c * kChunkRows + sub + G * h, pl.n_wspd_pad - 1)];
 #pragma unroll
-                            for (int o = 0; o < 2; ++o) {  // exactly the scan's operations
-                                const int ip = 2 * (L + 32 * j) + o;
-                                const float lc = __fadd_rn(o ? v.y : v.x, -rc.cs);
-                                const float mm = __fmaf_rn(lc, lc, rt.y);
-                                const float J = __fmaf_rn(rt.x, gq[2 * j + o], __fmaf_rn(rc.nq, lc, mm));
-                                if (ip >= pl.n_phi || !(J <= rc.thr)) continue;
-                                const int flat = iw * pl.n_phi + ip;
-                                const float jf = two_stage ? __fmaf_rn(rt.x, gq[2 * j + o], __fmaf_rn(kfull, lc, mm)) : J;
-                                if (stage == 0) {
-                                    if (jf < b1) {
-                                        b3 = b2;
-                                        b2 = b1;
-                                        f2 = f1;
-                                        b1 = jf;
-                                        f1 = flat;
-                                    } else if (jf < b2) {
-                                        b3 = b2;
-                                        b2 = jf;
-                                        f2 = flat;
-                                    } else
-                                        b3 = fminf(b3, jf);
-                                } else if (jf <= thr2) {
-                                    if (stage == 1) {
-                                        ++n_loc;
-                                        one_loc = flat;
-                                    } else
-                                        fp64_feed(flat);
+                        for (int idx = 0; idx < 4 * KP; ++idx) {
+                            const float4 t = q[idx >> 2];
+                            val[idx / (2 * KP)][idx % (2 * KP)] = (idx & 3) == 0 ? t.x : ((idx & 3) == 1 ? t.y : ((idx & 3) == 2 ? t.z : t.w));
+                        }
+                    }
+                    float jmin_cell = CUDART_INF_F;
+#pragma unroll
+                    for (int h = 0; h < RH; ++h) {
+                        const bool row_ok = c * kChunkRows + sub + G * h < pl.n_wspd;
+#pragma unroll
+                        for (int k = 0; k < 2 * KP; ++k) {  // exactly the scan's operations (padding slots give NaN or +inf)
+                            const float lc = __fadd_rn(val[h][k], -rc.cs);
+                            const float mm = __fmaf_rn(lc, lc, rtt[h].y);
+                            const float J = __fmaf_rn(rtt[h].x, gq[k], __fmaf_rn(rc.nq, lc, mm));
+                            jmin_cell = fminf(jmin_cell, row_ok ? J : CUDART_INF_F);
+                        }
+                    }
+                    if (jmin_cell <= rc.thr) {
+#pragma unroll
+                        for (int h = 0; h < RH; ++h) {
+                            const int iw = c * kChunkRows + sub + G * h;
+                            if (iw >= pl.n_wspd) continue;
+                            const float2 rt = rtt[h];
+#pragma unroll
+                            for (int j = 0; j < KP; ++j) {
+#pragma unroll
+                                for (int o = 0; o < 2; ++o) {
+                                    const int ip = 2 * (L + 32 * j) + o;
+                                    const float lc = __fadd_rn(val[h][2 * j + o], -rc.cs);
+                                    const float mm = __fmaf_rn(lc, lc, rt.y);
+                                    const float J = __fmaf_rn(rt.x, gq[2 * j + o], __fmaf_rn(rc.nq, lc, mm));
+                                    if (ip >= pl.n_phi || !(J <= rc.thr)) continue;
+                                    const int flat = iw * pl.n_phi + ip;
+                                    const float jf = two_stage ? __fmaf_rn(rt.x, gq[2 * j + o], __fmaf_rn(kfull, lc, mm)) : J;
+                                    if (stage == 0) {
+                                        if (jf < b1) {
+                                            b3 = b2;
+                                            b2 = b1;
+                                            f2 = f1;
+                                            b1 = jf;
+                                            f1 = flat;
+                                        } else if (jf < b2) {
+                                            b3 = b2;
+                                            b2 = jf;
+                                            f2 = flat;
+                                        } else
+                                            b3 = fminf(b3, jf);
+                                    } else if (jf <= thr2) {
+                                        if (stage == 1) {
+                                            ++n_loc;
+                                            one_loc = flat;
+                                        } else
+                                            fp64_feed(flat);
+                                    }
                                 }
                             }
                         }
@@ -845,17 +920,7 @@ static int launch_shape(const xs_plan *pl, const RasterArgs &ra, const Workspace
     if (timer) XS_CUDA(cudaEventRecord(timer->ev[0], st));
     XS_LAUNCH(kern, sms * per_sm, NW * 32, smem, st, *pl, ws, share_tau);
     if (timer) XS_CUDA(cudaEventRecord(timer->ev[1], st));
-    static int refine_g = -1;  // lanes per record position in k_refine_easy (XS_REFINE_G: development aid)
-    if (refine_g < 0) {
-        const char *e = getenv("XS_REFINE_G");
-        refine_g = e ? atoi(e) : 8;
-    }
-    if (refine_g == 4)
-        XS_LAUNCH((k_refine_easy<KP, 4>), sms * 6, 256, 0, st, *pl, ws, out, TP);
-    else if (refine_g == 16)
-        XS_LAUNCH((k_refine_easy<KP, 16>), sms * 6, 256, 0, st, *pl, ws, out, TP);
-    else
-        XS_LAUNCH((k_refine_easy<KP, 8>), sms * 6, 256, 0, st, *pl, ws, out, TP);
+    XS_LAUNCH((k_refine_easy<KP, 8>), sms * 8, 256, 0, st, *pl, ws, out, TP);
     if (timer) {
         XS_CUDA(cudaEventRecord(timer->ev[2], st));
         timer->recorded = 1;

@@ -9,6 +9,7 @@ GPU in row blocks on side streams so host<->device copies overlap the scan.
 from __future__ import annotations
 
 import logging
+import os
 import queue
 import threading
 import warnings
@@ -26,7 +27,7 @@ logger = logging.getLogger("xsarsea.windspeed")
 _PLAN_CACHE: "OrderedDict[tuple, dev.InversionPlan]" = OrderedDict()
 _PLAN_CACHE_MAX = 4
 _PLAN_LOCK = threading.RLock()
-BLOCK_PIXELS = 1 << 26  # pixels per compute block of the host path (64 Mi px: 2.7 GB of f64 inputs, 2.1 GB of outputs, 5.6 GB of workspace)
+BLOCK_PIXELS = int(os.environ.get("XS_BLOCK_PIXELS", 1 << 26))  # pixels per compute block of the host path (64 Mi px: 2.7 GB of f64 inputs, 2.1 GB of outputs, 5.6 GB of workspace)
 STAGE_PIXELS = 1 << 24  # pixels per pinned staging chunk (16 Mi px: 0.27 GB per complex128 raster)
 
 
