@@ -170,6 +170,16 @@ __global__ void __launch_bounds__(256) k_tile_plan(xs_plan pl, Workspace ws, int
                     if (lo > 0) v_lo = slab[(size_t)(lo - 1) * pl.n_phi + ip];
                     if (lo < pl.n_wspd) v_hi = slab[(size_t)lo * pl.n_phi + ip];
                     known = (lo == 0 || v_lo < s_mid) && (lo == pl.n_wspd || !(v_hi < s_mid));
+                    // sigma0 grows from tile to tile: the crossing has moved up by one row far more often than anywhere else
+                    if (!known && lo + 1 <= pl.n_wspd && lo < pl.n_wspd && v_hi < s_mid) {
+                        const double v_up = lo + 1 < pl.n_wspd ? slab[(size_t)(lo + 1) * pl.n_phi + ip] : 0.0;
+                        if (lo + 1 == pl.n_wspd || !(v_up < s_mid)) {
+                            v_lo = v_hi;
+                            v_hi = v_up;
+                            ++lo;
+                            known = true;
+                        }
+                    }
                 }
                 if (!known) {
                     int hi = pl.n_wspd;
@@ -626,8 +636,8 @@ __global__ void __launch_bounds__(NW * 32, MB) k_scan_co(xs_plan pl, Workspace w
 // sub + 8 of a cell and all 2 KP phi slots, so g(phi) is evaluated once per slot; a single band member settles the pixel,
 // several are evaluated in FP64 with the reference's operation order and reduced to the lexicographic (J, flat index)
 // minimum = numpy's first minimum.
-template <int KP, int G>  // G lanes per record position (32 / G positions per warp in flight)
-__global__ void __launch_bounds__(256, 2) k_refine_easy(xs_plan pl, Workspace ws, OutSpec out, int tile_px) {
+template <int KP, int G, int MB = 2>  // G lanes per record position (32 / G positions per warp in flight); MB CTAs per SM
+__global__ void __launch_bounds__(256, MB) k_refine_easy(xs_plan pl, Workspace ws, OutSpec out, int tile_px) {
     constexpr int PW = 32 / G;  // positions per warp
     const int lane = threadIdx.x & 31, sub = lane & (G - 1), grp = lane / G;
     const unsigned gmask = (G == 32 ? 0xffffffffu : ((1u << G) - 1u)) << (G * grp);
@@ -713,8 +723,8 @@ __global__ void __launch_bounds__(256, 2) k_refine_easy(xs_plan pl, Workspace ws
                     static_assert(G == 8 && RH == 2, "the cell image is laid out for 8 row-lanes with 2 rows each");
                     float2 rtt[RH];
                     float val[RH][2 * KP];
+                    const float4 *cp = reinterpret_cast<const float4 *>(cell_img) + (((size_t)c * 32 + L) * KP) * 8 + sub;
                     {
-                        const float4 *cp = reinterpret_cast<const float4 *>(cell_img) + (((size_t)c * 32 + L) * KP) * 8 + sub;
                         float4 q[KP];
 #pragma unroll
                         for (int m = 0; m < KP; ++m) q[m] = cp[m * 8];
@@ -726,7 +736,7 @@ __global__ void __launch_bounds__(256, 2) k_refine_easy(xs_plan pl, Workspace ws
                             val[idx / (2 * KP)][idx % (2 * KP)] = (idx & 3) == 0 ? t.x : ((idx & 3) == 1 ? t.y : ((idx & 3) == 2 ? t.z : t.w));
                         }
                     }
-                    float jmin_cell = CUDART_INF_F;
+                    unsigned hm = 0u;  // band members among this lane's 4 kp candidates of the cell (bit = h * 2 kp + slot)
 #pragma unroll
                     for (int h = 0; h < RH; ++h) {
                         const bool row_ok = c * kChunkRows + sub + G * h < pl.n_wspd;
@@ -735,48 +745,46 @@ __global__ void __launch_bounds__(256, 2) k_refine_easy(xs_plan pl, Workspace ws
                             const float lc = __fadd_rn(val[h][k], -rc.cs);
                             const float mm = __fmaf_rn(lc, lc, rtt[h].y);
                             const float J = __fmaf_rn(rtt[h].x, gq[k], __fmaf_rn(rc.nq, lc, mm));
-                            jmin_cell = fminf(jmin_cell, row_ok ? J : CUDART_INF_F);
+                            hm |= (row_ok && J <= rc.thr) ? (1u << (h * 2 * KP + k)) : 0u;
                         }
                     }
-                    if (jmin_cell <= rc.thr) {
-#pragma unroll
-                        for (int h = 0; h < RH; ++h) {
-                            const int iw = c * kChunkRows + sub + G * h;
-                            if (iw >= pl.n_wspd) continue;
-                            const float2 rt = rtt[h];
-#pragma unroll
-                            for (int j = 0; j < KP; ++j) {
-#pragma unroll
-                                for (int o = 0; o < 2; ++o) {
-                                    const int ip = 2 * (L + 32 * j) + o;
-                                    const float lc = __fadd_rn(val[h][2 * j + o], -rc.cs);
-                                    const float mm = __fmaf_rn(lc, lc, rt.y);
-                                    const float J = __fmaf_rn(rt.x, gq[2 * j + o], __fmaf_rn(rc.nq, lc, mm));
-                                    if (ip >= pl.n_phi || !(J <= rc.thr)) continue;
-                                    const int flat = iw * pl.n_phi + ip;
-                                    const float jf = two_stage ? __fmaf_rn(rt.x, gq[2 * j + o], __fmaf_rn(kfull, lc, mm)) : J;
-                                    if (stage == 0) {
-                                        if (jf < b1) {
-                                            b3 = b2;
-                                            b2 = b1;
-                                            f2 = f1;
-                                            b1 = jf;
-                                            f1 = flat;
-                                        } else if (jf < b2) {
-                                            b3 = b2;
-                                            b2 = jf;
-                                            f2 = flat;
-                                        } else
-                                            b3 = fminf(b3, jf);
-                                    } else if (jf <= thr2) {
-                                        if (stage == 1) {
-                                            ++n_loc;
-                                            one_loc = flat;
-                                        } else
-                                            fp64_feed(flat);
-                                    }
-                                }
-                            }
+                    // the members (one per cell as a rule, in one lane of the group): values re-read and re-computed with the
+                    // same operations rather than selected out of the registers above
+                    while (hm) {
+                        const int idx = __ffs(hm) - 1;
+                        hm &= hm - 1;
+                        const int h = idx / (2 * KP), k = idx - h * 2 * KP;
+                        const int iw = c * kChunkRows + sub + G * h;
+                        const int ip = 2 * (L + 32 * (k >> 1)) + (k & 1);
+                        if (ip >= pl.n_phi) continue;
+                        const float v = reinterpret_cast<const float *>(cp)[(idx >> 2) * 32 + (idx & 3)];
+                        const float2 rt = h ? rtt[RH - 1] : rtt[0];
+                        const float gk = g32(px.qa, px.qb, pl.cos_phi[ip], pl.sin_phi[ip]);
+                        const float lc = __fadd_rn(v, -rc.cs);
+                        const float mm = __fmaf_rn(lc, lc, rt.y);
+                        const float J = __fmaf_rn(rt.x, gk, __fmaf_rn(rc.nq, lc, mm));
+                        if (!(J <= rc.thr)) continue;
+                        const int flat = iw * pl.n_phi + ip;
+                        const float jf = two_stage ? __fmaf_rn(rt.x, gk, __fmaf_rn(kfull, lc, mm)) : J;
+                        if (stage == 0) {
+                            if (jf < b1) {
+                                b3 = b2;
+                                b2 = b1;
+                                f2 = f1;
+                                b1 = jf;
+                                f1 = flat;
+                            } else if (jf < b2) {
+                                b3 = b2;
+                                b2 = jf;
+                                f2 = flat;
+                            } else
+                                b3 = fminf(b3, jf);
+                        } else if (jf <= thr2) {
+                            if (stage == 1) {
+                                ++n_loc;
+                                one_loc = flat;
+                            } else
+                                fp64_feed(flat);
                         }
                     }
                     ++c;
@@ -920,7 +928,15 @@ static int launch_shape(const xs_plan *pl, const RasterArgs &ra, const Workspace
     if (timer) XS_CUDA(cudaEventRecord(timer->ev[0], st));
     XS_LAUNCH(kern, sms * per_sm, NW * 32, smem, st, *pl, ws, share_tau);
     if (timer) XS_CUDA(cudaEventRecord(timer->ev[1], st));
-    XS_LAUNCH((k_refine_easy<KP, 8>), sms * 8, 256, 0, st, *pl, ws, out, TP);
+    static int refine_mb = -1;  // CTAs per SM of k_refine_easy (XS_REFINE_MB: development aid)
+    if (refine_mb < 0) {
+        const char *e = getenv("XS_REFINE_MB");
+        refine_mb = e ? atoi(e) : 3;
+    }
+    if (refine_mb == 3)
+        XS_LAUNCH((k_refine_easy<KP, 8, 3>), sms * 9, 256, 0, st, *pl, ws, out, TP);
+    else
+        XS_LAUNCH((k_refine_easy<KP, 8, 2>), sms * 8, 256, 0, st, *pl, ws, out, TP);
     if (timer) {
         XS_CUDA(cudaEventRecord(timer->ev[2], st));
         timer->recorded = 1;

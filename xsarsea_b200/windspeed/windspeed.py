@@ -134,6 +134,30 @@ class _PinnedPool:
 
 
 _POOL = _PinnedPool()
+_COPY_THREADS = 4
+_COPY_POOL = None
+
+
+def _par_copy(dst, src):
+    """dst[...] = src for large 1-D / [k, m] host arrays, split along the last axis between a few threads (numpy releases the
+    GIL while it copies; one thread moves ~6-10 GB/s, and fresh pageable destinations also take their first-touch page
+    faults here)."""
+    global _COPY_POOL
+    m = dst.shape[-1]
+    if m < (1 << 20):
+        np.copyto(dst, src)
+        return
+    if _COPY_POOL is None:
+        with _PLAN_LOCK:
+            if _COPY_POOL is None:
+                from concurrent.futures import ThreadPoolExecutor
+
+                _COPY_POOL = ThreadPoolExecutor(max_workers=4 * _COPY_THREADS, thread_name_prefix="xs-copy")
+    cuts = [m * k // _COPY_THREADS for k in range(_COPY_THREADS + 1)]
+    futs = [_COPY_POOL.submit(np.copyto, dst[..., a:b], src[..., a:b]) for a, b in zip(cuts[1:], cuts[2:])]
+    np.copyto(dst[..., :cuts[1]], src[..., :cuts[1]])
+    for f in futs:
+        f.result()
 
 
 def _block_edges(n):
@@ -226,14 +250,8 @@ def _run_device(plan, inc, s_co, s_cr, dsig_cr, anc, *, sigma0_db, merge_dual, c
     counters = dict(in_chunk=0, out_chunk=0)
 
     def drain():
-        # the outputs are fresh pageable memory: the copy out of the staging chunk also takes the first-touch page faults
-        # (~6 GB/s per thread), so every finished chunk is split between a few helper threads (numpy releases the GIL)
-        def part(r, lo, m, k, parts):
-            a, b = m * k // parts, m * (k + 1) // parts
-            if out_co is not None:
-                out_co[:, lo + a:lo + b] = oco_stage[r][:out_co.shape[0] * m].reshape(out_co.shape[0], m)[:, a:b]
-            out_cr[:, lo + a:lo + b] = ocr_stage[r][:out_cr.shape[0] * m].reshape(out_cr.shape[0], m)[:, a:b]
-
+        # the outputs are fresh pageable memory: the copy out of the staging chunk also takes the first-touch page faults,
+        # so every finished chunk is split between a few threads (_par_copy)
         while True:
             job = jobs.get()
             if job is None:
@@ -241,13 +259,11 @@ def _run_device(plan, inc, s_co, s_cr, dsig_cr, anc, *, sigma0_db, merge_dual, c
             ev, r, lo, m = job
             try:
                 ev.synchronize()
-                parts = 4 if m >= (1 << 20) else 1
-                helpers = [threading.Thread(target=part, args=(r, lo, m, k, parts)) for k in range(1, parts)]
-                for t in helpers:
-                    t.start()
-                part(r, lo, m, 0, parts)
-                for t in helpers:
-                    t.join()
+                if out_co is not None:
+                    k = out_co.shape[0]
+                    _par_copy(out_co[:, lo:lo + m], oco_stage[r][:k * m].reshape(k, m))
+                k = out_cr.shape[0]
+                _par_copy(out_cr[:, lo:lo + m], ocr_stage[r][:k * m].reshape(k, m))
             except Exception as e:  # pragma: no cover
                 errors.append(e)
             finally:
@@ -271,7 +287,7 @@ def _run_device(plan, inc, s_co, s_cr, dsig_cr, anc, *, sigma0_db, merge_dual, c
                     counters["in_chunk"] += 1
                     if ev_stage_in[r] is not None:
                         ev_stage_in[r].synchronize()
-                    np.copyto(st[r][:m], h[a:a + m])
+                    _par_copy(st[r][:m], h[a:a + m])
                     d[slot][a - lo:a - lo + m].copy_(torch.from_numpy(st[r][:m]), non_blocking=True)
                     ev_stage_in[r] = torch.cuda.Event()
                     ev_stage_in[r].record(s_in)
