@@ -317,10 +317,10 @@ def wind_diff(got, want, tie=None):
                 max_dspeed=float(dspd.max()) if dspd.size else 0.0, max_ddir_deg=float(ddir.max()) if ddir.size else 0.0)
 
 
-def evaluated(stats, n_phi=181, rows=16, px_per_warp=8):
-    """Candidates the scan really evaluated per scanned pixel (padding rows of the last chunk included): every warp-chunk is
-    16 wspd rows x n_phi nodes for the warp's 8 pixels."""
-    return stats["warp_chunks"] * rows * n_phi * px_per_warp / max(stats["scan_pixels"], 1)
+def evaluated(stats, rows=16, px_per_warp=8):
+    """Candidates the scan really evaluated per scanned pixel (padding rows of the last chunk included): the kernel counts
+    the (chunk, phi node) pairs every warp computed on, each 16 wspd rows for the warp's 8 pixels."""
+    return stats["warp_chunk_phi"] * rows * px_per_warp / max(stats["scan_pixels"], 1)
 
 
 def scan_roof(stats, scan_ms, peak_tflops, peak_src):

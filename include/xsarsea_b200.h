@@ -200,8 +200,9 @@ int xs_invert(const xs_plan *plan, const xs_invert_args *args, void *stream);
  * the stream has reached the end of the call): [0] co-pol tiles, [1] pixels sent to the exhaustive FP64 scan,
  * [2] co-pol pixels settled by the FP32 scan (+ refinement), [3] (lane, chunk) cells re-examined by the refinement,
  * [4] pixels of a cross-pol-only call that the step-function kernel (k_cross_only) left to the general cross-pol pass,
- * [5] 16-row chunks the scan CTAs streamed (summed over tiles), [6] chunks the scan warps computed on (summed over the
- * warps of every tile; without pruning both are tiles x chunks per slab (x warps per tile)), [7], [9], [10] unused (0),
+ * [5] 16-row chunks the scan CTAs streamed (summed over tiles; tiles x chunks per slab without pruning), [6] (chunk, phi
+ * node) pairs the scan warps computed on, summed over the warps of every tile (x 16 rows x 8 pixels = candidates evaluated;
+ * tiles x warps per tile x chunks per slab x n_phi without pruning), [7], [9], [10] unused (0),
  * [8] tile hand-out cursor, [11] pixels the refinement settled in FP64 (more than one candidate inside the band),
  * [12] pixels with more than two contending lanes, [13] record positions scanned in shared-sigma0 mode. */
 

@@ -32,16 +32,22 @@ def exact_cost(slab, gw, cphi, sphi, a, b, s, dsig):
     return jw + ((slab - s) / dsig) ** 2
 
 
-def chunk_ranges(slab, gw):
+def chunk_ranges(slab, gw, phis=slice(None)):
+    """Value range of every chunk over the phi nodes `phis` (all of them, or one phi group = 64 consecutive nodes: what
+    one float2 slot of the scan lanes covers) and the |wspd| range of every chunk."""
     n_chunks = (len(gw) + CHUNK - 1) // CHUNK
     lo, hi, wlo, whi = (np.empty(n_chunks) for _ in range(4))
     for c in range(n_chunks):
         rows = slice(c * CHUNK, min((c + 1) * CHUNK, len(gw)))
-        v = slab[rows]
+        v = slab[rows][:, phis]
         fin = np.isfinite(v).all()
         lo[c], hi[c] = (v.min(), v.max()) if fin else (-np.inf, np.inf)
         wlo[c], whi[c] = np.abs(gw[rows]).min(), np.abs(gw[rows]).max()
     return lo, hi, wlo, whi
+
+
+def phi_groups(n_phi):
+    return [slice(64 * g, min(64 * (g + 1), n_phi)) for g in range((n_phi + 63) // 64)]
 
 
 def kept_chunks(slab, gw, cphi, sphi, ranges, a, b, s, s_mid, dsig, s_rng=None):
@@ -110,9 +116,12 @@ def test_argmin_chunk_is_never_pruned(slabs, kind):
     rng = np.random.default_rng({"benchmark": 1, "nodes": 2, "hostile": 3, "wide": 4}[kind])
     dsig = 0.1
     kept_frac = []
+    groups = phi_groups(len(gp))
+    cells_kept = []
     for b_ in range(len(gi)):
         slab = lut_db[b_]
         ranges = chunk_ranges(slab, gw)
+        granges = [chunk_ranges(slab, gw, g) for g in groups]
         s, a, b = pixels(rng, slab, gw, gp, 60, kind)
         order = np.argsort(s)
         for k0 in range(0, len(order), 32):       # tiles of 32 pixels in sigma0 order share the seed rows
@@ -129,10 +138,22 @@ def test_argmin_chunk_is_never_pruned(slabs, kind):
                 # stronger: every skipped chunk is strictly worse than the minimum
                 worst_skipped = min((J[c * CHUNK:(c + 1) * CHUNK].min() for c in np.flatnonzero(~keep)), default=np.inf)
                 assert worst_skipped > J.min()
+                # the same per cell = (chunk, phi group), the granularity the scan warps skip at
+                n_cells = 0
+                for g, gr in zip(groups, granges):
+                    keep_g = kept_chunks(slab, gw, cphi, sphi, gr, a[q], b[q], s[q], s_mid, dsig, s_rng)
+                    assert not (keep_g & ~keep).any()          # a cell's bound is at least its chunk's
+                    assert keep_g[ties[:, 0][(ties[:, 1] >= g.start) & (ties[:, 1] < g.stop)] // CHUNK].all(), (kind, b_, q)
+                    worst = min((J[c * CHUNK:(c + 1) * CHUNK, g].min() for c in np.flatnonzero(~keep_g)), default=np.inf)
+                    assert worst > J.min()
+                    n_cells += kept_chunks(slab, gw, cphi, sphi, gr, a[q], b[q], s[q], s[q], dsig).sum()   # dense tile, as below
+                cells_kept.append(n_cells / len(groups))
                 # a dense tile (the full scene: >= 1e5 pixels per bin) has its median sigma0 next to every pixel's own
                 kept_frac.append(kept_chunks(slab, gw, cphi, sphi, ranges, a[q], b[q], s[q], s[q], dsig).mean())
     if kind == "benchmark":
         assert np.mean(kept_frac) < 0.2, np.mean(kept_frac)
+        # the phi groups prune further inside the kept chunks (in chunk equivalents)
+        assert np.mean(cells_kept) < 0.8 * np.mean(kept_frac) * len(ranges[0]), (np.mean(cells_kept), np.mean(kept_frac))
 
 
 def test_non_finite_chunks_give_no_sigma0_bound(slabs):

@@ -401,10 +401,10 @@ def test_chunk_pruning_equals_brute_force(env, scene):
     bits = lambda z: torch.view_as_real(z).contiguous().view(torch.int64)
     assert torch.equal(bits(a), bits(b)) and torch.equal(bits(a), bits(c))
     n_chunks = (499 + 7) // 8 * 8 // 16 + (1 if ((499 + 7) // 8 * 8) % 16 else 0)
-    assert st0["chunks_streamed"] == st0["tiles"] * n_chunks and st0["warp_chunks"] <= 4 * st0["chunks_streamed"]
+    assert st0["chunks_streamed"] == st0["tiles"] * n_chunks and st0["warp_chunk_phi"] == 4 * 181 * st0["chunks_streamed"]
     assert st["tiles"] == st0["tiles"] and st["scan_pixels"] == st0["scan_pixels"]
     assert 4 * st["tiles"] <= st["chunks_streamed"] < 0.6 * st0["chunks_streamed"], (st, st0)
-    assert st["warp_chunks"] < 0.6 * st0["warp_chunks"]
+    assert st["warp_chunk_phi"] < 0.5 * st0["warp_chunk_phi"]
 
 
 def test_chunk_pruning_small_and_ragged_rasters(env):

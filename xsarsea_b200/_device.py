@@ -388,4 +388,4 @@ class InversionPlan:
     def last_stats(self):
         c = self.debug_counters()
         return dict(scan_pixels=c[2], fp64_chunks=c[3], exhaustive_pixels=c[1], tiles=c[0], fp64_pixels=c[11], many_lane_pixels=c[12],
-                    shared_mode_positions=c[13], cross_listed_pixels=c[4], chunks_streamed=c[5], warp_chunks=c[6])
+                    shared_mode_positions=c[13], cross_listed_pixels=c[4], chunks_streamed=c[5], warp_chunk_phi=c[6])

@@ -132,23 +132,33 @@ __global__ void k_build_rowtab(xs_plan pl) {
     }
     pl.rowtab[i] = v;
 }
-// value range of every chunk of every slab (all phi nodes, the chunk's valid rows) and the |wspd| range of every chunk:
-// what k_tile_plan's lower bounds are made of.  One warp per (bin, chunk).
+// value range of every cell (chunk x phi group) of every slab over the chunk's valid rows, and the |wspd| range of every chunk:
+// what k_tile_plan's lower bounds are made of.  One warp per (bin, chunk, group).
 __global__ void k_build_chunk_ranges(xs_plan pl) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (warp >= (int64_t)pl.n_inc * pl.n_chunks) return;
-    const int bin = (int)(warp / pl.n_chunks), c = (int)(warp % pl.n_chunks);
+    if (warp >= (int64_t)pl.n_inc * pl.n_chunks * pl.n_groups) return;
+    const int g = (int)(warp % pl.n_groups);
+    const int c = (int)((warp / pl.n_groups) % pl.n_chunks), bin = (int)(warp / pl.n_groups / pl.n_chunks);
     const int r0 = c * kChunkRows, r1 = min(r0 + kChunkRows, pl.n_wspd);
+    // phi nodes of the group: slots j with j * n_groups / kp == g
+    int j0 = 0, j1 = 0;
+    for (int j = 0; j < pl.kp; ++j)
+        if (j * pl.n_groups / pl.kp == g) {
+            if (j1 == 0) j0 = j;
+            j1 = j + 1;
+        }
+    const int p0 = min(64 * j0, pl.n_phi), p1 = min(64 * j1, pl.n_phi);
     double lo = CUDART_INF, hi = -CUDART_INF, wlo = CUDART_INF, whi = -CUDART_INF;
     bool finite = true;
     const double *slab = pl.co_lut + (int64_t)bin * pl.n_wspd * pl.n_phi;
-    for (int i = r0 * pl.n_phi + lane; i < r1 * pl.n_phi; i += 32) {
-        const double v = slab[i];
-        finite &= isfinite(v);
-        lo = fmin(lo, v);
-        hi = fmax(hi, v);
-    }
+    for (int r = r0; r < r1; ++r)
+        for (int ip = p0 + lane; ip < p1; ip += 32) {
+            const double v = slab[(int64_t)r * pl.n_phi + ip];
+            finite &= isfinite(v);
+            lo = fmin(lo, v);
+            hi = fmax(hi, v);
+        }
     for (int r = r0 + lane; r < r1; r += 32) {
         const double w = fabs(pl.wspd_grid[r]);
         wlo = fmin(wlo, w);
@@ -163,10 +173,11 @@ __global__ void k_build_chunk_ranges(xs_plan pl) {
     }
     finite = __all_sync(0xffffffffu, finite);
     if (lane == 0) {
-        // a chunk with a non-finite value (or without valid rows) gives no sigma0 bound
-        pl.chunk_lo[warp] = (finite && r1 > r0) ? lo : -CUDART_INF;
-        pl.chunk_hi[warp] = (finite && r1 > r0) ? hi : CUDART_INF;
-        if (bin == 0) {
+        // a cell with a non-finite value gives no sigma0 bound; a cell without candidates can always be skipped
+        const bool empty = r1 <= r0 || p1 <= p0;
+        pl.chunk_lo[warp] = empty ? CUDART_INF : (finite ? lo : -CUDART_INF);
+        pl.chunk_hi[warp] = empty ? CUDART_INF : (finite ? hi : CUDART_INF);
+        if (bin == 0 && g == 0) {
             pl.chunk_wlo[c] = r1 > r0 ? wlo : 0.0;
             pl.chunk_whi[c] = r1 > r0 ? whi : CUDART_INF;
         }
@@ -931,7 +942,8 @@ extern "C" int xs_plan_create(const xs_plan_desc *d, void *stream, xs_plan **out
             pl->n_chunks = (pl->n_wspd_pad + kChunkRows - 1) / kChunkRows;
             while ((pl->n_chunks + (1 << pl->mask_sh) - 1) >> pl->mask_sh > 32) ++pl->mask_sh;
             if ((rc = xs::check(cudaMalloc(&pl->cell, sizeof(float) * (size_t)d->n_inc * pl->n_chunks * kChunkRows * pl->nph_pad), "cudaMalloc cell image")) != XS_OK) return fail(rc);
-            const size_t n_cr = (size_t)d->n_inc * pl->n_chunks;
+            pl->n_groups = kp < kPlanGroups ? kp : kPlanGroups;
+            const size_t n_cr = (size_t)d->n_inc * pl->n_chunks * pl->n_groups;
             if ((rc = xs::check(cudaMalloc(&pl->chunk_lo, sizeof(double) * n_cr), "cudaMalloc")) != XS_OK) return fail(rc);
             if ((rc = xs::check(cudaMalloc(&pl->chunk_hi, sizeof(double) * n_cr), "cudaMalloc")) != XS_OK) return fail(rc);
             if ((rc = xs::check(cudaMalloc(&pl->chunk_wlo, sizeof(double) * (size_t)pl->n_chunks), "cudaMalloc")) != XS_OK) return fail(rc);
@@ -991,7 +1003,7 @@ extern "C" int xs_plan_create(const xs_plan_desc *d, void *stream, xs_plan **out
             XS_LAUNCH(k_build_scan, kNumSMs * 8, 256, 0, st, *pl);
             XS_LAUNCH(k_build_cell, kNumSMs * 8, 256, 0, st, *pl);
             XS_LAUNCH(k_build_rowtab, (int)ceil_div(pl->n_wspd_pad, 256), 256, 0, st, *pl);
-            XS_LAUNCH(k_build_chunk_ranges, (int)ceil_div((int64_t)pl->n_inc * pl->n_chunks * 32, 256), 256, 0, st, *pl);
+            XS_LAUNCH(k_build_chunk_ranges, (int)ceil_div((int64_t)pl->n_inc * pl->n_chunks * pl->n_groups * 32, 256), 256, 0, st, *pl);
         } else {
             XS_LAUNCH(k_find_first_nan, kNumSMs * 8, 256, 0, st, *pl);
         }

@@ -26,10 +26,13 @@ struct xs_plan {
     int kp;             // float2 pairs per lane: nph_pad = 64*kp
     int nph_pad, n_wspd_pad;
     int fast_ok;        // the FP32 scan can be used for this plan
-    // exact chunk pruning (k_tile_plan): value range of every 16-row chunk of every slab over all phi nodes (FP64 dB;
-    // -inf / +inf when the chunk holds a non-finite value) and the range of |wspd| over the chunk's rows
+    // exact pruning (k_tile_plan): value range of every cell = (16-row chunk, phi group) of every slab (FP64 dB; -inf / +inf
+    // when the cell holds a non-finite value) and the range of |wspd| over the chunk's rows.  A phi group is what a scan lane
+    // walks with one (or, kp > 3, two) of its kp float2 slots: slots j with j * n_groups / kp == g, i.e. the phi nodes
+    // [64 j, 64 j + 63]
     int n_chunks, mask_sh;  // chunks per slab; a bit of the 32-bit chunk masks covers 2^mask_sh chunks
-    double *chunk_lo, *chunk_hi;    // [n_inc][n_chunks]
+    int n_groups;           // min(kp, 3)
+    double *chunk_lo, *chunk_hi;    // [n_inc][n_chunks][n_groups]
     double *chunk_wlo, *chunk_whi;  // [n_chunks]
     int inc_sorted;     // inc_grid strictly ascending (binary search allowed)
     // ---- cross-pol model (n_inc_cr == 0 when absent) ----
@@ -75,7 +78,8 @@ constexpr int kStages = 4;         // shared-memory ring depth of the scan (4 x 
 constexpr int kCrInvBuckets = 1024;
 constexpr float kBandMargin = 0.5f;  // every accepted error band is narrower than this (2 E < kBandMargin)
 constexpr int kTilePad = 64;       // upper bound of the pixels per scan tile (the bin segments of the pixel list are padded to tiles)
-constexpr int kPlanWords = 8;      // 32-byte scan plan of a tile: [0] chunks the CTA streams, [1 + w] chunks warp w computes on
+constexpr int kPlanGroups = 3;     // phi groups of the pruning (xs_plan::n_groups <= this)
+constexpr int kPlanWords = 16;     // 64-byte scan plan of a tile: [0] chunks the CTA streams, [1 + 3 w + g] chunks on which warp w computes phi group g
 constexpr int kMinTilePx = 16;     // smallest scan tile (sizes the tile-plan array)
 constexpr int kMaxIncBins = 6144;  // bins whose two shared-memory histograms (k_bin_scatter) fit the default 48 KB
 

@@ -121,8 +121,10 @@ constexpr int kPlanMaxChunks = 256;  // plan creation: n_wspd_pad <= 256 * kChun
 
 __global__ void __launch_bounds__(256) k_tile_plan(xs_plan pl, Workspace ws, int tile_px, int nw, int min_items, int prune) {
     __shared__ float4 seed_s[8][kSeedMax];       // {w cos phi, w sin phi, L / dsig_co, flat index} of the warp's seeds
-    __shared__ double lbs_s[8][kPlanMaxChunks];  // sigma0 part of the tile's lower bounds, per chunk
-    __shared__ double2 wr_s[kPlanMaxChunks];     // {wlo, whi} of every chunk
+    extern __shared__ __align__(16) unsigned char plan_smem[];
+    double2 *wr_s = reinterpret_cast<double2 *>(plan_smem);  // [n_chunks] {wlo, whi} of every chunk
+    // sigma0 part of the tile's lower bounds, [warp][chunk][group]
+    double *lbs_all = reinterpret_cast<double *>(plan_smem + sizeof(double2) * pl.n_chunks);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_gw = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -131,22 +133,38 @@ __global__ void __launch_bounds__(256) k_tile_plan(xs_plan pl, Workspace ws, int
     const int nb = (n_chunks + (1 << sh) - 1) >> sh;
     const unsigned all = nb >= 32 ? 0xffffffffu : ((1u << nb) - 1u);
     const int P = tile_px / nw;
+    const int ng = pl.n_groups;
+    double *lbs_s = lbs_all + (size_t)wid * n_chunks * ng;
     const int stride = (pl.n_phi + kSeedMax - 1) / kSeedMax, n_seed = (pl.n_phi + stride - 1) / stride;
     const double inv_d = 1.0 / fabs(pl.dsig_co);
     for (int c = threadIdx.x; c < n_chunks; c += blockDim.x) wr_s[c] = make_double2(pl.chunk_wlo[c], pl.chunk_whi[c]);
     __syncthreads();
+    // phi nodes per group (statistics: candidates the scan evaluates)
+    int gphi[kPlanGroups];
+#pragma unroll
+    for (int g = 0; g < kPlanGroups; ++g) {
+        int cnt = 0;
+        for (int j = 0; j < pl.kp; ++j)
+            if (g < ng && j * ng / pl.kp == g) cnt += max(min(64 * (j + 1), pl.n_phi) - 64 * j, 0);
+        gphi[g] = cnt;
+    }
     // lanes of the scan warp w of a tile (pixels [w P, (w + 1) P))
     unsigned grp[4];
 #pragma unroll
     for (int w = 0; w < 4; ++w) grp[w] = (w < nw && lane >= w * P && lane < (w + 1) * P) ? 0xffffffffu : 0u;
-    unsigned n_items = 0, n_warp_items = 0;
+    unsigned n_items = 0;
+    u64 n_warp_items = 0;
     // a warp plans a contiguous range of tiles: neighbouring tiles of a bin have nearly the same sigma0, so the rows where the
     // slab crosses it are those of the previous tile almost always (two loads verify that; a bisection otherwise)
     const int64_t per = (n_tiles + n_gw - 1) / n_gw;
     const int64_t t_end = min((gw + 1) * per, n_tiles);
     int lo_prev[2] = {-1, -1}, bin_prev = -1;
     for (int64_t t = gw * per; t < t_end; ++t) {
-        unsigned uni = all, wm[4] = {all, all, all, all};
+        unsigned uni = all, wm[4][kPlanGroups];  // [scan warp][phi group]
+#pragma unroll
+        for (int w = 0; w < 4; ++w)
+#pragma unroll
+            for (int g = 0; g < kPlanGroups; ++g) wm[w][g] = g < ng ? all : 0u;
         PixRec rec;
         rec.qa = rec.qb = rec.s = 0.0;
         rec.bin = 0;
@@ -213,10 +231,10 @@ __global__ void __launch_bounds__(256) k_tile_plan(xs_plan pl, Workspace ws, int
                 const float f_lo = float_from_order_key(__reduce_min_sync(0xffffffffu, on ? float_order_key(sf) : 0x7fffffff));
                 const float f_hi = float_from_order_key(__reduce_max_sync(0xffffffffu, on ? float_order_key(sf) : (int)0x80000000));
                 const double s_lo = (double)nextafterf(f_lo, -CUDART_INF_F), s_hi = (double)nextafterf(f_hi, CUDART_INF_F);
-                const double *clo = pl.chunk_lo + (size_t)bin * n_chunks, *chi = pl.chunk_hi + (size_t)bin * n_chunks;
-                for (int c = lane; c < n_chunks; c += 32) {
+                const double *clo = pl.chunk_lo + (size_t)bin * n_chunks * ng, *chi = pl.chunk_hi + (size_t)bin * n_chunks * ng;
+                for (int c = lane; c < n_chunks * ng; c += 32) {  // (chunk, group) cells
                     const double ds = fmax(fmax(clo[c] - s_hi, s_lo - chi[c]), 0.0) * inv_d;
-                    lbs_s[wid][c] = ds * ds;
+                    lbs_s[c] = ds * ds;
                 }
             }
             __syncwarp();
@@ -242,17 +260,22 @@ __global__ void __launch_bounds__(256) k_tile_plan(xs_plan pl, Workspace ws, int
                 // the margin: 1e-6 relative and absolute (in units of the magnitudes involved), plus the (1 - 1e-9) of the bound
                 thr = (U * (1.0 + 1e-6) + 1e-6 * (1.0 + A * A + pl.w_absmax * pl.w_absmax)) * (1.0 + 2e-9);
             }
-            unsigned km = 0u;  // chunk bits this lane's pixel keeps
+            unsigned km[kPlanGroups] = {0u, 0u, 0u};  // chunk bits this lane's pixel keeps, per phi group
             for (int c = 0; c < n_chunks; ++c) {
                 const double2 wr = wr_s[c];
                 const double dw = fmax(fmax(wr.x - A, A - wr.y), 0.0) * 0.5;
-                const double lb = fma(dw, dw, lbs_s[wid][c]);
-                km |= (on && !(lb > thr)) ? (1u << (c >> sh)) : 0u;  // NaN / inf thresholds keep everything
+                const double dw2 = dw * dw;
+                const unsigned bit = on ? (1u << (c >> sh)) : 0u;
+#pragma unroll
+                for (int g = 0; g < kPlanGroups; ++g)
+                    if (g < ng) km[g] |= !(dw2 + lbs_s[c * ng + g] > thr) ? bit : 0u;  // NaN / inf thresholds keep everything
             }
             __syncwarp();  // the next tile overwrites the warp's shared-memory tables
-            uni = __reduce_or_sync(0xffffffffu, km);
+            uni = __reduce_or_sync(0xffffffffu, km[0] | km[1] | km[2]);
 #pragma unroll
-            for (int w = 0; w < 4; ++w) wm[w] = __reduce_or_sync(0xffffffffu, km & grp[w]);
+            for (int w = 0; w < 4; ++w)
+#pragma unroll
+                for (int g = 0; g < kPlanGroups; ++g) wm[w][g] = __reduce_or_sync(0xffffffffu, km[g] & grp[w]);
             // the scan's ring looks kStages chunks ahead, at most into the next tile
             while (mask_chunks(uni, sh, n_chunks) < min_items) {
                 unsigned ext = ((uni << 1) | (uni >> 1)) & ~uni & all;
@@ -261,21 +284,26 @@ __global__ void __launch_bounds__(256) k_tile_plan(xs_plan pl, Workspace ws, int
                 uni |= ext & (0u - ext);
             }
         } else if (prune && !on_mask) {
-            wm[0] = wm[1] = wm[2] = wm[3] = 0u;  // nothing to scan in this tile (NaN slab / exhaustive pixels only)
+#pragma unroll
+            for (int w = 0; w < 4; ++w) wm[w][0] = wm[w][1] = wm[w][2] = 0u;  // nothing to scan in this tile (NaN slab / exhaustive pixels only)
             uni = 0u;
             for (int c = 0, k = 0; c < n_chunks && k < min_items; ++c, ++k) uni |= 1u << (c >> sh);
         }
         if (lane == 0) {
             uint4 *dst = reinterpret_cast<uint4 *>(ws.tile_plan + (size_t)t * kPlanWords);
-            dst[0] = make_uint4(uni, wm[0], wm[1], wm[2]);
-            dst[1] = make_uint4(wm[3], 0u, 0u, 0u);
+            dst[0] = make_uint4(uni, wm[0][0], wm[0][1], wm[0][2]);
+            dst[1] = make_uint4(wm[1][0], wm[1][1], wm[1][2], wm[2][0]);
+            dst[2] = make_uint4(wm[2][1], wm[2][2], wm[3][0], wm[3][1]);
+            dst[3] = make_uint4(wm[3][2], 0u, 0u, 0u);
             n_items += (unsigned)mask_chunks(uni, sh, n_chunks);
-            for (int w = 0; w < nw && w < 4; ++w) n_warp_items += (unsigned)mask_chunks(wm[w] & uni, sh, n_chunks);
+            for (int w = 0; w < nw && w < 4; ++w)
+#pragma unroll
+                for (int g = 0; g < kPlanGroups; ++g) n_warp_items += (u64)mask_chunks(wm[w][g] & uni, sh, n_chunks) * gphi[g];
         }
     }
     if (lane == 0) {
         if (n_items) atomicAdd(&ws.counters[5], (u64)n_items);
-        if (n_warp_items) atomicAdd(&ws.counters[6], (u64)n_warp_items);
+        if (n_warp_items) atomicAdd(&ws.counters[6], n_warp_items);
     }
 }
 
@@ -436,8 +464,58 @@ __global__ void __launch_bounds__(NW * 32, MB) k_scan_co(xs_plan pl, Workspace w
         const int c_first = next_chunk(tmask, -1, mask_sh, n_chunks);
         for (int c = c_first; c < n_chunks; c = next_chunk(tmask, c, mask_sh, n_chunks)) {
             mbar_wait(&sm.full[stage], phase);
-            const bool mine_on = (sm.plan[b][1 + warp] >> (c >> mask_sh)) & 1u;  // one of this warp's pixels keeps the chunk
-            if (mine_on && shared) {
+            // phi groups of the chunk that one of this warp's pixels keeps (bit g: the float2 slots j with j * NG / KP == g)
+            constexpr int NG = KP < kPlanGroups ? KP : kPlanGroups;
+            unsigned jm = 0u;
+#pragma unroll
+            for (int gI = 0; gI < NG; ++gI) jm |= ((sm.plan[b][1 + kPlanGroups * warp + gI] >> (c >> mask_sh)) & 1u) << gI;
+            const bool mine_on = jm == (1u << NG) - 1u;  // every group: the fused loops below
+            if (!mine_on && jm && any) {
+                // some groups only: one loop per float2 slot (the same operations per candidate as the fused loops)
+                const u64 *rows = reinterpret_cast<const u64 *>(sm.ring[stage]);
+                const int rows_here = min(kChunkRows, pl.n_wspd_pad - c * kChunkRows);
+#pragma unroll
+                for (int j = 0; j < KP; ++j) {
+                    if (!((jm >> (j * NG / KP)) & 1u)) continue;
+                    if (shared) {
+#pragma unroll 2
+                        for (int r = 0; r < rows_here; ++r) {
+                            const float2 rt = rowtab_s[c * kChunkRows + r];
+                            const u64 nwh = pack2(rt.x, rt.x), w2q = pack2(rt.y, rt.y);
+                            const u64 lam = fadd2(rows[r * (32 * KP) + lane + 32 * j], ncs2);
+                            const u64 Mj = ffma2(lam, lam, w2q);
+#pragma unroll
+                            for (int p = 0; p < P; ++p) {
+                                float j0, j1;
+                                if constexpr (SC) {
+                                    float g0, g1, M0, M1;
+                                    unpack2(g[p][j], g0, g1);
+                                    unpack2(Mj, M0, M1);
+                                    j0 = __fmaf_rn(rt.x, g0, M0);
+                                    j1 = __fmaf_rn(rt.x, g1, M1);
+                                } else
+                                    unpack2(ffma2(nwh, g[p][j], Mj), j0, j1);
+                                m[p] = fmin3(m[p], j0, j1);
+                            }
+                        }
+                    } else {
+#pragma unroll 2
+                        for (int r = 0; r < rows_here; ++r) {
+                            const float2 rt = rowtab_s[c * kChunkRows + r];
+                            const u64 nwh = pack2(rt.x, rt.x), w2q = pack2(rt.y, rt.y);
+                            const u64 Lj = fadd2(rows[r * (32 * KP) + lane + 32 * j], ncs2);
+                            const u64 Mj = ffma2(Lj, Lj, w2q);
+#pragma unroll
+                            for (int p = 0; p < P; ++p) {
+                                const u64 q2 = pack2(nqs[p], nqs[p]);
+                                float j0, j1;
+                                unpack2(ffma2(nwh, g[p][j], ffma2(q2, Lj, Mj)), j0, j1);
+                                m[p] = fmin3(m[p], j0, j1);
+                            }
+                        }
+                    }
+                }
+            } else if (mine_on && shared) {
                 const u64 *rows = reinterpret_cast<const u64 *>(sm.ring[stage]);
                 const int rows_here = min(kChunkRows, pl.n_wspd_pad - c * kChunkRows);
 #pragma unroll 2
@@ -899,7 +977,9 @@ static int launch_shape(const xs_plan *pl, const RasterArgs &ra, const Workspace
         const char *e = getenv("XS_NO_PRUNE");
         no_prune = e ? atoi(e) : 0;
     }
-    XS_LAUNCH(k_tile_plan, sms * 16, 256, 0, st, *pl, ws, TP, NW, kStages, (ra.flags & XS_FLAG_NO_PRUNE) || no_prune ? 0 : 1);
+    const size_t plan_smem = sizeof(double2) * pl->n_chunks + sizeof(double) * 8 * (size_t)pl->n_chunks * pl->n_groups;
+    if (plan_smem > 40 * 1024) XS_CUDA(cudaFuncSetAttribute(k_tile_plan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan_smem));
+    XS_LAUNCH(k_tile_plan, sms * 16, 256, plan_smem, st, *pl, ws, TP, NW, kStages, (ra.flags & XS_FLAG_NO_PRUNE) || no_prune ? 0 : 1);
 
     static int scalar = -1;  // XS_SCAN_SCALAR: development aid (KP 3, P 8 only)
     if (scalar < 0) {
