@@ -134,7 +134,7 @@ class _PinnedPool:
 
 
 _POOL = _PinnedPool()
-_COPY_THREADS = 4
+_COPY_THREADS = int(os.environ.get("XS_COPY_THREADS", 8))
 _COPY_POOL = None
 
 
