@@ -261,14 +261,25 @@ __global__ void __launch_bounds__(256) k_tile_plan(xs_plan pl, Workspace ws, int
                 thr = (U * (1.0 + 1e-6) + 1e-6 * (1.0 + A * A + pl.w_absmax * pl.w_absmax)) * (1.0 + 2e-9);
             }
             unsigned km[kPlanGroups] = {0u, 0u, 0u};  // chunk bits this lane's pixel keeps, per phi group
-            for (int c = 0; c < n_chunks; ++c) {
-                const double2 wr = wr_s[c];
-                const double dw = fmax(fmax(wr.x - A, A - wr.y), 0.0) * 0.5;
-                const double dw2 = dw * dw;
-                const unsigned bit = on ? (1u << (c >> sh)) : 0u;
+            // only the chunks whose sigma0 bound alone does not already exceed the largest threshold of the tile are examined
+            // per pixel (a handful of the slab's chunks): float image of the threshold rounded up, lane <-> chunk
+            const float thr_f = __uint_as_float(__reduce_max_sync(0xffffffffu, on ? __float_as_uint(fabsf(__double2float_ru(thr))) : 0u));
+            for (int c0 = 0; c0 < n_chunks; c0 += 32) {
+                bool cand = false;
+                if (c0 + lane < n_chunks)
+                    for (int g = 0; g < ng; ++g) cand |= !(lbs_s[(c0 + lane) * ng + g] > (double)thr_f);  // NaN / inf thresholds keep everything
+                unsigned todo = __ballot_sync(0xffffffffu, cand);
+                while (todo) {
+                    const int c = c0 + __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    const double2 wr = wr_s[c];
+                    const double dw = fmax(fmax(wr.x - A, A - wr.y), 0.0) * 0.5;
+                    const double dw2 = dw * dw;
+                    const unsigned bit = on ? (1u << (c >> sh)) : 0u;
 #pragma unroll
-                for (int g = 0; g < kPlanGroups; ++g)
-                    if (g < ng) km[g] |= !(dw2 + lbs_s[c * ng + g] > thr) ? bit : 0u;  // NaN / inf thresholds keep everything
+                    for (int g = 0; g < kPlanGroups; ++g)
+                        if (g < ng) km[g] |= !(dw2 + lbs_s[c * ng + g] > thr) ? bit : 0u;
+                }
             }
             __syncwarp();  // the next tile overwrites the warp's shared-memory tables
             uni = __reduce_or_sync(0xffffffffu, km[0] | km[1] | km[2]);
@@ -726,25 +737,38 @@ __global__ void __launch_bounds__(256, MB) k_refine_easy(xs_plan pl, Workspace w
     const int n_chunks = pl.n_chunks, mask_sh = pl.mask_sh;
     unsigned n_settled = 0, n_cells = 0, n_fp64 = 0, n_many = 0;
     for (int64_t e0 = warp * PW; e0 < n_pos; e0 += n_warps * PW) {
+        // The four groups of a warp stay in lockstep from iteration to iteration (a group that `continue`d out of an
+        // iteration used to run ahead for good, and the warp then issued every group's instructions separately): no early
+        // exits, one structured block per case, explicit reconvergence here.
+        __syncwarp();
         const int64_t e = e0 + grp;
-        if (e >= n_pos) continue;
-        if (sub < 2 && e + n_warps * PW < n_pos) {  // the next iteration's records: into L2 while this one computes
+        const bool in_range = e < n_pos;
+        if (in_range && sub < 2 && e + n_warps * PW < n_pos) {  // the next iteration's records: into L2 while this one computes
             const void *nxt = sub == 0 ? (const void *)&ws.pix[e + n_warps * PW] : (const void *)&ws.rec[e + n_warps * PW];
             asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt));
         }
-        const PixRec px = ws.pix[e];
-        const RefRec rc = ws.rec[e];  // loaded together with the pixel (only meaningful for state 1)
-        if (px.state == 0) continue;  // uniform within the group; no warp-wide synchronisation below
-        if (px.state != 1 || rc.cont == 0u) {
-            if (sub == 0) {
-                if (px.state == 2)
-                    write_co(pl, out, pl.first_nan[px.bin], px.neg, px.px);  // J is NaN exactly where L is NaN
-                else  // non-finite inputs, or the scan could not bound its error for this pixel
-                    ws.fallback[atomicAdd(&ws.counters[1], 1ull)] = px.px;
-            }
-            continue;
+        PixRec px;
+        RefRec rc;
+        px.qa = px.qb = px.s = 0.0;
+        px.px = 0u;
+        px.bin = 0;
+        px.state = 0;
+        px.neg = 0;
+        rc.thr = rc.cs = rc.nq = rc.efp = 0.f;
+        rc.cont = rc.mask[0] = rc.mask[1] = rc.mask[2] = 0u;
+        if (in_range) {
+            px = ws.pix[e];
+            rc = ws.rec[e];  // loaded together with the pixel (only meaningful for state 1)
         }
-        if (sub == 0 && __popc(rc.cont) > 2) ++n_many;
+        // padding (state 0) needs nothing; NaN slabs and pixels for the exhaustive kernel are settled by the group's first lane
+        if (px.state != 0 && (px.state != 1 || rc.cont == 0u) && sub == 0) {
+            if (px.state == 2)
+                write_co(pl, out, pl.first_nan[px.bin], px.neg, px.px);  // J is NaN exactly where L is NaN
+            else  // non-finite inputs, or the scan could not bound its error for this pixel
+                ws.fallback[atomicAdd(&ws.counters[1], 1ull)] = px.px;
+        }
+        const bool work = px.state == 1 && rc.cont != 0u;  // uniform within the group
+        if (work && sub == 0 && __popc(rc.cont) > 2) ++n_many;
         const float *cell_img = pl.cell + (size_t)px.bin * pl.n_chunks * kChunkRows * pl.nph_pad;
         const double *slab64 = pl.co_lut + (size_t)px.bin * pl.n_wspd * pl.n_phi;
         // Shared-sigma0 records (nq == 0): the scanned cost left k lambda out and the band is wider by 2 |sigma| Lam.  The
@@ -769,6 +793,88 @@ __global__ void __launch_bounds__(256, MB) k_refine_easy(xs_plan pl, Workspace w
                 bi = flat;
             }
         };
+        // one recorded cell = (scan lane L, chunk c): re-create its FP32 costs, collect the band members.
+        // stage 0: keep the lane's best members; 1: count the members that pass the second filter; 2: evaluate them in FP64
+        auto do_cell = [&](int stage, int L, int c, const float (&gq)[2 * KP]) {
+            if (sub == 0 && stage == 0) ++n_cells;
+            // the cell's kp lines first (independent loads: their latencies overlap), then the costs, branch-free; only a
+            // lane that holds a band member (rare) goes on to the bookkeeping below
+            constexpr int RH = kChunkRows / G;
+            static_assert(G == 8 && RH == 2, "the cell image is laid out for 8 row-lanes with 2 rows each");
+            float2 rtt[RH];
+            float val[RH][2 * KP];
+            const float4 *cp = reinterpret_cast<const float4 *>(cell_img) + (((size_t)c * 32 + L) * KP) * 8 + sub;
+            {
+                float4 q[KP];
+#pragma unroll
+                for (int m = 0; m < KP; ++m) q[m] = cp[m * 8];
+#pragma unroll
+                for (int h = 0; h < RH; ++h) rtt[h] = pl.rowtab[min(c * kChunkRows + sub + G * h, pl.n_wspd_pad - 1)];
+#pragma unroll
+                for (int idx = 0; idx < 4 * KP; ++idx) {
+                    const float4 t = q[idx >> 2];
+                    val[idx / (2 * KP)][idx % (2 * KP)] = (idx & 3) == 0 ? t.x : ((idx & 3) == 1 ? t.y : ((idx & 3) == 2 ? t.z : t.w));
+                }
+            }
+            unsigned hm = 0u;  // band members among this lane's 4 kp candidates of the cell (bit = h * 2 kp + slot)
+#pragma unroll
+            for (int h = 0; h < RH; ++h) {
+                const bool row_ok = c * kChunkRows + sub + G * h < pl.n_wspd;
+#pragma unroll
+                for (int k = 0; k < 2 * KP; ++k) {  // exactly the scan's operations (padding slots give NaN or +inf)
+                    const float lc = __fadd_rn(val[h][k], -rc.cs);
+                    const float mm = __fmaf_rn(lc, lc, rtt[h].y);
+                    const float J = __fmaf_rn(rtt[h].x, gq[k], __fmaf_rn(rc.nq, lc, mm));
+                    hm |= (row_ok && J <= rc.thr) ? (1u << (h * 2 * KP + k)) : 0u;
+                }
+            }
+            // the members (one per cell as a rule, in one lane of the group): values re-read and re-computed with the
+            // same operations rather than selected out of the registers above
+            while (hm) {
+                const int idx = __ffs(hm) - 1;
+                hm &= hm - 1;
+                const int h = idx / (2 * KP), k = idx - h * 2 * KP;
+                const int iw = c * kChunkRows + sub + G * h;
+                const int ip = 2 * (L + 32 * (k >> 1)) + (k & 1);
+                if (ip >= pl.n_phi) continue;
+                const float v = reinterpret_cast<const float *>(cp)[(idx >> 2) * 32 + (idx & 3)];
+                const float2 rt = h ? rtt[RH - 1] : rtt[0];
+                const float gk = g32(px.qa, px.qb, pl.cos_phi[ip], pl.sin_phi[ip]);
+                const float lc = __fadd_rn(v, -rc.cs);
+                const float mm = __fmaf_rn(lc, lc, rt.y);
+                const float J = __fmaf_rn(rt.x, gk, __fmaf_rn(rc.nq, lc, mm));
+                if (!(J <= rc.thr)) continue;
+                const int flat = iw * pl.n_phi + ip;
+                const float jf = two_stage ? __fmaf_rn(rt.x, gk, __fmaf_rn(kfull, lc, mm)) : J;
+                if (stage == 0) {
+                    if (jf < b1) {
+                        b3 = b2;
+                        b2 = b1;
+                        f2 = f1;
+                        b1 = jf;
+                        f1 = flat;
+                    } else if (jf < b2) {
+                        b3 = b2;
+                        b2 = jf;
+                        f2 = flat;
+                    } else
+                        b3 = fminf(b3, jf);
+                } else if (jf <= thr2) {
+                    if (stage == 1) {
+                        ++n_loc;
+                        one_loc = flat;
+                    } else
+                        fp64_feed(flat);
+                }
+            }
+        };
+        auto lane_g = [&](int L, float (&gq)[2 * KP]) {  // g(phi) of the scan lane's phi slots, bit-identical to the scan's
+#pragma unroll
+            for (int sl = 0; sl < 2 * KP; ++sl) {
+                const int ip = 2 * (L + 32 * (sl >> 1)) + (sl & 1);
+                gq[sl] = ip < pl.n_phi ? g32(px.qa, px.qb, pl.cos_phi[ip], pl.sin_phi[ip]) : 0.f;
+            }
+        };
         // walk the recorded cells.  stage 0: collect the band members; 1: count the members that pass the second filter;
         // 2: evaluate them in FP64 (stages 1 and 2 only when a lane holds more than two candidates)
         auto walk = [&](int stage) {
@@ -778,11 +884,7 @@ __global__ void __launch_bounds__(256, MB) k_refine_easy(xs_plan pl, Workspace w
                 const int L = __ffs(lanes) - 1;
                 lanes &= lanes - 1;
                 float gq[2 * KP];
-#pragma unroll
-                for (int sl = 0; sl < 2 * KP; ++sl) {
-                    const int ip = 2 * (L + 32 * (sl >> 1)) + (sl & 1);
-                    gq[sl] = ip < pl.n_phi ? g32(px.qa, px.qb, pl.cos_phi[ip], pl.sin_phi[ip]) : 0.f;
-                }
+                lane_g(L, gq);
                 // the chunks of this lane that came within the margin of its minimum (a bit covers 2^mask_sh chunks)
                 unsigned cm = li == 0 ? rc.mask[0] : (li == 1 ? rc.mask[1] : rc.mask[2]);
                 int c = 0, c_end = 0;
@@ -794,77 +896,7 @@ __global__ void __launch_bounds__(256, MB) k_refine_easy(xs_plan pl, Workspace w
                         c_end = min(c + (1 << mask_sh), n_chunks);
                         cm &= cm - 1;
                     }
-                    if (sub == 0 && stage == 0) ++n_cells;
-                    // the cell's kp lines first (independent loads: their latencies overlap), then the costs, branch-free; only a
-                    // lane that holds a band member (rare) goes on to the bookkeeping below
-                    constexpr int RH = kChunkRows / G;
-                    static_assert(G == 8 && RH == 2, "the cell image is laid out for 8 row-lanes with 2 rows each");
-                    float2 rtt[RH];
-                    float val[RH][2 * KP];
-                    const float4 *cp = reinterpret_cast<const float4 *>(cell_img) + (((size_t)c * 32 + L) * KP) * 8 + sub;
-                    {
-                        float4 q[KP];
-#pragma unroll
-                        for (int m = 0; m < KP; ++m) q[m] = cp[m * 8];
-#pragma unroll
-                        for (int h = 0; h < RH; ++h) rtt[h] = pl.rowtab[min(c * kChunkRows + sub + G * h, pl.n_wspd_pad - 1)];
-#pragma unroll
-                        for (int idx = 0; idx < 4 * KP; ++idx) {
-                            const float4 t = q[idx >> 2];
-                            val[idx / (2 * KP)][idx % (2 * KP)] = (idx & 3) == 0 ? t.x : ((idx & 3) == 1 ? t.y : ((idx & 3) == 2 ? t.z : t.w));
-                        }
-                    }
-                    unsigned hm = 0u;  // band members among this lane's 4 kp candidates of the cell (bit = h * 2 kp + slot)
-#pragma unroll
-                    for (int h = 0; h < RH; ++h) {
-                        const bool row_ok = c * kChunkRows + sub + G * h < pl.n_wspd;
-#pragma unroll
-                        for (int k = 0; k < 2 * KP; ++k) {  // exactly the scan's operations (padding slots give NaN or +inf)
-                            const float lc = __fadd_rn(val[h][k], -rc.cs);
-                            const float mm = __fmaf_rn(lc, lc, rtt[h].y);
-                            const float J = __fmaf_rn(rtt[h].x, gq[k], __fmaf_rn(rc.nq, lc, mm));
-                            hm |= (row_ok && J <= rc.thr) ? (1u << (h * 2 * KP + k)) : 0u;
-                        }
-                    }
-                    // the members (one per cell as a rule, in one lane of the group): values re-read and re-computed with the
-                    // same operations rather than selected out of the registers above
-                    while (hm) {
-                        const int idx = __ffs(hm) - 1;
-                        hm &= hm - 1;
-                        const int h = idx / (2 * KP), k = idx - h * 2 * KP;
-                        const int iw = c * kChunkRows + sub + G * h;
-                        const int ip = 2 * (L + 32 * (k >> 1)) + (k & 1);
-                        if (ip >= pl.n_phi) continue;
-                        const float v = reinterpret_cast<const float *>(cp)[(idx >> 2) * 32 + (idx & 3)];
-                        const float2 rt = h ? rtt[RH - 1] : rtt[0];
-                        const float gk = g32(px.qa, px.qb, pl.cos_phi[ip], pl.sin_phi[ip]);
-                        const float lc = __fadd_rn(v, -rc.cs);
-                        const float mm = __fmaf_rn(lc, lc, rt.y);
-                        const float J = __fmaf_rn(rt.x, gk, __fmaf_rn(rc.nq, lc, mm));
-                        if (!(J <= rc.thr)) continue;
-                        const int flat = iw * pl.n_phi + ip;
-                        const float jf = two_stage ? __fmaf_rn(rt.x, gk, __fmaf_rn(kfull, lc, mm)) : J;
-                        if (stage == 0) {
-                            if (jf < b1) {
-                                b3 = b2;
-                                b2 = b1;
-                                f2 = f1;
-                                b1 = jf;
-                                f1 = flat;
-                            } else if (jf < b2) {
-                                b3 = b2;
-                                b2 = jf;
-                                f2 = flat;
-                            } else
-                                b3 = fminf(b3, jf);
-                        } else if (jf <= thr2) {
-                            if (stage == 1) {
-                                ++n_loc;
-                                one_loc = flat;
-                            } else
-                                fp64_feed(flat);
-                        }
-                    }
+                    do_cell(stage, L, c, gq);
                     ++c;
                 }
             }
@@ -879,6 +911,7 @@ __global__ void __launch_bounds__(256, MB) k_refine_easy(xs_plan pl, Workspace w
             for (int o = G / 2; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(gmask, v, o));
             return v;
         };
+        if (work) {
         walk(0);
         if (two_stage) {
             float jmin = b1;
@@ -924,7 +957,9 @@ __global__ void __launch_bounds__(256, MB) k_refine_easy(xs_plan pl, Workspace w
             } else  // cannot happen if the re-created costs equal the scan's; be safe
                 ws.fallback[atomicAdd(&ws.counters[1], 1ull)] = px.px;
         }
+        }
     }
+    __syncwarp();
     n_settled = __reduce_add_sync(0xffffffffu, n_settled);
     n_cells = __reduce_add_sync(0xffffffffu, n_cells);
     n_fp64 = __reduce_add_sync(0xffffffffu, n_fp64);
@@ -1013,7 +1048,9 @@ static int launch_shape(const xs_plan *pl, const RasterArgs &ra, const Workspace
         const char *e = getenv("XS_REFINE_MB");
         refine_mb = e ? atoi(e) : 3;
     }
-    if (refine_mb == 3)
+    if (refine_mb == 4)
+        XS_LAUNCH((k_refine_easy<KP, 8, 4>), sms * 8, 256, 0, st, *pl, ws, out, TP);
+    else if (refine_mb == 3)
         XS_LAUNCH((k_refine_easy<KP, 8, 3>), sms * 9, 256, 0, st, *pl, ws, out, TP);
     else
         XS_LAUNCH((k_refine_easy<KP, 8, 2>), sms * 8, 256, 0, st, *pl, ws, out, TP);
