@@ -14,6 +14,7 @@
 // are written (6 B/px).  k_grad_finish does the 3x3 post-smoothing, c and the complex square root on the half-size
 // planes (6 B/px read, 8 B/px written).  FP64 CUDA-core math throughout (the reference is FP64).
 #include <math_constants.h>
+#include <stdlib.h>
 
 #include "xs_common.cuh"
 
@@ -144,6 +145,143 @@ __global__ void __launch_bounds__(256) k_grad_reduce(const T *__restrict__ image
     }
 }
 
+// ---- streaming variant (round 2) -----------------------------------------------------------------------------------
+// The same arithmetic as k_grad_reduce, organised as a register sliding window: a CTA owns a strip of 124 image columns
+// (62 threads x 2 adjacent columns + one halo thread on either side) and walks down a segment of lines.  Per line a thread
+//   * loads the 3 x 4 image patch around its two columns (L1-resident after the first of the three visits) and evaluates the
+//     Scharr gradient and the three planes (re, im, |.|) of its square for its two columns -- at the 'symm'-mirrored position
+//     when the line or the column lies outside the image, so the borders need no special pass;
+//   * pushes them into a 5-line window held in registers (5 phases unrolled: the window slots are compile-time indices) and
+//     forms the 5-tap binomial along the line axis;
+//   * exchanges those 6 values with its neighbours through shared memory (double-buffered: one barrier per line), forms
+//     the 5-tap binomial along the sample axis, and every second line emits the NaN-skipping 2 x 2 mean.
+// Shared-memory traffic 72 B per pixel (the tiled kernel: > 300 B, its bound); what binds this one is the FP64 pipe
+// (~55 FP64 instructions per pixel).
+constexpr int kGS_Threads = 64;   // small CTAs: the kernel is a chain of dependent steps per line, many CTAs per SM overlap them
+constexpr int kGS_Core = kGS_Threads - 2;     // threads that produce output columns
+constexpr int kGS_SegRows = 64;               // half-size lines per CTA
+
+template <typename T>
+__global__ void __launch_bounds__(kGS_Threads) k_grad_stream(const T *__restrict__ image, int h, int w, int h2, int w2,
+                                                              double *__restrict__ c_re, double *__restrict__ c_im,
+                                                              double *__restrict__ c_abs) {
+    __shared__ double sv[2][3][2 * kGS_Threads];
+    const int t = threadIdx.x;
+    const int cx = blockIdx.x * kGS_Core + t - 1;       // half-size column of this thread (halo threads: -1 / beyond)
+    const int x0 = 2 * cx;                               // its image columns x0, x0 + 1
+    const int cy0 = blockIdx.y * kGS_SegRows, cy1 = min(cy0 + kGS_SegRows, h2);
+    // effective (mirrored) columns of the two own columns and the reflect-101 neighbours the Scharr kernel reads around them
+    int col[2][3];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const int xe = reflect_symm(x0 + k, w);
+        col[k][0] = reflect101(xe - 1, w);
+        col[k][1] = xe;
+        col[k][2] = reflect101(xe + 1, w);
+    }
+    const int v0 = 2 * cy0 - 2, v1 = 2 * cy1 + 2;  // virtual lines of the squared-gradient planes this segment needs
+    // neither a line of the segment nor one of the warp's columns (nor a Scharr neighbour) is mirrored
+    const bool fast = v0 - 1 >= 0 && v1 <= h - 1 && __all_sync(0xffffffffu, x0 - 1 >= 0 && x0 + 2 < w);
+    const T *pcur = image + (int64_t)max(v0, 0) * w + (x0 - 1);  // fast path: line v, column x0 - 1
+    double win[5][6];   // g planes of the last five virtual lines: [slot][2 * plane + column]
+    double prevP[6];    // pre-smoothed values of the even line of the current pair
+#pragma unroll
+    for (int i = 0; i < 6; ++i) prevP[i] = 0.0;
+    for (int vb = v0; vb < v1; vb += 5) {
+#pragma unroll
+        for (int K = 0; K < 5; ++K) {
+            const int v = vb + K;
+            if (v >= v1) break;  // CTA-uniform
+            // ---- squared gradient at virtual line v (effective line: 'symm' mirror), own two columns ----
+            double Ia[3][3], Ib[3][3];  // image patches around the first / second own column
+            if (fast) {
+                // interior lines (CTA-uniform) and interior columns (warp-uniform): three consecutive lines, four consecutive
+                // columns, immediate offsets from one pointer that moves down a line per step
+                const T *pm = pcur - w, *pp = pcur + w;
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(v + 4 < h ? pcur + 4 * (int64_t)w + 1 : pcur));
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    const T *line = r == 0 ? pm : (r == 1 ? pcur : pp);
+                    Ia[r][0] = (double)__ldg(line);
+                    Ia[r][1] = Ib[r][0] = (double)__ldg(line + 1);
+                    Ia[r][2] = Ib[r][1] = (double)__ldg(line + 2);
+                    Ib[r][2] = (double)__ldg(line + 3);
+                }
+                pcur += w;
+            } else {
+                const int ye = reflect_symm(v, h);
+                const int rows[3] = {reflect101(ye - 1, h), ye, reflect101(ye + 1, h)};
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    const T *line = image + (int64_t)rows[r] * w;
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) {
+                        Ia[r][q] = (double)__ldg(line + col[0][q]);
+                        Ib[r][q] = (double)__ldg(line + col[1][q]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const double (&I)[3][3] = k ? Ib : Ia;
+                // separable Scharr as cv2 evaluates it: difference along one axis, then 10*centre + 3*(sum of neighbours)
+                const double dx0 = I[0][2] - I[0][0], dx1 = I[1][2] - I[1][0], dx2 = I[2][2] - I[2][0];
+                const double dy0 = I[2][0] - I[0][0], dy1 = I[2][1] - I[0][1], dy2 = I[2][2] - I[0][2];
+                const double gr = __dadd_rn(__dmul_rn(10.0, dx1), __dmul_rn(3.0, __dadd_rn(dx0, dx2)));
+                const double gi = __dadd_rn(__dmul_rn(10.0, dy1), __dmul_rn(3.0, __dadd_rn(dy0, dy2)));
+                win[K][0 + k] = __dsub_rn(__dmul_rn(gr, gr), __dmul_rn(gi, gi));
+                win[K][2 + k] = __dadd_rn(__dmul_rn(gr, gi), __dmul_rn(gi, gr));
+                win[K][4 + k] = fma(gr, gr, gi * gi);
+            }
+            if (v < v0 + 4) continue;  // the window is not full yet (CTA-uniform)
+            // ---- 5-tap binomial along the line axis: line Y = v - 2 (slots K-4 .. K modulo 5) ----
+            const int Y = v - 2;
+            const int buf = Y & 1;
+            double V[6];
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+                V[i] = (win[(K + 1) % 5][i] + win[K][i]) * 0.0625 + (win[(K + 2) % 5][i] + win[(K + 4) % 5][i]) * 0.25 + win[(K + 3) % 5][i] * 0.375;
+                sv[buf][i >> 1][2 * t + (i & 1)] = V[i];
+            }
+            __syncthreads();
+            if (t >= 1 && t <= kGS_Core) {
+                // ---- 5-tap binomial along the sample axis + NaN-skipping 2 x 2 mean ----
+                double P[6];
+#pragma unroll
+                for (int pl = 0; pl < 3; ++pl) {
+                    const double *row = &sv[buf][pl][2 * t];
+                    const double m2 = row[-2], m1 = row[-1], p2 = row[2], p3 = row[3];
+                    P[2 * pl] = (m2 + p2) * 0.0625 + (m1 + V[2 * pl + 1]) * 0.25 + V[2 * pl] * 0.375;
+                    P[2 * pl + 1] = (m1 + p3) * 0.0625 + (V[2 * pl] + p2) * 0.25 + V[2 * pl + 1] * 0.375;
+                }
+                if (Y & 1) {
+                    const int cy = Y >> 1;
+                    if (cx < w2 && cy < h2) {
+#pragma unroll
+                        for (int pl = 0; pl < 3; ++pl) {
+                            double sum = 0.0;
+                            int cnt = 0;
+                            const double q[4] = {prevP[2 * pl], prevP[2 * pl + 1], P[2 * pl], P[2 * pl + 1]};
+#pragma unroll
+                            for (int i = 0; i < 4; ++i)
+                                if (!isnan(q[i])) {
+                                    sum += q[i];
+                                    ++cnt;
+                                }
+                            double *dst = pl == 0 ? c_re : (pl == 1 ? c_im : c_abs);
+                            // sum / cnt: exact scalings for 4, 2 and 1 summands
+                            dst[(int64_t)cy * w2 + cx] = cnt == 4 ? sum * 0.25 : (cnt == 2 ? sum * 0.5 : (cnt == 1 ? sum : (cnt == 3 ? sum / 3.0 : CUDART_NAN)));
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) prevP[i] = P[i];
+                }
+            }
+        }
+    }
+}
+
 // numpy's complex square root (npy_csqrt, the FreeBSD msun algorithm) without the overflow rescaling, which the
 // magnitudes of a squared gradient never need.
 __device__ __forceinline__ double2 csqrt_np(double a, double b, double mod) {  // mod = hypot(a, b)
@@ -225,6 +363,22 @@ extern "C" int xs_local_gradients(const void *image, int64_t n_lines, int64_t n_
     }
     double *c_re = reinterpret_cast<double *>(workspace);
     double *c_im = c_re + (size_t)h2 * w2, *c_abs = c_im + (size_t)h2 * w2;
+    static int tiled = -1;  // XS_GRAD_TILED=1: the round-1 tiled kernel (development aid / cross-check)
+    if (tiled < 0) {
+        const char *e = getenv("XS_GRAD_TILED");
+        tiled = e ? atoi(e) : 0;
+    }
+    if (!tiled) {
+        const dim3 grid((unsigned)ceil_div(w2, kGS_Core), (unsigned)ceil_div(h2, kGS_SegRows));
+        if (grid.y > 65535u) {
+            set_error("xs_local_gradients: more than 65535 x 128 lines");
+            return XS_E_UNSUPPORTED;
+        }
+        if (dtype == XS_F64)
+            XS_LAUNCH(k_grad_stream<double>, grid, kGS_Threads, 0, stream, (const double *)image, h, w, h2, w2, c_re, c_im, c_abs);
+        else
+            XS_LAUNCH(k_grad_stream<float>, grid, kGS_Threads, 0, stream, (const float *)image, h, w, h2, w2, c_re, c_im, c_abs);
+    } else {
     const dim3 grid((unsigned)ceil_div(w2, kGT_W), (unsigned)ceil_div(h2, kGT_H));
     if (grid.y > 65535u) {
         set_error("xs_local_gradients: more than 65535 x 16 lines");
@@ -240,6 +394,7 @@ extern "C" int xs_local_gradients(const void *image, int64_t n_lines, int64_t n_
         XS_LAUNCH(k_grad_reduce<double>, grid, 256, smem, stream, (const double *)image, h, w, h2, w2, c_re, c_im, c_abs);
     else
         XS_LAUNCH(k_grad_reduce<float>, grid, 256, smem, stream, (const float *)image, h, w, h2, w2, c_re, c_im, c_abs);
+    }
     const dim3 grid2((unsigned)ceil_div(w2, 256), (unsigned)h2);
     XS_LAUNCH(k_grad_finish, grid2, 256, 0, stream, c_re, c_im, c_abs, h2, w2, (double2 *)g2, g3, c);
     return XS_OK;
