@@ -71,6 +71,19 @@ def kept_chunks(slab, gw, cphi, sphi, ranges, a, b, s, s_mid, dsig, s_rng=None):
         r = min(l, n_w - 1)
         if 0 < l < n_w and abs(col[l - 1] - s_mid) <= abs(col[l] - s_mid):
             r = l - 1
+        if l == n_w:   # sigma0 above the column's last value: the column's largest value may sit at a lower wind speed
+            rm = int(np.argmax(col))
+            if col[rm] > col[r]:
+                r = rm
+                if col[rm] >= s_mid:
+                    a_, b_ = 0, rm
+                    while a_ < b_:
+                        mid = (a_ + b_) >> 1
+                        if col[mid] < s_mid:
+                            a_ = mid + 1
+                        else:
+                            b_ = mid
+                    r = a_
         f = np.float32
         ta = f(0.5) * (f(gw[r] * cphi[ip]) - f(a))
         tz = f(0.5) * (f(gw[r] * sphi[ip]) - f(b))

@@ -183,6 +183,26 @@ __global__ void k_build_chunk_ranges(xs_plan pl) {
         }
     }
 }
+// row of the largest LUT value on every seed phi node of every slab (GMFs saturate: the largest sigma0 is not at the largest
+// wind speed for every direction); the seed of a pixel whose sigma0 lies above the column (k_tile_plan)
+__global__ void k_build_seed_rmax(xs_plan pl) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= pl.n_inc * 64) return;
+    const int bin = i >> 6, ip = (i & 63) * pl.seed_stride;
+    int best = 0;
+    if (ip < pl.n_phi) {
+        const double *slab = pl.co_lut + (int64_t)bin * pl.n_wspd * pl.n_phi;
+        double bv = -CUDART_INF;
+        for (int r = 0; r < pl.n_wspd; ++r) {
+            const double v = slab[(int64_t)r * pl.n_phi + ip];
+            if (v > bv) {
+                bv = v;
+                best = r;
+            }
+        }
+    }
+    pl.seed_rmax[i] = (unsigned short)best;
+}
 // plans without a scan image still need the first-NaN table
 __global__ void k_find_first_nan(xs_plan pl) {
     const int64_t per_slab = (int64_t)pl.n_wspd * pl.n_phi;
@@ -860,6 +880,7 @@ extern "C" void xs_plan_destroy(xs_plan *pl) {
     cudaFree(pl->chunk_hi);
     cudaFree(pl->chunk_wlo);
     cudaFree(pl->chunk_whi);
+    cudaFree(pl->seed_rmax);
     cudaFree(pl->inc_cr_grid);
     cudaFree(pl->wspd_cr_grid);
     cudaFree(pl->wspd_cr_half);
@@ -948,6 +969,8 @@ extern "C" int xs_plan_create(const xs_plan_desc *d, void *stream, xs_plan **out
             if ((rc = xs::check(cudaMalloc(&pl->chunk_hi, sizeof(double) * n_cr), "cudaMalloc")) != XS_OK) return fail(rc);
             if ((rc = xs::check(cudaMalloc(&pl->chunk_wlo, sizeof(double) * (size_t)pl->n_chunks), "cudaMalloc")) != XS_OK) return fail(rc);
             if ((rc = xs::check(cudaMalloc(&pl->chunk_whi, sizeof(double) * (size_t)pl->n_chunks), "cudaMalloc")) != XS_OK) return fail(rc);
+            if ((rc = xs::check(cudaMalloc(&pl->seed_rmax, sizeof(unsigned short) * 64 * (size_t)d->n_inc), "cudaMalloc")) != XS_OK) return fail(rc);
+            pl->seed_stride = (d->n_phi + 63) / 64;
         }
     }
     if (has_cr) {
@@ -1003,6 +1026,7 @@ extern "C" int xs_plan_create(const xs_plan_desc *d, void *stream, xs_plan **out
             XS_LAUNCH(k_build_scan, kNumSMs * 8, 256, 0, st, *pl);
             XS_LAUNCH(k_build_cell, kNumSMs * 8, 256, 0, st, *pl);
             XS_LAUNCH(k_build_rowtab, (int)ceil_div(pl->n_wspd_pad, 256), 256, 0, st, *pl);
+            XS_LAUNCH(k_build_seed_rmax, (int)ceil_div((int64_t)pl->n_inc * 64, 256), 256, 0, st, *pl);
             XS_LAUNCH(k_build_chunk_ranges, (int)ceil_div((int64_t)pl->n_inc * pl->n_chunks * pl->n_groups * 32, 256), 256, 0, st, *pl);
         } else {
             XS_LAUNCH(k_find_first_nan, kNumSMs * 8, 256, 0, st, *pl);

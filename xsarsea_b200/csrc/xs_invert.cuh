@@ -34,6 +34,8 @@ struct xs_plan {
     int n_groups;           // min(kp, 3)
     double *chunk_lo, *chunk_hi;    // [n_inc][n_chunks][n_groups]
     double *chunk_wlo, *chunk_whi;  // [n_chunks]
+    unsigned short *seed_rmax;      // [n_inc][64] row of the largest LUT value on the j-th seed phi node of k_tile_plan (node j * seed_stride)
+    int seed_stride;                // ceil(n_phi / 64)
     int inc_sorted;     // inc_grid strictly ascending (binary search allowed)
     // ---- cross-pol model (n_inc_cr == 0 when absent) ----
     int n_inc_cr, n_wspd_cr;

@@ -135,7 +135,8 @@ __global__ void __launch_bounds__(256) k_tile_plan(xs_plan pl, Workspace ws, int
     const int P = tile_px / nw;
     const int ng = pl.n_groups;
     double *lbs_s = lbs_all + (size_t)wid * n_chunks * ng;
-    const int stride = (pl.n_phi + kSeedMax - 1) / kSeedMax, n_seed = (pl.n_phi + stride - 1) / stride;
+    const int stride = pl.seed_stride, n_seed = (pl.n_phi + stride - 1) / stride;
+    static_assert(kSeedMax == 64, "xs_plan::seed_rmax holds 64 seed nodes per slab");
     const double inv_d = 1.0 / fabs(pl.dsig_co);
     for (int c = threadIdx.x; c < n_chunks; c += blockDim.x) wr_s[c] = make_double2(pl.chunk_wlo[c], pl.chunk_whi[c]);
     __syncthreads();
@@ -218,6 +219,28 @@ __global__ void __launch_bounds__(256) k_tile_plan(xs_plan pl, Workspace ws, int
                 if (lo > 0 && lo < pl.n_wspd && fabs(v_lo - s_mid) <= fabs(v_hi - s_mid)) {
                     r = lo - 1;
                     v = v_lo;
+                }
+                if (lo == pl.n_wspd) {
+                    // sigma0 above the column's last value: GMFs saturate, the column's largest value may sit at a lower wind
+                    // speed -- seed there, or where the rising part of the column crosses sigma0
+                    const int rm = pl.seed_rmax[bin * 64 + j];
+                    const double vm = slab[(size_t)rm * pl.n_phi + ip];
+                    if (vm > v) {
+                        r = rm;
+                        v = vm;
+                        if (vm >= s_mid) {
+                            int a = 0, b = rm;  // first row of [0, rm] whose value reaches s_mid
+                            while (a < b) {
+                                const int mid = (a + b) >> 1;
+                                if (slab[(size_t)mid * pl.n_phi + ip] < s_mid)
+                                    a = mid + 1;
+                                else
+                                    b = mid;
+                            }
+                            r = a;
+                            v = slab[(size_t)a * pl.n_phi + ip];
+                        }
+                    }
                 }
                 const double w = pl.wspd_grid[r];
                 seed_s[wid][j] = make_float4((float)(w * pl.cos_phi[ip]), (float)(w * pl.sin_phi[ip]), (float)(v * inv_d),
