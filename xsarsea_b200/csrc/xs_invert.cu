@@ -2,13 +2,15 @@
 //
 // Pipeline of one xs_invert call (all on the caller's stream, no host synchronisation; every piece of mutable state --
 // workspace, counters, timer -- belongs to the call, so one plan serves concurrent calls):
-//   k_bin_count / k_bin_offsets / k_bin_scatter   counting sort of the co-pol pixels by incidence bin; every bin's segment
-//                  of the list is padded to whole scan tiles
-//   k_list_prepare / k_scan_co / k_refine_easy    the co-pol argmin: FP32 FFMA2 scan + exact refinement (xs_scan.cu)
+//   k_bin_keys / k_bin_offsets / radix sort (xs_sort.cu)   the co-pol pixels ordered by (incidence bin, sigma0); every bin's
+//                  segment of the list is padded to whole scan tiles
+//   k_list_prepare / k_tile_plan / k_scan_co / k_refine_easy    the co-pol argmin: exact pruning of the slab, FP32 FFMA2 scan
+//                  of what is kept, exact refinement (xs_scan.cu)
 //   k_exact        exhaustive FP64 scan (warp per pixel) of the pixels the fast path cannot handle (non-finite
 //                  inputs, magnitudes outside the error bound's range) and of XS_MODE_FP64
 //   k_cross        cross-pol / dual-pol pass (windspeed.py:252-279), merge (:426-428), NaN classes, and the output
-//                  epilogue (complex128, or speed / direction planes: row F2)
+//                  epilogue (complex128, or speed / direction planes: row F2); cross-pol-only calls on strictly increasing LUT
+//                  rows go through k_cross_only first (the argmin as a step function of sigma0)
 #include <stdlib.h>
 #include <string.h>
 

@@ -14,19 +14,25 @@
 // and one FMNMX3 per pixel and candidate pair) and widens the error band by the bound 2 |sigma| Lam of the omitted term;
 // the refinement filters the members of the wider band once more with the full FP32 cost before any FP64 work.
 //
+// Exact pruning.  Most of the slab cannot hold the argmin: k_tile_plan bounds the cost of every (16-row chunk, phi group) cell
+// from below and keeps only the cells whose bound does not exceed the cost of a seed candidate (see the comment there).
+//
 // Kernels, all on the caller's stream, no host synchronisation:
 //   k_list_prepare  one 32-byte PixRec per record position from the sorted pixel indices (bins padded to whole tiles)
+//   k_tile_plan     one warp per run of consecutive tiles: seeds, lower bounds, the 64-byte plan of every tile (the chunks
+//                   the CTA streams; per scan warp and phi group the chunks it computes on)
 //   k_scan_co       persistent CTAs (4 per SM, 4 warps, 128 registers): a tile = 32 record positions of one bin; the tile's
-//                   PixRecs and the bin's slab of the FP32 scan image arrive by bulk-async (TMA) copies -- records
-//                   double-buffered one tile ahead, slab chunks of 16 wspd rows through a 4-stage ring that keeps
-//                   streaming across tile boundaries; there is no producer thread and no CTA barrier: the warp that is
-//                   the last to finish a chunk refills its stage (shared-memory arrival counter), so no warp ever waits
-//                   for another one to release a stage.  Lane l owns the phi pairs {2(l+32j), 2(l+32j)+1}; per lane and
-//                   pixel only the running minimum and a bit mask of the chunks whose minimum came within kBandMargin of it
-//                   are kept.  After the slab: warp-shuffle min, the rigorous error band, and one RefRec per pixel.
+//                   PixRecs, its plan and the planned chunks of the bin's slab of the FP32 scan image arrive by bulk-async
+//                   (TMA) copies -- records double-buffered one tile ahead, chunks of 16 wspd rows through a 4-stage ring
+//                   that keeps streaming across tile boundaries; there is no producer thread and no CTA barrier: the warp
+//                   that is the last to finish a chunk refills its stage (shared-memory arrival counter), so no warp ever
+//                   waits for another one to release a stage.  Lane l owns the phi pairs {2(l+32j), 2(l+32j)+1}; per lane
+//                   and pixel only the running minimum and a bit mask of the chunks whose minimum came within kBandMargin
+//                   of it are kept.  After the tile's chunks: warp minima, the rigorous error band (evaluated once per
+//                   pixel, in the pixel's lane), and one RefRec per pixel.
 //   k_refine_easy   eight lanes per pixel: re-creates the FP32 costs (bit-identical operations) of the recorded (lane,
-//                   chunk) cells; a single band member settles the pixel, several are evaluated in FP64 with the
-//                   reference's operation order, lexicographic (J, index) minimum = numpy's first minimum
+//                   chunk) cells from the cell image; a single band member settles the pixel, several are evaluated in FP64
+//                   with the reference's operation order, lexicographic (J, index) minimum = numpy's first minimum
 #include <stdio.h>
 #include <stdlib.h>
 
