@@ -941,51 +941,51 @@ __global__ void __launch_bounds__(256, MB) k_refine_easy(xs_plan pl, Workspace w
             return v;
         };
         if (work) {
-        walk(0);
-        if (two_stage) {
-            float jmin = b1;
+            walk(0);
+            if (two_stage) {
+                float jmin = b1;
 #pragma unroll
-            for (int o = G / 2; o > 0; o >>= 1) jmin = fminf(jmin, __shfl_xor_sync(gmask, jmin, o));
-            thr2 = jmin + 2.f * rc.efp;
-        }
-        else
-            thr2 = rc.thr;  // exact-k records: the members are the candidates
-        const bool in1 = f1 >= 0 && b1 <= thr2, in2 = f2 >= 0 && b2 <= thr2;
-        const bool overflow = group_max((b3 < CUDART_INF_F && b3 <= thr2) ? 1 : 0) != 0;  // a lane with more than two candidates
-        int n_in, result;
-        if (!overflow) {
-            n_in = group_sum((in1 ? 1 : 0) + (in2 ? 1 : 0));
-            result = group_max(in1 ? f1 : -1);  // the candidate itself when there is exactly one
-            if (n_in > 1) {
-                if (in1) fp64_feed(f1);
-                if (in2) fp64_feed(f2);
+                for (int o = G / 2; o > 0; o >>= 1) jmin = fminf(jmin, __shfl_xor_sync(gmask, jmin, o));
+                thr2 = jmin + 2.f * rc.efp;
             }
-        } else {
-            walk(1);
-            n_in = group_sum(n_loc);
-            result = group_max(one_loc);
-            if (n_in > 1) walk(2);
-        }
-        if (n_in > 1) {  // FP64 with the reference's operation order over the candidates, first minimum wins
-#pragma unroll
-            for (int o = G / 2; o > 0; o >>= 1) {
-                const double oj = __shfl_xor_sync(gmask, bj, o);
-                const int oi = __shfl_xor_sync(gmask, bi, o);
-                if (oj < bj || (oj == bj && oi < bi)) {
-                    bj = oj;
-                    bi = oi;
+            else
+                thr2 = rc.thr;  // exact-k records: the members are the candidates
+            const bool in1 = f1 >= 0 && b1 <= thr2, in2 = f2 >= 0 && b2 <= thr2;
+            const bool overflow = group_max((b3 < CUDART_INF_F && b3 <= thr2) ? 1 : 0) != 0;  // a lane with more than two candidates
+            int n_in, result;
+            if (!overflow) {
+                n_in = group_sum((in1 ? 1 : 0) + (in2 ? 1 : 0));
+                result = group_max(in1 ? f1 : -1);  // the candidate itself when there is exactly one
+                if (n_in > 1) {
+                    if (in1) fp64_feed(f1);
+                    if (in2) fp64_feed(f2);
                 }
+            } else {
+                walk(1);
+                n_in = group_sum(n_loc);
+                result = group_max(one_loc);
+                if (n_in > 1) walk(2);
             }
-            result = bi;
-            if (sub == 0) ++n_fp64;
-        }
-        if (sub == 0) {
-            if (n_in >= 1) {
-                write_co(pl, out, result, px.neg, px.px);
-                ++n_settled;
-            } else  // cannot happen if the re-created costs equal the scan's; be safe
-                ws.fallback[atomicAdd(&ws.counters[1], 1ull)] = px.px;
-        }
+            if (n_in > 1) {  // FP64 with the reference's operation order over the candidates, first minimum wins
+#pragma unroll
+                for (int o = G / 2; o > 0; o >>= 1) {
+                    const double oj = __shfl_xor_sync(gmask, bj, o);
+                    const int oi = __shfl_xor_sync(gmask, bi, o);
+                    if (oj < bj || (oj == bj && oi < bi)) {
+                        bj = oj;
+                        bi = oi;
+                    }
+                }
+                result = bi;
+                if (sub == 0) ++n_fp64;
+            }
+            if (sub == 0) {
+                if (n_in >= 1) {
+                    write_co(pl, out, result, px.neg, px.px);
+                    ++n_settled;
+                } else  // cannot happen if the re-created costs equal the scan's; be safe
+                    ws.fallback[atomicAdd(&ws.counters[1], 1ull)] = px.px;
+            }
         }
     }
     __syncwarp();
