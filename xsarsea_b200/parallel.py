@@ -64,14 +64,26 @@ def _comm_stream(device):
     return _COMM_STREAMS[key]
 
 
+PIECE_RATIO = 0.6   # every sub-block is this fraction of the one before it
+
+
 def piece_edges(lo: int, hi: int, pieces: int):
-    """Row edges of the `pieces` contiguous sub-blocks of [lo, hi) (the remainder goes to the first ones)."""
-    return [lo + row_shard(hi - lo, pieces, k)[0] for k in range(pieces)] + [hi]
+    """Row edges of the `pieces` contiguous sub-blocks of [lo, hi).  The sub-blocks shrink geometrically (PIECE_RATIO): only
+    the transfer of the last one is exposed, so the last one is small, while the first ones stay large enough for the
+    scan to work at its full rate.  Every sub-block of a non-empty range with at least `pieces` rows is non-empty."""
+    n = hi - lo
+    if pieces <= 1 or n <= pieces:
+        return [lo + min(k, n) for k in range(pieces)] + [hi]
+    w = np.array([PIECE_RATIO ** k for k in range(pieces)])
+    cuts = np.floor(np.cumsum(w) / w.sum() * n + 0.5).astype(int)
+    cuts = np.maximum(cuts, np.arange(1, pieces + 1))          # at least one row each
+    cuts = np.minimum(cuts, n - (pieces - 1 - np.arange(pieces)))
+    return [lo] + [lo + int(c) for c in cuts[:-1]] + [hi]
 
 
-def n_pieces(n_lines: int, width: int, world: int, target_px: int = 24 << 20) -> int:
-    """Sub-blocks per rank: as many as keep ~24 Mpx each (enough pixels per incidence bin for the scan's fast mode),
-    at most 4; the same number on every rank."""
+def n_pieces(n_lines: int, width: int, world: int, target_px: int = 16 << 20) -> int:
+    """Sub-blocks per rank: as many as keep ~16 Mpx on average (enough pixels per incidence bin for the scan's fast mode
+    and its pruning), at most 4; the same number on every rank."""
     per_rank = (n_lines // max(world, 1)) * max(width, 1)
     return int(max(1, min(4, per_rank // target_px)))
 
