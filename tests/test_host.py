@@ -391,3 +391,20 @@ def test_cmod7_table_reader_host_side(tmp_path):
             ws.get_model("gmf_cmod7")._raw_lut_host()
     finally:
         Model._available_models.pop("gmf_cmod7", None)
+
+
+def test_piece_edges_shrink_and_cover():
+    """Sub-blocks of a rank's rows (parallel.piece_edges): contiguous, covering, non-increasing in size, every one non-empty
+    when there are enough rows, and the last one small (its transfer is the exposed one)."""
+    from xsarsea_b200 import parallel as P
+
+    for lo, hi, p in ((0, 2087, 3), (100, 8450, 4), (5, 9, 4), (0, 3, 4), (0, 0, 2), (10, 11, 3), (0, 16700, 1)):
+        e = P.piece_edges(lo, hi, p)
+        assert len(e) == p + 1 and e[0] == lo and e[-1] == hi
+        sizes = [b - a for a, b in zip(e, e[1:])]
+        assert all(s >= 0 for s in sizes) and sum(sizes) == hi - lo
+        if hi - lo >= p:
+            assert all(s >= 1 for s in sizes)
+        if hi - lo >= 100 * p:
+            assert all(a >= b for a, b in zip(sizes, sizes[1:])) and (p == 1 or sizes[-1] <= 0.25 * (hi - lo) + 1)
+    assert P.n_pieces(16700, 25000, 8) == 3 and P.n_pieces(16700, 25000, 2) == 4 and P.n_pieces(100, 100, 2) == 1
