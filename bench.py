@@ -783,6 +783,9 @@ def main():
             "config": {"workload": workload_text(args),
                        "l2": "inputs (40 B/px x %.1f Mpx = %.1f GB) exceed L2 (126 MB)" % (n_px / 1e6, 40 * n_px / 1e9),
                        "sharding": "one scene per GPU, no data-path collective (see `strong` for one scene over N GPUs)",
+                       "scan": "shipped call: exact pruning of the LUT slab (cells whose rigorous lower bound exceeds a seed's cost are "
+                               "skipped; results bit-identical to the brute-force scan); `roofline` is quoted on the brute-force launch "
+                               "(XS_FLAG_NO_PRUNE) timed in the same run, `roofline.pruned` describes the shipped launch",
                        "lut_build_s": lut_s},
             "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "e2e": e2e, "strong": strong, "gpu_launches": launches,
             "clocks": clocks, "stats": stats, "aux": aux,
