@@ -160,11 +160,18 @@ def _par_copy(dst, src):
         f.result()
 
 
+MIN_BLOCK_PIXELS = 1 << 22  # a raster is split for overlap only into blocks of at least 4 Mi px
+
+
 def _block_edges(n):
     """Compute blocks of the host path: BLOCK_PIXELS each, with a short first and last one (STAGE_PIXELS) so that the
-    upload that cannot overlap anything (the first) and the download that cannot (the last) are small."""
+    upload that cannot overlap anything (the first) and the download that cannot (the last) are small.  A raster below
+    BLOCK_PIXELS is cut into four blocks (of at least MIN_BLOCK_PIXELS) so that its copies overlap its kernels too."""
     if n <= BLOCK_PIXELS:
-        return [0, n]
+        k = min(4, n // MIN_BLOCK_PIXELS)
+        if k < 2:
+            return [0, n]
+        return [n * i // k for i in range(k)] + [n]
     short = min(STAGE_PIXELS, BLOCK_PIXELS)
     edges = [0, short]
     while n - edges[-1] > BLOCK_PIXELS + short:
