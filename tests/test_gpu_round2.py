@@ -241,6 +241,12 @@ def test_streamed_blocks_pageable_and_pinned_inputs(env, monkeypatch):
         got = ws.invert_from_model(pin(inc), pin(s_co), pin(s_cr), ancillary_wind=pin(anc), model=model, **kw)
         assert all(np.array_equal(a, b, equal_nan=True) for a, b in zip(got, ref))
         sd = ws.invert_to_speed_dir(inc, s_co, s_cr, ancillary_wind=anc, model=model, ground_heading=10.0, **kw)
+        # a raster below one block is cut into four blocks (so that its copies overlap its kernels): same results
+        monkeypatch.setattr(impl, "BLOCK_PIXELS", 1 << 26)
+        monkeypatch.setattr(impl, "MIN_BLOCK_PIXELS", 1500)
+        assert len(impl._block_edges(inc.size)) == 5
+        got = ws.invert_from_model(inc, s_co, s_cr, ancillary_wind=anc, model=model, **kw)
+        assert all(np.array_equal(a, b, equal_nan=True) for a, b in zip(got, ref))
     np.testing.assert_allclose(sd[1][0], np.abs(ref[1]), rtol=1e-13, equal_nan=True)
 
 

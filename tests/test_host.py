@@ -408,3 +408,17 @@ def test_piece_edges_shrink_and_cover():
         if hi - lo >= 100 * p:
             assert all(a >= b for a, b in zip(sizes, sizes[1:])) and (p == 1 or sizes[-1] <= 0.25 * (hi - lo) + 1)
     assert P.n_pieces(16700, 25000, 8) == 3 and P.n_pieces(16700, 25000, 2) == 4 and P.n_pieces(100, 100, 2) == 1
+
+
+def test_block_edges_of_the_host_path():
+    """Compute blocks of `_run_device`: contiguous cover; one block for small rasters, four for a raster below one block,
+    short first / last blocks beyond."""
+    from xsarsea_b200.windspeed import windspeed as impl
+
+    for n in (1, 1000, impl.MIN_BLOCK_PIXELS, 2 * impl.MIN_BLOCK_PIXELS + 5, 50_000_000, impl.BLOCK_PIXELS, impl.BLOCK_PIXELS + 1, 417_500_000):
+        e = impl._block_edges(n)
+        assert e[0] == 0 and e[-1] == n and all(b > a for a, b in zip(e, e[1:]))
+        assert max(b - a for a, b in zip(e, e[1:])) <= impl.BLOCK_PIXELS + impl.STAGE_PIXELS
+    assert len(impl._block_edges(1000)) == 2 and len(impl._block_edges(50_000_000)) == 5
+    big = impl._block_edges(417_500_000)
+    assert big[1] - big[0] == impl.STAGE_PIXELS and big[-1] - big[-2] == impl.STAGE_PIXELS
