@@ -714,7 +714,7 @@ def main():
             # F2 epilogue end to end: float32 speed / direction planes (a quarter of the device->host bytes)
             with warnings.catch_warnings():
                 warnings.simplefilter("ignore")
-                k = min(2 * 672, args.lines)   # two full blocks: the staging buffers of this output format get page-locked here
+                k = min(2800, args.lines)   # more than one compute block (64 Mi px): the full-size staging buffers of this output format get page-locked here
                 windspeed.invert_to_speed_dir(h_inc[:k], h_co[:k], h_cr[:k], ancillary_wind=h_anc[:k], model=model,
                                               ground_heading=190.0, dtype=np.float32)
                 t0 = time.perf_counter()
