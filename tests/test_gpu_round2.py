@@ -414,12 +414,13 @@ def test_chunk_pruning_equals_brute_force(env, scene):
 
 
 def test_chunk_pruning_small_and_ragged_rasters(env):
-    """Sparse bins (tiles whose pixels differ widely in sigma0), a NaN-holding LUT and a coarse LUT with few chunks: pruned
-    == brute force == FP64."""
+    """Sparse bins (tiles whose pixels differ widely in sigma0), far-off and zero sigma0 / ancillary winds, coarse LUTs with
+    few chunks and a long wspd grid (several chunks per mask bit): pruned == brute force == FP64."""
     torch, D, nat, ws, impl = env
     g = torch.Generator(device="cuda").manual_seed(11)
     f64 = dict(device="cuda", dtype=torch.float64)
-    for (n_w, n_p, w_hi) in ((499, 181, 50.0), (70, 37, 35.0), (130, 73, 80.0)):
+    # the last grid has 69 chunks: a bit of the 32-bit chunk masks then covers 4 chunks
+    for (n_w, n_p, w_hi) in ((499, 181, 50.0), (70, 37, 35.0), (130, 73, 80.0), (1100, 91, 60.0)):
         gi, gw, gp = np.linspace(17, 50, 34), np.linspace(0.2, w_hi, n_w), np.linspace(0, 180, n_p)
         co = D.lut_to_db(D.lut_build(nat.GMF_IDS["gmf_cmod5n"], gi, gw, gp))
         plan = D.InversionPlan(co=(co, gi, gw, gp), cr=None)
