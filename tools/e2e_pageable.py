@@ -19,7 +19,8 @@ def run(arrs):
         co, du = windspeed.invert_from_model(arrs[0], arrs[1], arrs[2], ancillary_wind=arrs[3], dsig_cr=0.1, model=model)
         x = float(np.nanmean(np.abs(du[0])))
         return time.perf_counter() - t0
-run([p.numpy() for p in pinned])
+t_first = run([p.numpy() for p in pinned])
+print('first call (plan + LUTs + page-locking the staging buffers) s', round(t_first, 2))
 n = lines * 25000
 for name, arrs in (("pinned", [p.numpy() for p in pinned]), ("pageable", pageable)):
     ts = [run(arrs) for _ in range(3)]

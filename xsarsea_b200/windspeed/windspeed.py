@@ -28,7 +28,7 @@ _PLAN_CACHE: "OrderedDict[tuple, dev.InversionPlan]" = OrderedDict()
 _PLAN_CACHE_MAX = 4
 _PLAN_LOCK = threading.RLock()
 BLOCK_PIXELS = int(os.environ.get("XS_BLOCK_PIXELS", 1 << 26))  # pixels per compute block of the host path (64 Mi px: 2.7 GB of f64 inputs, 2.1 GB of outputs, 5.6 GB of workspace)
-STAGE_PIXELS = 1 << 24  # pixels per pinned staging chunk (16 Mi px: 0.27 GB per complex128 raster)
+STAGE_PIXELS = int(os.environ.get("XS_STAGE_PIXELS", 1 << 24))  # pixels per pinned staging chunk (16 Mi px: 0.27 GB per complex128 raster)
 
 
 def _get_plan(model_co, model_cr, dsig_co, kwargs):
