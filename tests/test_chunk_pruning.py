@@ -182,3 +182,37 @@ def test_non_finite_chunks_give_no_sigma0_bound(slabs):
     J = exact_cost(slab, gw, cphi, sphi, 3.0, 4.0, slab[98, 7], 0.1)
     iw = np.unravel_index(np.argmin(J), J.shape)[0]
     assert keep[iw // CHUNK]
+
+
+def _next_chunk(mask, c, sh, n_chunks):
+    """Transcription of next_chunk (xs_scan.cu): smallest chunk > c whose mask bit (chunk >> sh) is set, or n_chunks."""
+    c1 = c + 1
+    if c1 >= n_chunks:
+        return n_chunks
+    b = c1 >> sh
+    if (mask >> b) & 1:
+        return c1
+    rest = 0 if b >= 31 else ((mask >> (b + 1)) << (b + 1)) & 0xFFFFFFFF
+    if not rest:
+        return n_chunks
+    c2 = ((rest & -rest).bit_length() - 1) << sh
+    return c2 if c2 < n_chunks else n_chunks
+
+
+def test_chunk_iteration_over_a_mask():
+    """The scan walks a tile's plan with next_chunk: it must visit exactly the chunks whose mask bit is set, in ascending
+    order, for every granularity of the mask (1, 2, 4, 8 chunks per bit) and slabs whose last bit is only partly filled."""
+    rng = np.random.default_rng(7)
+    for sh in range(4):
+        for n_chunks in (4, 5, 31, 32, 33, 69, 100, 250):
+            nb = (n_chunks + (1 << sh) - 1) >> sh
+            if nb > 32:
+                continue
+            for _ in range(40):
+                mask = int(rng.integers(0, 1 << nb)) | (1 << int(rng.integers(0, nb)))
+                want = [c for c in range(n_chunks) if (mask >> (c >> sh)) & 1]
+                got, c = [], _next_chunk(mask, -1, sh, n_chunks)
+                while c < n_chunks:
+                    got.append(c)
+                    c = _next_chunk(mask, c, sh, n_chunks)
+                assert got == want, (sh, n_chunks, bin(mask))
